@@ -1,0 +1,71 @@
+"""TEST INFRASTRUCTURE: deterministic synthetic inputs shared by oracle/make_golden.py and tests/.
+
+Inputs are regenerated from numpy RandomState seeds (platform independent), so the committed golden
+fixtures only need to hold the REFERENCE's outputs.  Shapes follow the collate contract
+(data_loaders/tensors.py:33-86): x [B,C,1,T], keyframes [B,ceil(T/30),104], mask [B,1,1,T] bool.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+
+@dataclass(frozen=True)
+class Case:
+    name: str
+    fmt: str
+    L: int
+    H: int
+    B: int
+    T: int
+    S: int                 # audio tokens (without the 2 time tokens)
+    respacing: str = "ddim10"
+    guidance: float = 2.0
+    seed: int = 0
+    wseed: int = 1
+    masked: bool = False   # knock out some keyframes through y["mask"]
+
+
+CASES: Dict[str, Case] = {c.name: c for c in [
+    Case("pose_small", "pose", 2, 8, 2, 60, 198, masked=True),
+    Case("pose_small_h4", "pose", 1, 4, 1, 45, 150, seed=3, wseed=4),
+    Case("face_small", "face", 2, 8, 2, 64, 211, guidance=10.0, seed=5, wseed=6),
+    Case("pose_full", "pose", 6, 8, 1, 600, 1998, seed=7, wseed=8),
+    Case("face_cfg1", "face", 8, 8, 1, 64, 211, guidance=10.0, seed=9, wseed=10),   # BASELINE config 1 geometry
+    Case("face_full", "face", 8, 8, 1, 600, 1998, guidance=10.0, seed=11, wseed=12),
+]}
+
+
+def dims_of(case: Case):
+    from audio2photoreal_b200.weights import model_dims
+    return model_dims(case.fmt, case.L, case.H)
+
+
+def make_inputs(case: Case, n_noise: int = 0) -> Dict[str, torch.Tensor]:
+    rs = np.random.RandomState(1000 + case.seed)
+    C = 104 if case.fmt == "pose" else 256
+    cd = 1024 if case.fmt == "pose" else 2038
+    f32 = lambda a: torch.from_numpy(np.asarray(a, dtype=np.float32))
+    out = {
+        "x": f32(rs.standard_normal((case.B, C, 1, case.T))),
+        "feats": f32(rs.standard_normal((case.B, case.S, cd))),
+        "scale": f32(case.guidance + 1.5 * np.arange(case.B)),
+        "times": torch.from_numpy(rs.randint(0, 1000, size=(case.B,)).astype(np.int64)),
+    }
+    nk = len(range(0, case.T, 30))
+    out["keyframes"] = f32(rs.standard_normal((case.B, nk, 104)))
+    mask = np.ones((case.B, 1, 1, case.T), dtype=bool)
+    if case.masked:
+        mask[0, ..., 30:] = False
+    out["mask"] = torch.from_numpy(mask)
+    if n_noise:
+        out["noise_tape"] = [f32(rs.standard_normal((case.B, C, 1, case.T))) for _ in range(n_noise)]
+    return out
+
+
+def weights_of(case: Case):
+    from audio2photoreal_b200.weights import synthetic_state_dict
+    return synthetic_state_dict(dims_of(case), seed=case.wseed)

@@ -1,0 +1,142 @@
+"""TEST INFRASTRUCTURE: generate tests/golden/*.npz from the RUNNING REFERENCE and pin the oracle.
+
+Run only in the build container (needs /root/reference):   python -m oracle.make_golden
+For each case the unmodified reference (through oracle/ref_harness.py's shims) is executed on CPU fp32;
+its outputs are (1) compared with oracle/a2p_oracle.py -- the script fails if they disagree -- and
+(2) written as the committed fixtures.  The fixtures are the reference's numbers, not the oracle's.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import a2p_oracle as O  # noqa: E402
+from oracle import ref_harness as RH  # noqa: E402
+from oracle.cases import CASES, make_inputs, weights_of, dims_of  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+TABLES = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
+          "posterior_variance", "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2"]
+
+
+def _close(a, b, what, atol=2e-5, rtol=1e-5):
+    """fp32-vs-fp32 noise floor check: tolerances are relative to the output scale max|ref| (CFG with g=10
+    amplifies rounding noise ~13x, so face outputs of O(100) carry O(1e-3) absolute fp32 noise)."""
+    a, b = a.double(), b.double()
+    err = (a - b).abs().max().item()
+    scale = max(1.0, b.abs().max().item())
+    ok = torch.allclose(a, b, atol=atol * scale, rtol=rtol)
+    strict = ((a - b).abs() > 1e-4 + 1e-3 * b.abs()).double().mean().item()
+    print(f"   oracle vs reference [{what}]: max|d|={err:.3e} (|ref|max={b.abs().max().item():.3f}; "
+          f"outside atol1e-4+rtol1e-3: {100 * strict:.3f}%) {'OK' if ok else 'MISMATCH'}")
+    assert ok, what
+
+
+def golden_schedule():
+    ref = RH.import_reference()
+    out = {}
+    for tag, resp in [("full", ""), ("ddim500", "ddim500"), ("ddim100", "ddim100"), ("ddim10", "ddim10"),
+                      ("sec10", "10"), ("sec25_10", "25,10")]:
+        args = RH.make_args("pose", 1, 8, resp)
+        d = ref.model_util.create_gaussian_diffusion(args)
+        o = O.OracleDiffusion(resp)
+        out[f"{tag}/timestep_map"] = np.array(d.timestep_map, dtype=np.int64)
+        assert list(o.timestep_map) == list(d.timestep_map), tag
+        for t in TABLES:
+            out[f"{tag}/{t}"] = np.asarray(getattr(d, t), dtype=np.float64)
+            if hasattr(o, t):
+                assert np.array_equal(getattr(o, t), getattr(d, t)), (tag, t)   # bit-exact
+    np.savez_compressed(os.path.join(GOLD, "schedule.npz"), **out)
+    print("schedule.npz written; oracle tables bit-identical to reference")
+
+
+def _ref_model(case, respacing):
+    sd = weights_of(case)
+    ref, args, model, diffusion = RH.build_reference(case.fmt, case.L, case.H, respacing, sd)
+    theirs = {k for k in model.state_dict() if not k.startswith(("audio_model.", "lip_model."))}
+    assert theirs == set(sd), theirs ^ set(sd)       # checkpoint key contract == reference
+    return ref, model, diffusion, sd
+
+
+def golden_forward(name):
+    case = CASES[name]
+    inp = make_inputs(case)
+    ref, model, _, sd = _ref_model(case, "ddim10")
+    cfg = ref.cfg.ClassifierFreeSampleModel(model)
+    y = {"audio": torch.zeros(case.B, 8, 2), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"],
+         "scale": inp["scale"]}
+    with torch.no_grad(), RH.synthetic_features(model, inp["feats"]):
+        c = model(inp["x"], inp["times"], y, cond_drop_prob=0.0)
+        u = model(inp["x"], inp["times"], y, cond_drop_prob=1.0)
+        g = cfg(inp["x"], inp["times"], y)
+    oc = O.denoiser_forward(sd, case.fmt, case.H, inp["x"], inp["times"], inp["feats"], inp["keyframes"], inp["mask"], 0.0)
+    ou = O.denoiser_forward(sd, case.fmt, case.H, inp["x"], inp["times"], inp["feats"], inp["keyframes"], inp["mask"], 1.0)
+    og = O.cfg_forward(sd, case.fmt, case.H, inp["x"], inp["times"], inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
+    _close(oc, c, name + "/cond"); _close(ou, u, name + "/uncond"); _close(og, g, name + "/cfg", atol=2e-4)
+    np.savez_compressed(os.path.join(GOLD, f"fwd_{name}.npz"), cond=c.numpy(), uncond=u.numpy(), cfg=g.numpy(),
+                        x_sha1=hashlib.sha1(inp["x"].numpy().tobytes()).hexdigest())
+    print(f"fwd_{name}.npz written")
+
+
+def golden_loop(name, respacing, kind, eta=0.0):
+    case = CASES[name]
+    ref, model, diffusion, sd = _ref_model(case, respacing)
+    n = diffusion.num_timesteps
+    inp = make_inputs(case, n_noise=n)
+    cfg = ref.cfg.ClassifierFreeSampleModel(model)
+    y = {"audio": torch.zeros(case.B, 8, 2), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"],
+         "scale": inp["scale"]}
+    shape = tuple(inp["x"].shape)
+    t0 = time.time()
+    with torch.no_grad(), RH.synthetic_features(model, inp["feats"]):
+        if kind == "ddim":
+            tape = list(inp["noise_tape"])
+            old = torch.randn_like
+            torch.randn_like = lambda x, *a, **k: tape.pop(0)     # explicit per-step noise tape (eta>0)
+            try:
+                res = diffusion.ddim_sample_loop(cfg, shape, noise=inp["x"], clip_denoised=False, model_kwargs={"y": y},
+                                                 eta=eta)
+            finally:
+                torch.randn_like = old
+        else:
+            with RH.repaired_p_sample(ref.gd, inp["noise_tape"]):
+                res = diffusion.p_sample_loop(cfg, shape, noise=inp["x"], clip_denoised=False, model_kwargs={"y": y})
+    print(f"   reference {kind} loop {name}/{respacing or 'full'}: {time.time() - t0:.1f}s")
+    od = O.OracleDiffusion(respacing)
+    fn = lambda x, ts: O.cfg_forward(sd, case.fmt, case.H, x, ts, inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
+    if kind == "ddim":
+        ores = od.ddim_sample_loop(fn, inp["x"], eta=eta, noise_tape=inp["noise_tape"])
+    else:
+        ores = od.p_sample_loop(fn, inp["x"], inp["noise_tape"])
+    tag = f"{kind}_{name}_{respacing or 'full'}" + (f"_eta{eta}" if eta else "")
+    _close(ores, res, tag, atol=3e-4, rtol=1e-4)
+    np.savez_compressed(os.path.join(GOLD, f"loop_{tag}.npz"), result=res.numpy())
+    print(f"loop_{tag}.npz written")
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    os.makedirs(GOLD, exist_ok=True)
+    golden_schedule()
+    for n in ["pose_small", "pose_small_h4", "face_small", "pose_full", "face_full"]:
+        golden_forward(n)
+    golden_loop("pose_small", "ddim10", "ddim")
+    golden_loop("pose_small", "ddim10", "ddim", eta=0.5)
+    golden_loop("pose_small", "ddim100", "ddim")
+    golden_loop("pose_small", "10", "ancestral")
+    golden_loop("face_small", "ddim10", "ddim")
+    golden_loop("face_cfg1", "ddim10", "ddim")
+    golden_loop("pose_full", "ddim10", "ddim")
+
+
+if __name__ == "__main__":
+    main()
