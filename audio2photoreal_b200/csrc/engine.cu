@@ -1,0 +1,693 @@
+// a2p_b200 engine: the denoiser handle, conditioning caches, one denoiser evaluation, the fused sampler
+// epilogue and the graph-captured reverse loop, exported through the C-ABI of include/a2p_b200.h.
+//
+// Reference behaviour implemented (paths relative to the reference tree):
+//   model/diffusion.py:338-403                       FiLMTransformer.forward (step-dependent part)
+//   model/modules/transformer_modules.py:190-267     FiLMTransformerDecoderLayer (pre-LN branch)
+//   model/cfg_sampler.py:30-33                       CFG: both branches batched as 2B rows
+//   diffusion/gaussian_diffusion.py:667-718,434-477  DDIM / ancestral update (K3)
+//   diffusion/respace.py:140-145                     timestep_map lookup (host builds the table)
+#include <cuda_runtime.h>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/a2p_b200.h"
+#include "attention_simt.cuh"
+#include "common.cuh"
+#include "elementwise.cuh"
+#include "sgemm.cuh"
+
+using namespace a2p;
+
+namespace {
+
+constexpr int MAXL = 16;
+constexpr int TCN_PAD = 24;  // receptive_field - 1 (model/diffusion.py:153,215)
+const int TCN_DIL[6] = {1, 2, 3, 1, 2, 3};
+
+struct AttnW { const float *in_w, *in_b, *out_w, *out_b; };
+struct LayerW {
+  AttnW sa, ca, c2;
+  const float *l1w, *l1b, *l2w, *l2b;
+  const float *n1w, *n1b, *n2w, *n2b, *n2aw, *n2ab, *n3w, *n3b;
+};
+
+struct CondSet {
+  bool set = false;
+  int Bc = 0, S = 0, S2 = 0;
+  float* base = nullptr;      // kv cache arena
+  const float* hidden = nullptr;  // [Bc, D] copy inside the arena
+};
+
+struct GraphKey {
+  int B, T, kind, n_steps, clip, mask;
+  const void *coeffs, *ts, *scale, *x, *pred, *noise, *ws;
+  const void *kv0, *kv1;
+  bool operator==(const GraphKey& o) const {
+    return B == o.B && T == o.T && kind == o.kind && n_steps == o.n_steps && clip == o.clip && mask == o.mask &&
+           coeffs == o.coeffs && ts == o.ts && scale == o.scale && x == o.x && pred == o.pred && noise == o.noise &&
+           ws == o.ws && kv0 == o.kv0 && kv1 == o.kv1;
+  }
+};
+
+}  // namespace
+
+struct a2p_denoiser {
+  a2p_model_cfg cfg{};
+  int dh = 0, nf = 0;
+  bool bound = false;
+  LayerW lw[MAXL]{};
+  const float *time_w1, *time_b1, *time_w2, *time_b2, *time_w3, *time_b3;
+  const float *normc_w, *normc_b, *inp_w, *inp_b, *fin_w, *fin_b, *fconv_w, *fconv_b;
+  const float* conv_b[6];
+  const float* time_freqs;
+  // derived arena
+  float *film_w = nullptr, *film_b = nullptr, *ttk_w = nullptr, *ttk_b = nullptr, *ttv_w = nullptr, *ttv_b = nullptr;
+  float* conv_w[6]{};
+  float2* rope_tab = nullptr;
+  CondSet cond[2];
+  int64_t launches = 0;
+  int64_t graph_nodes = 0;
+  cudaGraphExec_t gexec = nullptr;
+  GraphKey gkey{};
+  bool gvalid = false;
+};
+
+namespace {
+
+// ---------------------------------------------------------------- arena layouts
+struct PackedLayout {
+  size_t film_w, film_b, ttk_w, ttk_b, ttv_w, ttv_b, conv_w[6], rope, total;
+};
+PackedLayout packed_layout(const a2p_model_cfg& c) {
+  PackedLayout p{};
+  size_t off = 0;
+  auto take = [&](size_t nfloats) { size_t o = off; off = align_up(off + nfloats * 4, 256); return o; };
+  const int nf = c.fmt == A2P_FMT_POSE ? 4 : 3;
+  p.film_w = take((size_t)c.L * nf * 2 * c.D * c.D);
+  p.film_b = take((size_t)c.L * nf * 2 * c.D);
+  p.ttk_w = take((size_t)c.L * c.D * c.D);
+  p.ttk_b = take((size_t)c.L * c.D);
+  p.ttv_w = take((size_t)c.L * c.D * c.D);
+  p.ttv_b = take((size_t)c.L * c.D);
+  if (c.fmt == A2P_FMT_POSE) {
+    const int cm = c.C > 256 ? c.C : 256;
+    const int chans[6][2] = {{cm, c.C}, {c.C, cm}, {c.C, c.C}, {c.C, c.C}, {c.C, c.C}, {c.C, c.C}};
+    for (int i = 0; i < 6; ++i) p.conv_w[i] = take((size_t)chans[i][0] * chans[i][1] * 3);
+  }
+  p.rope = take((size_t)c.max_pos * (c.D / 2) * 2);
+  p.total = off;
+  return p;
+}
+
+struct KvLayout {
+  size_t per_layer, ka, va, k2, v2, hidden, total;  // float offsets
+};
+KvLayout kv_layout(const a2p_model_cfg& c, int Bc, int S, int S2) {
+  KvLayout k{};
+  size_t a = (size_t)Bc * S * c.D, b = (size_t)Bc * S2 * c.D;
+  k.ka = 0; k.va = a; k.k2 = 2 * a; k.v2 = 2 * a + b;
+  k.per_layer = 2 * a + 2 * b;
+  k.hidden = k.per_layer * c.L;
+  k.total = k.hidden + (size_t)Bc * c.D;
+  return k;
+}
+
+struct WsLayout {
+  size_t counter, e, th, mt, ttok, tt, ttr, ktt, vtt, film, xin, x, h, hr, qkv, att, u, out, tcnA, tcnB, tcnC, total;
+};
+WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
+  WsLayout w{};
+  size_t off = 0;
+  auto take = [&](size_t nfloats) { size_t o = off; off = align_up(off + nfloats * 4, 256); return o; };
+  const size_t R = 2 * (size_t)B, D = c.D;
+  const int nf = c.fmt == A2P_FMT_POSE ? 4 : 3;
+  w.counter = take(64);
+  w.e = take(R * D); w.th = take(R * 4 * D); w.mt = take(R * D); w.ttok = take(R * 2 * D);
+  w.tt = take(2 * R * D); w.ttr = take(2 * R * D);
+  w.ktt = take(2 * R * c.L * D); w.vtt = take(2 * R * c.L * D);
+  w.film = take(R * c.L * nf * 2 * D);
+  w.xin = take((size_t)B * T * c.C);
+  w.x = take(R * T * D); w.h = take(R * T * D); w.hr = take(R * T * D);
+  w.qkv = take(R * T * 3 * D); w.att = take(R * T * D); w.u = take(R * T * c.FF);
+  w.out = take(R * T * c.C);
+  if (c.fmt == A2P_FMT_POSE) {
+    const size_t cm = c.C > 256 ? c.C : 256;
+    w.tcnA = take(R * (T + TCN_PAD) * c.C); w.tcnB = take(R * (T + TCN_PAD) * cm); w.tcnC = take(R * (T + TCN_PAD) * c.C);
+  }
+  w.total = off;
+  return w;
+}
+
+// ---------------------------------------------------------------- small kernels local to the engine
+__global__ void rope_only_kernel(const float* __restrict__ x, float* __restrict__ out, const float2* __restrict__ tab,
+                                 int D, int pos_mod, long long rows) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int half = D / 2;
+  if (idx >= rows * half) return;
+  long long r = idx / half;
+  int i = idx - r * half;
+  int pos = r % pos_mod;
+  float2 cs = tab[(long long)pos * half + i];
+  float a = x[r * D + 2 * i], b = x[r * D + 2 * i + 1];
+  out[r * D + 2 * i] = a * cs.x - b * cs.y;
+  out[r * D + 2 * i + 1] = b * cs.x + a * cs.y;
+}
+
+// conv weight [Cout, Cin, 3] -> [Cout, 3*Cin] with k = tap*Cin + ci
+__global__ void permute_conv_w_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * Cin * 3) return;
+  int co = idx / (Cin * 3), rem = idx - co * Cin * 3, tap = rem / Cin, ci = rem - tap * Cin;
+  out[idx] = w[((long long)co * Cin + ci) * 3 + tap];
+}
+
+// dst[r][p][c] = p < pad ? 0 : src[r][p-pad][c]
+__global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict__ dst, int T, int pad, int C4, long long total) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int c = idx % C4;
+  long long rp = idx / C4;
+  int pp = rp % (T + pad);
+  long long r = rp / (T + pad);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (pp >= pad) v = reinterpret_cast<const float4*>(src)[(r * T + (pp - pad)) * C4 + c];
+  reinterpret_cast<float4*>(dst)[idx] = v;
+}
+
+struct Ctx {
+  a2p_denoiser* h;
+  cudaStream_t st;
+};
+
+int gemm(Ctx& c, const float* A, long long lda, int M, const float* W, long long ldw, const float* bias, int N, int K,
+         float* C, long long ldc, int epi = EPI_BIAS, GemmParams* extra = nullptr) {
+  GemmParams p{};
+  if (extra) p = *extra;
+  p.A = A; p.lda = lda; p.W = W; p.ldw = ldw; p.bias = bias; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
+  if (p.taps == 0) { p.taps = 1; p.dil = 0; p.Kc = K; }
+  p.epi = epi;
+  c.h->launches++;
+  return launch_sgemm(p, c.st);
+}
+
+int film_gemm(Ctx& c, const float* A, long long lda, int M, const float* W, const float* bias, int N, int K, float* x,
+              long long ldx, const float* film, long long film_ld, int film_off, int D, int rows_per_sample) {
+  GemmParams e{};
+  e.film = film; e.film_ld = film_ld; e.film_scale_off = film_off; e.film_shift_off = film_off + D;
+  e.rows_per_sample = rows_per_sample;
+  return gemm(c, A, lda, M, W, K, bias, N, K, x, ldx, EPI_FILM_RESID, &e);
+}
+
+const float* find(const std::map<std::string, std::pair<const float*, int64_t>>& m, const std::string& k, int64_t numel,
+                  std::string& err) {
+  auto it = m.find(k);
+  if (it == m.end()) { if (err.empty()) err = "missing weight '" + k + "'"; return nullptr; }
+  if (numel >= 0 && it->second.second != numel) {
+    if (err.empty()) err = "weight '" + k + "' has " + std::to_string(it->second.second) + " elements, expected " + std::to_string(numel);
+    return nullptr;
+  }
+  return it->second.first;
+}
+
+int check_cfg(const a2p_model_cfg* c) {
+  if (!c) A2P_FAIL("null cfg");
+  if (c->fmt != A2P_FMT_POSE && c->fmt != A2P_FMT_FACE) A2P_FAIL("cfg.fmt must be 0 (pose) or 1 (face)");
+  if (c->D != 256 && c->D != 512) A2P_FAIL("cfg.D=%d unsupported (256 or 512)", c->D);
+  if (c->H <= 0 || c->D % c->H) A2P_FAIL("cfg.H=%d does not divide D=%d", c->H, c->D);
+  int dh = c->D / c->H;
+  if (dh != 32 && dh != 64) A2P_FAIL("head dim %d unsupported (32 or 64)", dh);
+  if (c->L <= 0 || c->L > MAXL) A2P_FAIL("cfg.L=%d out of range", c->L);
+  if (c->C % 8 || c->FF % 8) A2P_FAIL("cfg.C/FF must be multiples of 8");
+  if (c->fmt == A2P_FMT_POSE && c->S2 <= 0) A2P_FAIL("pose needs S2 > 0");
+  if (c->fmt == A2P_FMT_FACE && c->S2 != 0) A2P_FAIL("face must have S2 == 0");
+  if (c->split_terms != 0) A2P_FAIL("split_terms=%d: tensor-core arm not built in this version", c->split_terms);
+  if (c->max_pos < 2) A2P_FAIL("cfg.max_pos too small");
+  return 0;
+}
+
+// ---------------------------------------------------------------- one denoiser evaluation
+// xin: [B,T,C] (already transposed).  ts: per-row [B] int64 (counter == nullptr) or the step table.
+int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, const int* counter, int mask, char* wsb,
+                 const float** x0_cond, const float** x0_uncond, long long* x0_sample_stride) {
+  a2p_denoiser* h = c.h;
+  const a2p_model_cfg& cf = h->cfg;
+  const int D = cf.D, L = cf.L, C = cf.C, nf = h->nf, H = cf.H, dh = h->dh;
+  const int nb = (mask == A2P_MASK_BOTH) ? 2 : 1;
+  const int R = nb * B;
+  const int br0 = (mask == A2P_MASK_UNCOND) ? 1 : 0;  // branch of rows [0,B)
+  const CondSet& c0 = h->cond[br0];
+  const CondSet& c1 = h->cond[1];
+  if (!c0.set || (nb == 2 && !c1.set)) A2P_FAIL("conditioning not set for the requested branch(es)");
+  if (nb == 2 && c0.S != c1.S) A2P_FAIL("cond/uncond token counts differ (%d vs %d)", c0.S, c1.S);
+  if ((c0.Bc != 1 && c0.Bc != B) || (nb == 2 && c1.Bc != 1 && c1.Bc != B)) A2P_FAIL("conditioning batch does not match B=%d", B);
+  const int S = c0.S;
+  if (T > cf.max_pos || S + 2 > cf.max_pos) A2P_FAIL("T=%d / S+2=%d exceed cfg.max_pos=%d", T, S + 2, cf.max_pos);
+  const WsLayout w = ws_layout(cf, B, T);
+  auto F = [&](size_t off) { return reinterpret_cast<float*>(wsb + off); };
+  float *e = F(w.e), *th = F(w.th), *mt = F(w.mt), *ttok = F(w.ttok), *tt = F(w.tt), *ttr = F(w.ttr);
+  float *ktt = F(w.ktt), *vtt = F(w.vtt), *film = F(w.film), *x = F(w.x), *hh = F(w.h), *hr = F(w.hr);
+  float *qkv = F(w.qkv), *att = F(w.att), *u = F(w.u), *out = F(w.out);
+  const KvLayout k0 = kv_layout(cf, c0.Bc, S, c0.S2), k1 = kv_layout(cf, c1.Bc, S, c1.S2);
+  if (nb == 2 && c0.S2 != c1.S2) A2P_FAIL("cond/uncond keyframe token counts differ (%d vs %d)", c0.S2, c1.S2);
+  const int S2 = c0.S2;
+  const long long film_ld = (long long)L * nf * 2 * D;
+  cudaStream_t st = c.st;
+
+  // --- time conditioning (model/diffusion.py:384-389, model/utils.py:67-79)
+  time_embed_kernel<<<ceil_div(R * D / 2, 256), 256, 0, st>>>(ts, counter, B, R, D, h->time_freqs, e);
+  h->launches++;
+  A2P_TRY(gemm(c, e, D, R, h->time_w1, D, h->time_b1, 4 * D, D, th, 4 * D, EPI_MISH));
+  {
+    GemmParams ex{};
+    ex.rowvec.base[0] = c0.hidden; ex.rowvec.stride[0] = c0.Bc == 1 ? 0 : D;
+    ex.rowvec.base[1] = c1.hidden; ex.rowvec.stride[1] = c1.Bc == 1 ? 0 : D;
+    ex.rowvec.rows_per_branch = B;
+    A2P_TRY(gemm(c, th, 4 * D, R, h->time_w2, 4 * D, h->time_b2, D, 4 * D, mt, D, EPI_ADDROW_MISH, &ex));
+  }
+  A2P_TRY(gemm(c, th, 4 * D, R, h->time_w3, 4 * D, h->time_b3, 2 * D, 4 * D, ttok, 2 * D));
+  // time tokens -> norm_cond rows at positions S, S+1 (model/diffusion.py:392-393) -> per-layer K/V rows
+  A2P_TRY(launch_ln_rope(D, ttok, D, h->normc_w, h->normc_b, tt, ttr, D, h->rope_tab, 2, S, 2 * R, st));
+  h->launches++;
+  A2P_TRY(gemm(c, ttr, D, 2 * R, h->ttk_w, D, h->ttk_b, L * D, D, ktt, (long long)L * D));
+  A2P_TRY(gemm(c, tt, D, 2 * R, h->ttv_w, D, h->ttv_b, L * D, D, vtt, (long long)L * D));
+  // all FiLM (scale, shift) pairs of all layers in one GEMM (transformer_modules.py:105-119)
+  A2P_TRY(gemm(c, mt, D, R, h->film_w, D, h->film_b, (int)film_ld, D, film, film_ld));
+  // --- input projection (identical for both branches: computed once, duplicated)
+  A2P_TRY(gemm(c, xin, C, B * T, h->inp_w, C, h->inp_b, D, C, x, D));
+  if (nb == 2) {
+    A2P_CUDA(cudaMemcpyAsync(x + (size_t)B * T * D, x, sizeof(float) * (size_t)B * T * D, cudaMemcpyDeviceToDevice, st));
+  }
+  const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+  const long long sT = (long long)T * D;
+  for (int l = 0; l < L; ++l) {
+    const LayerW& lw = h->lw[l];
+    const int fo = l * nf * 2 * D;
+    // ---- self attention: q = k = rot(LN1 x), v = LN1 x  (transformer_modules.py:237-247)
+    A2P_TRY(launch_ln_rope(D, x, D, lw.n1w, lw.n1b, hh, hr, D, h->rope_tab, T, 0, R * T, st));
+    h->launches++;
+    A2P_TRY(gemm(c, hr, D, R * T, lw.sa.in_w, D, lw.sa.in_b, 2 * D, D, qkv, 3 * D));
+    A2P_TRY(gemm(c, hh, D, R * T, lw.sa.in_w + (size_t)2 * D * D, D, lw.sa.in_b + 2 * D, D, D, qkv + 2 * D, 3 * D));
+    {
+      AttnParams a{};
+      a.Q = qkv; a.q_ld = 3 * D; a.q_sample_stride = 3 * sT;
+      a.K.base[0] = qkv + D; a.K.stride[0] = 3 * sT; a.K.base[1] = nullptr; a.K.stride[1] = 0; a.K.rows_per_branch = R;
+      a.V = a.K; a.V.base[0] = qkv + 2 * D;
+      a.kv_ld = 3 * D; a.S_main = T; a.S_extra = 0;
+      a.O = att; a.o_ld = D; a.o_sample_stride = sT; a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
+      A2P_TRY(launch_attn_simt(a, dh, st));
+      h->launches++;
+    }
+    A2P_TRY(film_gemm(c, att, D, R * T, lw.sa.out_w, lw.sa.out_b, D, D, x, D, film, film_ld, fo + 0 * 2 * D, D, T));
+    // ---- cross attention over [audio tokens | 2 time tokens]  (transformer_modules.py:251-262)
+    A2P_TRY(launch_ln_rope(D, x, D, lw.n2w, lw.n2b, nullptr, hr, D, h->rope_tab, T, 0, R * T, st));
+    h->launches++;
+    A2P_TRY(gemm(c, hr, D, R * T, lw.ca.in_w, D, lw.ca.in_b, D, D, qkv, 3 * D));
+    {
+      AttnParams a{};
+      a.Q = qkv; a.q_ld = 3 * D; a.q_sample_stride = 3 * sT;
+      a.K.base[0] = c0.base + k0.per_layer * l + k0.ka; a.K.stride[0] = c0.Bc == 1 ? 0 : (long long)S * D;
+      a.K.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.ka : nullptr; a.K.stride[1] = c1.Bc == 1 ? 0 : (long long)S * D;
+      a.K.rows_per_branch = B;
+      a.V = a.K;
+      a.V.base[0] = c0.base + k0.per_layer * l + k0.va;
+      a.V.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.va : nullptr;
+      a.kv_ld = D; a.S_main = S;
+      a.Kx = ktt + (size_t)l * D; a.Vx = vtt + (size_t)l * D; a.x_ld = (long long)L * D; a.x_sample_stride = 2LL * L * D; a.S_extra = 2;
+      a.O = att; a.o_ld = D; a.o_sample_stride = sT; a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
+      A2P_TRY(launch_attn_simt(a, dh, st));
+      h->launches++;
+    }
+    A2P_TRY(film_gemm(c, att, D, R * T, lw.ca.out_w, lw.ca.out_b, D, D, x, D, film, film_ld, fo + 1 * 2 * D, D, T));
+    // ---- cross attention over keyframe tokens (pose; transformer_modules.py:204-214)
+    if (cf.fmt == A2P_FMT_POSE) {
+      A2P_TRY(launch_ln_rope(D, x, D, lw.n2aw, lw.n2ab, nullptr, hr, D, h->rope_tab, T, 0, R * T, st));
+      h->launches++;
+      A2P_TRY(gemm(c, hr, D, R * T, lw.c2.in_w, D, lw.c2.in_b, D, D, qkv, 3 * D));
+      AttnParams a{};
+      a.Q = qkv; a.q_ld = 3 * D; a.q_sample_stride = 3 * sT;
+      a.K.base[0] = c0.base + k0.per_layer * l + k0.k2; a.K.stride[0] = c0.Bc == 1 ? 0 : (long long)S2 * D;
+      a.K.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.k2 : nullptr; a.K.stride[1] = c1.Bc == 1 ? 0 : (long long)S2 * D;
+      a.K.rows_per_branch = B;
+      a.V = a.K;
+      a.V.base[0] = c0.base + k0.per_layer * l + k0.v2;
+      a.V.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.v2 : nullptr;
+      a.kv_ld = D; a.S_main = S2; a.S_extra = 0;
+      a.O = att; a.o_ld = D; a.o_sample_stride = sT; a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
+      A2P_TRY(launch_attn_simt(a, dh, st));
+      h->launches++;
+      A2P_TRY(film_gemm(c, att, D, R * T, lw.c2.out_w, lw.c2.out_b, D, D, x, D, film, film_ld, fo + 2 * 2 * D, D, T));
+    }
+    // ---- feed forward (transformer_modules.py:265-267)
+    A2P_TRY(launch_ln_rope(D, x, D, lw.n3w, lw.n3b, hh, nullptr, D, h->rope_tab, T, 0, R * T, st));
+    h->launches++;
+    A2P_TRY(gemm(c, hh, D, R * T, lw.l1w, D, lw.l1b, cf.FF, D, u, cf.FF, EPI_GELU));
+    A2P_TRY(film_gemm(c, u, cf.FF, R * T, lw.l2w, lw.l2b, D, cf.FF, x, D, film, film_ld, fo + (nf - 1) * 2 * D, D, T));
+  }
+  // ---- final projection (+ causal TCN for pose; model/diffusion.py:397-402)
+  A2P_TRY(gemm(c, x, D, R * T, h->fin_w, D, h->fin_b, C, D, out, C));
+  if (cf.fmt == A2P_FMT_POSE) {
+    const int cm = C > 256 ? C : 256;
+    const int P = T + TCN_PAD;
+    float *A = F(w.tcnA), *Bf = F(w.tcnB), *Cc = F(w.tcnC);
+    long long total = (long long)R * P * (C / 4);
+    pad_copy_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, A, T, TCN_PAD, C / 4, total);
+    h->launches++;
+    struct Stage { const float* in; int cin; float* outp; int cout; bool skip; };
+    Stage stg[6] = {{A, C, Bf, cm, false}, {Bf, cm, A, C, false}, {A, C, Cc, C, true},
+                    {Cc, C, A, C, true},   {A, C, Cc, C, true},   {Cc, C, A, C, true}};
+    for (int i = 0; i < 6; ++i) {
+      GemmParams ex{};
+      ex.taps = 3; ex.dil = TCN_DIL[i]; ex.Kc = stg[i].cin; ex.slope = 0.2f;
+      ex.skip = stg[i].in; ex.ldskip = stg[i].cin;
+      const bool skip = stg[i].skip && stg[i].cin == stg[i].cout;
+      A2P_TRY(gemm(c, stg[i].in, stg[i].cin, R * P, h->conv_w[i], 3LL * stg[i].cin, h->conv_b[i], stg[i].cout, 3 * stg[i].cin,
+                   stg[i].outp, stg[i].cout, skip ? EPI_LRELU_SKIPAVG : EPI_LRELU, &ex));
+    }
+    A2P_TRY(gemm(c, A, C, R * P, h->fconv_w, C, h->fconv_b, C, C, Cc, C));
+    *x0_sample_stride = (long long)P * C;
+    const float* o0 = Cc + (size_t)TCN_PAD * C;
+    *x0_cond = (mask & A2P_MASK_COND) ? o0 : nullptr;
+    *x0_uncond = (mask == A2P_MASK_BOTH) ? o0 + (size_t)B * P * C : (mask == A2P_MASK_UNCOND ? o0 : nullptr);
+  } else {
+    *x0_sample_stride = (long long)T * C;
+    *x0_cond = (mask & A2P_MASK_COND) ? out : nullptr;
+    *x0_uncond = (mask == A2P_MASK_BOTH) ? out + (size_t)B * T * C : (mask == A2P_MASK_UNCOND ? out : nullptr);
+  }
+  return 0;
+}
+
+int launch_k3(Ctx& c, K3Params p) {
+  dim3 grid(ceil_div(p.T, 32), ceil_div(p.C, 32), p.B), block(32, 8);
+  k3_sampler_kernel<<<grid, block, 0, c.st>>>(p);
+  if (c.h) c.h->launches++;
+  A2P_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int transpose_in(Ctx& c, const float* x, float* xin, int B, int C, int T) {
+  dim3 grid(ceil_div(T, 32), ceil_div(C, 32), B), block(32, 8);
+  bct_to_btc_kernel<<<grid, block, 0, c.st>>>(x, xin, C, T);
+  c.h->launches++;
+  A2P_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================== C-ABI
+extern "C" {
+
+int a2p_abi_version(void) { return A2P_ABI_VERSION; }
+const char* a2p_last_error(void) { return a2p::last_error().c_str(); }
+int a2p_has_tcgen05(void) { return 0; }
+
+int a2p_denoiser_create(a2p_denoiser_t** out, const a2p_model_cfg* cfg) {
+  if (!out) A2P_FAIL("null out");
+  A2P_TRY(check_cfg(cfg));
+  int ndev = 0;
+  A2P_CUDA(cudaGetDeviceCount(&ndev));
+  if (ndev <= 0) A2P_FAIL("no CUDA device: a2p_b200 has no CPU fallback");
+  A2P_TRY(init_attn_simt());
+  a2p_denoiser* h = new a2p_denoiser();
+  h->cfg = *cfg;
+  h->dh = cfg->D / cfg->H;
+  h->nf = cfg->fmt == A2P_FMT_POSE ? 4 : 3;
+  *out = h;
+  return 0;
+}
+
+void a2p_denoiser_destroy(a2p_denoiser_t* h) {
+  if (!h) return;
+  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  delete h;
+}
+
+size_t a2p_packed_weight_bytes(const a2p_model_cfg* cfg) {
+  if (check_cfg(cfg)) return 0;
+  return packed_layout(*cfg).total;
+}
+
+int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int n, void* packed, size_t packed_bytes,
+                              void* stream) {
+  if (!h || !table || !packed) A2P_FAIL("bind_weights: null argument");
+  const a2p_model_cfg& cf = h->cfg;
+  const PackedLayout pl = packed_layout(cf);
+  if (packed_bytes < pl.total) A2P_FAIL("bind_weights: packed arena too small (%zu < %zu)", packed_bytes, pl.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  std::map<std::string, std::pair<const float*, int64_t>> m;
+  for (int i = 0; i < n; ++i) m[table[i].name] = {table[i].ptr, table[i].numel};
+  std::string err;
+  const int64_t D = cf.D, C = cf.C, FF = cf.FF;
+  auto W = [&](const std::string& k, int64_t numel) { return find(m, k, numel, err); };
+  h->time_w1 = W("time_mlp.1.weight", 4 * D * D); h->time_b1 = W("time_mlp.1.bias", 4 * D);
+  h->time_w2 = W("to_time_cond.0.weight", 4 * D * D); h->time_b2 = W("to_time_cond.0.bias", D);
+  h->time_w3 = W("to_time_tokens.0.weight", 8 * D * D); h->time_b3 = W("to_time_tokens.0.bias", 2 * D);
+  h->normc_w = W("norm_cond.weight", D); h->normc_b = W("norm_cond.bias", D);
+  h->inp_w = W("input_projection.weight", D * C); h->inp_b = W("input_projection.bias", D);
+  h->fin_w = W("final_layer.weight", C * D); h->fin_b = W("final_layer.bias", C);
+  h->time_freqs = W("a2p.time_freqs", D / 2);
+  const float* freqs = W("rotary.freqs", D / 2);
+  char* pb = (char*)packed;
+  auto P = [&](size_t off) { return reinterpret_cast<float*>(pb + off); };
+  h->film_w = P(pl.film_w); h->film_b = P(pl.film_b); h->ttk_w = P(pl.ttk_w); h->ttk_b = P(pl.ttk_b);
+  h->ttv_w = P(pl.ttv_w); h->ttv_b = P(pl.ttv_b); h->rope_tab = reinterpret_cast<float2*>(pb + pl.rope);
+  const char* film_names_pose[4] = {"film1", "film2", "film2a", "film3"};
+  const char* film_names_face[3] = {"film1", "film2", "film3"};
+  for (int l = 0; l < cf.L; ++l) {
+    const std::string p = "seqTransDecoder.stack." + std::to_string(l) + ".";
+    LayerW& lw = h->lw[l];
+    auto A = [&](const std::string& name, AttnW& a) {
+      a.in_w = W(p + name + ".in_proj_weight", 3 * D * D); a.in_b = W(p + name + ".in_proj_bias", 3 * D);
+      a.out_w = W(p + name + ".out_proj.weight", D * D); a.out_b = W(p + name + ".out_proj.bias", D);
+    };
+    A("self_attn", lw.sa); A("multihead_attn", lw.ca);
+    if (cf.fmt == A2P_FMT_POSE) {
+      A("multihead_attn2", lw.c2);
+      lw.n2aw = W(p + "norm2a.weight", D); lw.n2ab = W(p + "norm2a.bias", D);
+    }
+    lw.l1w = W(p + "linear1.weight", FF * D); lw.l1b = W(p + "linear1.bias", FF);
+    lw.l2w = W(p + "linear2.weight", D * FF); lw.l2b = W(p + "linear2.bias", D);
+    lw.n1w = W(p + "norm1.weight", D); lw.n1b = W(p + "norm1.bias", D);
+    lw.n2w = W(p + "norm2.weight", D); lw.n2b = W(p + "norm2.bias", D);
+    lw.n3w = W(p + "norm3.weight", D); lw.n3b = W(p + "norm3.bias", D);
+    if (!err.empty()) A2P_FAIL("bind_weights: %s", err.c_str());
+    for (int f = 0; f < h->nf; ++f) {
+      const std::string fn = p + (cf.fmt == A2P_FMT_POSE ? film_names_pose[f] : film_names_face[f]) + ".block.1.";
+      const float* fw = W(fn + "weight", 2 * D * D);
+      const float* fb = W(fn + "bias", 2 * D);
+      if (!err.empty()) A2P_FAIL("bind_weights: %s", err.c_str());
+      A2P_CUDA(cudaMemcpyAsync(h->film_w + ((size_t)l * h->nf + f) * 2 * D * D, fw, sizeof(float) * 2 * D * D, cudaMemcpyDeviceToDevice, st));
+      A2P_CUDA(cudaMemcpyAsync(h->film_b + ((size_t)l * h->nf + f) * 2 * D, fb, sizeof(float) * 2 * D, cudaMemcpyDeviceToDevice, st));
+    }
+    // stacked K / V projections of the cross-attention (rows [D,2D) and [2D,3D) of in_proj) for the time tokens
+    A2P_CUDA(cudaMemcpyAsync(h->ttk_w + (size_t)l * D * D, lw.ca.in_w + D * D, sizeof(float) * D * D, cudaMemcpyDeviceToDevice, st));
+    A2P_CUDA(cudaMemcpyAsync(h->ttk_b + (size_t)l * D, lw.ca.in_b + D, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+    A2P_CUDA(cudaMemcpyAsync(h->ttv_w + (size_t)l * D * D, lw.ca.in_w + 2 * D * D, sizeof(float) * D * D, cudaMemcpyDeviceToDevice, st));
+    A2P_CUDA(cudaMemcpyAsync(h->ttv_b + (size_t)l * D, lw.ca.in_b + 2 * D, sizeof(float) * D, cudaMemcpyDeviceToDevice, st));
+  }
+  if (cf.fmt == A2P_FMT_POSE) {
+    const int64_t cm = C > 256 ? C : 256;
+    const int64_t chans[6][2] = {{cm, C}, {C, cm}, {C, C}, {C, C}, {C, C}, {C, C}};
+    for (int i = 0; i < 6; ++i) {
+      const std::string p = "post_pose_layers." + std::to_string(i) + ".";
+      const float* cw = W(p + "weight", chans[i][0] * chans[i][1] * 3);
+      h->conv_b[i] = W(p + "bias", chans[i][0]);
+      if (!err.empty()) A2P_FAIL("bind_weights: %s", err.c_str());
+      h->conv_w[i] = P(pl.conv_w[i]);
+      int tot = (int)(chans[i][0] * chans[i][1] * 3);
+      permute_conv_w_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(cw, h->conv_w[i], (int)chans[i][0], (int)chans[i][1]);
+    }
+    h->fconv_w = W("final_conv.weight", C * C); h->fconv_b = W("final_conv.bias", C);
+  }
+  if (!err.empty()) A2P_FAIL("bind_weights: %s", err.c_str());
+  rope_table_kernel<<<ceil_div(cf.max_pos * (int)(D / 2), 256), 256, 0, st>>>(freqs, h->rope_tab, cf.max_pos, (int)(D / 2));
+  A2P_CUDA(cudaGetLastError());
+  h->bound = true;
+  h->gvalid = false;
+  return 0;
+}
+
+size_t a2p_kv_cache_bytes(const a2p_model_cfg* cfg, int Bc, int S) {
+  if (check_cfg(cfg) || Bc <= 0 || S <= 0) return 0;
+  return kv_layout(*cfg, Bc, S, cfg->S2).total * sizeof(float);
+}
+
+size_t a2p_conditioning_workspace_bytes(const a2p_model_cfg* cfg, int Bc, int S) {
+  if (check_cfg(cfg) || Bc <= 0 || S <= 0) return 0;
+  const size_t D = cfg->D;
+  return (2 * align_up((size_t)Bc * S * D, 64) + align_up((size_t)Bc * (cfg->S2 > 0 ? cfg->S2 : 1) * D, 64)) * sizeof(float) + 512;
+}
+
+size_t a2p_workspace_bytes(const a2p_model_cfg* cfg, int B, int T) {
+  if (check_cfg(cfg) || B <= 0 || T <= 0) return 0;
+  return ws_layout(*cfg, B, T).total;
+}
+
+int a2p_denoiser_set_conditioning(a2p_denoiser_t* h, int branch, int Bc, int S, int S2, const float* cond_tokens,
+                                  const float* cond_hidden, const float* pose_tokens, void* kv_cache, size_t kv_bytes,
+                                  void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !h->bound) A2P_FAIL("set_conditioning: weights not bound");
+  if (branch != 0 && branch != 1) A2P_FAIL("set_conditioning: branch must be 0 or 1");
+  const a2p_model_cfg& cf = h->cfg;
+  if (Bc <= 0 || S <= 0 || !cond_tokens || !cond_hidden || !kv_cache || !ws) A2P_FAIL("set_conditioning: bad argument");
+  if (cf.fmt == A2P_FMT_POSE && (!pose_tokens || S2 <= 0 || S2 > cf.S2)) A2P_FAIL("set_conditioning: pose model needs pose_tokens with 0 < S2 <= %d", cf.S2);
+  if (cf.fmt == A2P_FMT_FACE) S2 = 0;
+  if (S + 2 > cf.max_pos) A2P_FAIL("set_conditioning: S+2=%d exceeds cfg.max_pos=%d", S + 2, cf.max_pos);
+  const KvLayout kl = kv_layout(cf, Bc, S, S2);
+  if (kv_bytes < kl.total * sizeof(float)) A2P_FAIL("set_conditioning: kv cache too small");
+  const size_t D = cf.D;
+  const size_t need = a2p_conditioning_workspace_bytes(&cf, Bc, S);
+  if (ws_bytes < need) A2P_FAIL("set_conditioning: workspace too small (%zu < %zu)", ws_bytes, need);
+  Ctx c{h, (cudaStream_t)stream};
+  float* base = (float*)kv_cache;
+  float* mem_n = (float*)ws;
+  float* mem_r = mem_n + align_up((size_t)Bc * S * D, 64);
+  float* pose_buf = mem_r + align_up((size_t)Bc * S * D, 64);
+  // norm_cond on the audio rows + rotation at positions 0..S-1 (model/diffusion.py:392-393; transformer_modules.py:253)
+  A2P_TRY(launch_ln_rope(cf.D, cond_tokens, D, h->normc_w, h->normc_b, mem_n, mem_r, D, h->rope_tab, S, 0, Bc * S, c.st));
+  h->launches++;
+  float* pose_r = pose_buf;
+  for (int l = 0; l < cf.L; ++l) {
+    const LayerW& lw = h->lw[l];
+    float* lb = base + kl.per_layer * l;
+    A2P_TRY(gemm(c, mem_r, D, Bc * S, lw.ca.in_w + D * D, D, lw.ca.in_b + D, cf.D, cf.D, lb + kl.ka, D));
+    A2P_TRY(gemm(c, mem_n, D, Bc * S, lw.ca.in_w + 2 * D * D, D, lw.ca.in_b + 2 * D, cf.D, cf.D, lb + kl.va, D));
+  }
+  if (cf.fmt == A2P_FMT_POSE) {
+    long long rows = (long long)Bc * S2;
+    rope_only_kernel<<<(unsigned)((rows * (D / 2) + 255) / 256), 256, 0, c.st>>>(pose_tokens, pose_r, h->rope_tab, cf.D, S2, rows);
+    h->launches++;
+    for (int l = 0; l < cf.L; ++l) {
+      const LayerW& lw = h->lw[l];
+      float* lb = base + kl.per_layer * l;
+      A2P_TRY(gemm(c, pose_r, D, (int)rows, lw.c2.in_w + D * D, D, lw.c2.in_b + D, cf.D, cf.D, lb + kl.k2, D));
+      A2P_TRY(gemm(c, pose_tokens, D, (int)rows, lw.c2.in_w + 2 * D * D, D, lw.c2.in_b + 2 * D, cf.D, cf.D, lb + kl.v2, D));
+    }
+  }
+  A2P_CUDA(cudaMemcpyAsync(base + kl.hidden, cond_hidden, sizeof(float) * Bc * D, cudaMemcpyDeviceToDevice, c.st));
+  CondSet& cs = h->cond[branch];
+  cs.set = true; cs.Bc = Bc; cs.S = S; cs.S2 = S2; cs.base = base; cs.hidden = base + kl.hidden;
+  h->gvalid = false;
+  return 0;
+}
+
+int a2p_denoiser_forward(a2p_denoiser_t* h, int B, int T, const float* x, int x_layout, const int64_t* timesteps,
+                         int branch_mask, float* out_cond, float* out_uncond, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !h->bound) A2P_FAIL("forward: weights not bound");
+  if (B <= 0 || T <= 0 || !x || !timesteps || !ws) A2P_FAIL("forward: bad argument");
+  if (branch_mask < 1 || branch_mask > 3) A2P_FAIL("forward: branch_mask must be 1, 2 or 3");
+  if ((branch_mask & A2P_MASK_COND) && !out_cond) A2P_FAIL("forward: out_cond is null");
+  if ((branch_mask & A2P_MASK_UNCOND) && !out_uncond) A2P_FAIL("forward: out_uncond is null");
+  const a2p_model_cfg& cf = h->cfg;
+  const WsLayout w = ws_layout(cf, B, T);
+  if (ws_bytes < w.total) A2P_FAIL("forward: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  Ctx c{h, (cudaStream_t)stream};
+  char* wsb = (char*)ws;
+  const float* xin = x;
+  if (x_layout == A2P_LAYOUT_BC1T) {
+    float* xt = reinterpret_cast<float*>(wsb + w.xin);
+    A2P_TRY(transpose_in(c, x, xt, B, cf.C, T));
+    xin = xt;
+  }
+  const float *x0c = nullptr, *x0u = nullptr;
+  long long sstride = 0;
+  A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, nullptr, branch_mask, wsb, &x0c, &x0u, &sstride));
+  auto emit = [&](const float* src, float* dst) -> int {
+    long long total = (long long)B * T * (cf.C / 4);
+    copy_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c.st>>>(src, cf.C, sstride, dst, cf.C, (long long)T * cf.C, T, cf.C / 4, B);
+    h->launches++;
+    A2P_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (x0c) A2P_TRY(emit(x0c, out_cond));
+  if (x0u) A2P_TRY(emit(x0u, out_uncond));
+  return 0;
+}
+
+int a2p_sampler_step(int kind, int B, int C, int T, const float* x_t, const float* x0_cond, const float* x0_uncond,
+                     const float* scale, const float* coeffs, const float* noise, int clip_denoised, float* x_prev,
+                     float* pred_xstart, void* stream) {
+  if (kind != A2P_SAMPLER_DDIM && kind != A2P_SAMPLER_ANCESTRAL) A2P_FAIL("sampler_step: unknown kind %d", kind);
+  if (B <= 0 || C <= 0 || T <= 0 || !x_t || !x0_cond || !coeffs || !x_prev || !pred_xstart) A2P_FAIL("sampler_step: bad argument");
+  if (x0_uncond && !scale) A2P_FAIL("sampler_step: guidance needs scale");
+  Ctx c{nullptr, (cudaStream_t)stream};
+  K3Params p{};
+  p.x_t = x_t; p.x0c = x0_cond; p.x0u = x0_uncond; p.scale = scale; p.coeffs = coeffs; p.step_counter = nullptr;
+  p.noise = noise; p.noise_step_stride = 0; p.n_steps = 1; p.x_prev = x_prev; p.pred = pred_xstart;
+  p.B = B; p.C = C; p.T = T; p.kind = kind; p.clip = clip_denoised; p.x0_sample_stride = (long long)T * C;
+  return launch_k3(c, p);
+}
+
+int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, const float* coeffs, const int64_t* timesteps,
+                    const float* scale, float* x, float* pred_xstart, const float* noise_tape, int clip_denoised,
+                    int branch_mask, int use_graph, void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !h->bound) A2P_FAIL("sample_loop: weights not bound");
+  if (kind != A2P_SAMPLER_DDIM && kind != A2P_SAMPLER_ANCESTRAL) A2P_FAIL("sample_loop: unknown kind %d", kind);
+  if (B <= 0 || T <= 0 || n_steps <= 0 || !coeffs || !timesteps || !x || !pred_xstart || !ws) A2P_FAIL("sample_loop: bad argument");
+  if (branch_mask != A2P_MASK_BOTH && branch_mask != A2P_MASK_COND) A2P_FAIL("sample_loop: branch_mask must be BOTH or COND");
+  if (branch_mask == A2P_MASK_BOTH && !scale) A2P_FAIL("sample_loop: CFG needs scale");
+  if (kind == A2P_SAMPLER_ANCESTRAL && !noise_tape) A2P_FAIL("sample_loop: ancestral sampling needs a noise tape");
+  const a2p_model_cfg& cf = h->cfg;
+  const WsLayout w = ws_layout(cf, B, T);
+  if (ws_bytes < w.total) A2P_FAIL("sample_loop: workspace too small (%zu < %zu)", ws_bytes, w.total);
+  Ctx c{h, (cudaStream_t)stream};
+  char* wsb = (char*)ws;
+  int* counter = reinterpret_cast<int*>(wsb + w.counter);
+  float* xin = reinterpret_cast<float*>(wsb + w.xin);
+
+  auto step_body = [&]() -> int {
+    A2P_TRY(transpose_in(c, x, xin, B, cf.C, T));
+    const float *x0c = nullptr, *x0u = nullptr;
+    long long sstride = 0;
+    A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, counter, branch_mask, wsb, &x0c, &x0u, &sstride));
+    K3Params p{};
+    p.x_t = x; p.x0c = x0c; p.x0u = x0u; p.scale = scale; p.coeffs = coeffs; p.step_counter = counter;
+    p.noise = noise_tape; p.noise_step_stride = (long long)B * cf.C * T; p.n_steps = n_steps;
+    p.x_prev = x; p.pred = pred_xstart; p.B = B; p.C = cf.C; p.T = T; p.kind = kind; p.clip = clip_denoised;
+    p.x0_sample_stride = sstride;
+    A2P_TRY(launch_k3(c, p));
+    step_dec_kernel<<<1, 1, 0, c.st>>>(counter);
+    h->launches++;
+    A2P_CUDA(cudaGetLastError());
+    return 0;
+  };
+
+  step_set_kernel<<<1, 1, 0, c.st>>>(counter, n_steps - 1);
+  h->launches++;
+  if (!use_graph) {
+    for (int i = 0; i < n_steps; ++i) A2P_TRY(step_body());
+    return 0;
+  }
+  GraphKey key{B, T, kind, n_steps, clip_denoised, branch_mask, coeffs, timesteps, scale, x, pred_xstart, noise_tape, ws,
+               h->cond[0].base, h->cond[1].base};
+  if (!h->gvalid || !(h->gkey == key)) {
+    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    h->gvalid = false;
+    cudaGraph_t graph = nullptr;
+    int64_t before = h->launches;
+    A2P_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeRelaxed));
+    int rc = step_body();
+    cudaError_t ce = cudaStreamEndCapture(c.st, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (ce != cudaSuccess) A2P_FAIL("graph capture failed: %s", cudaGetErrorString(ce));
+    h->launches = before;  // captured launches are counted per replay below
+    h->graph_nodes = 0;
+    size_t nn = 0;
+    cudaGraphGetNodes(graph, nullptr, &nn);
+    h->graph_nodes = (int64_t)nn;
+    ce = cudaGraphInstantiate(&h->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) A2P_FAIL("graph instantiate failed: %s", cudaGetErrorString(ce));
+    h->gkey = key;
+    h->gvalid = true;
+  }
+  for (int i = 0; i < n_steps; ++i) A2P_CUDA(cudaGraphLaunch(h->gexec, c.st));
+  h->launches += h->graph_nodes * n_steps;
+  return 0;
+}
+
+int64_t a2p_launch_count(const a2p_denoiser_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,85 @@
+"""Host-side contract: C-ABI exports, checkpoint keys, error behaviour without a GPU, sharding helpers."""
+import os
+import re
+from argparse import Namespace
+
+import pytest
+import torch
+
+from audio2photoreal_b200 import _lib
+from audio2photoreal_b200.api import create_model_and_diffusion, load_model
+from audio2photoreal_b200.dist import shard_range, shard_y
+from audio2photoreal_b200.weights import denoiser_param_spec, model_dims, synthetic_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(fmt, layers=2, heads=8, resp="ddim10"):
+    return Namespace(data_format=fmt, add_frame_cond=1 if fmt == "pose" else None, max_seq_length=600, layers=layers,
+                     heads=heads, not_rotary=False, unconstrained=False, device="cuda", timestep_respacing=resp,
+                     noise_schedule="cosine", sigma_small=True, lambda_vel=0.0, model_path="x", resume_trans=None)
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "a2p_b200.h")).read()
+    declared = set(re.findall(r"\b(a2p_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.load()                      # dlopen works without a GPU; no compute is called here
+    for s in declared:
+        assert hasattr(lib, s), s
+    assert lib.a2p_abi_version() == 1
+
+
+def test_create_fails_loudly_without_gpu_or_bad_cfg():
+    import ctypes as C
+    lib = _lib.load()
+    h = C.c_void_p()
+    bad = _lib.ModelCfg(fmt=0, C=104, D=300, L=6, H=8, FF=1024, S2=20, max_pos=2000, split_terms=0, reserved=0)
+    assert lib.a2p_denoiser_create(C.byref(h), C.byref(bad)) != 0
+    assert b"D=300" in lib.a2p_last_error()
+    if not torch.cuda.is_available():
+        ok = _lib.ModelCfg(fmt=0, C=104, D=256, L=6, H=8, FF=1024, S2=20, max_pos=2000, split_terms=0, reserved=0)
+        assert lib.a2p_denoiser_create(C.byref(h), C.byref(ok)) != 0     # no device -> error, never a CPU fallback
+
+
+def test_checkpoint_contract_pose_face():
+    d = model_dims("pose", 6, 8)
+    assert len(denoiser_param_spec(d)) == 241   # = reference state_dict minus frozen audio_model.* (make_golden.py asserts set equality)
+    for fmt in ("pose", "face"):
+        model, _ = create_model_and_diffusion(_args(fmt), "test")
+        keys = set(model.state_dict().keys())
+        assert keys == {n for n, _, _ in denoiser_param_spec(model.dims)}
+        sd = synthetic_state_dict(model.dims, seed=3)
+        sd["audio_model.feature_extractor.conv_layers.0.0.weight"] = torch.zeros(512, 1, 10)   # frozen fairseq entry
+        load_model(model, sd)
+        assert torch.equal(model.state_dict()["final_layer.weight"], sd["final_layer.weight"])
+        with pytest.raises(AssertionError):
+            load_model(model, {**sd, "bogus.weight": torch.zeros(1)})
+
+
+def test_no_cpu_fallback_in_product_path():
+    model, diff = create_model_and_diffusion(_args("pose"), "test")
+    x = torch.zeros(1, 104, 1, 30)
+    with pytest.raises(_lib.A2PError):
+        model(x, torch.zeros(1, dtype=torch.long), {"audio_embed": torch.zeros(1, 98, 1024)})
+    with pytest.raises(_lib.A2PError):
+        diff.ddim_sample_loop(model, (1, 104, 1, 30), model_kwargs={"y": {}})
+    with pytest.raises(NotImplementedError):
+        create_model_and_diffusion(Namespace(**{**vars(_args("pose")), "not_rotary": True}), "test")
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "audio2photoreal_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", ""), os.path.join(dirpath, f)
+
+
+def test_shard_helpers():
+    assert [shard_range(10, 4, r) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert [shard_range(2, 4, r) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    y = {"audio_embed": torch.arange(8).view(8, 1), "scale": torch.ones(8), "name": "x"}
+    s = shard_y(y, 2, 5, 8)
+    assert s["audio_embed"].flatten().tolist() == [2, 3, 4] and s["scale"].shape == (3,) and s["name"] == "x"

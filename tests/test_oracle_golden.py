@@ -1,0 +1,54 @@
+"""The oracle (oracle/a2p_oracle.py) against the REFERENCE's outputs committed under tests/golden/.
+CPU only; sized to finish in about a minute."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import a2p_oracle as O
+from oracle.cases import CASES, make_inputs, weights_of
+
+
+def _check(got, ref, atol=2e-5, rtol=1e-5):
+    ref = torch.as_tensor(ref).double()
+    scale = max(1.0, ref.abs().max().item())     # fp32-vs-fp32 noise floor scales with the output magnitude
+    assert torch.allclose(got.double(), ref, atol=atol * scale, rtol=rtol), (got.double() - ref).abs().max().item()
+
+
+@pytest.mark.parametrize("name", ["pose_small", "pose_small_h4", "face_small"])
+def test_forward_matches_reference(golden_dir, name):
+    case, g = CASES[name], np.load(os.path.join(golden_dir, f"fwd_{name}.npz"))
+    inp, sd = make_inputs(case), weights_of(case)
+    a = (sd, case.fmt, case.H, inp["x"], inp["times"], inp["feats"], inp["keyframes"], inp["mask"])
+    _check(O.denoiser_forward(*a, 0.0), g["cond"])
+    _check(O.denoiser_forward(*a, 1.0), g["uncond"])
+    _check(O.cfg_forward(*a, inp["scale"]), g["cfg"], atol=2e-4)
+
+
+def test_forward_full_size_pose(golden_dir):
+    case, g = CASES["pose_full"], np.load(os.path.join(golden_dir, "fwd_pose_full.npz"))
+    inp, sd = make_inputs(case), weights_of(case)
+    _check(O.denoiser_forward(sd, case.fmt, case.H, inp["x"], inp["times"], inp["feats"], inp["keyframes"], inp["mask"], 0.0),
+           g["cond"])
+
+
+@pytest.mark.parametrize("name,resp,kind,eta", [("pose_small", "ddim10", "ddim", 0.0), ("pose_small", "ddim10", "ddim", 0.5),
+                                                ("pose_small", "10", "ancestral", 0.0), ("face_small", "ddim10", "ddim", 0.0)])
+def test_loops_match_reference(golden_dir, name, resp, kind, eta):
+    case = CASES[name]
+    od = O.OracleDiffusion(resp)
+    inp, sd = make_inputs(case, n_noise=od.num_timesteps), weights_of(case)
+    fn = lambda x, ts: O.cfg_forward(sd, case.fmt, case.H, x, ts, inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
+    tag = f"{kind}_{name}_{resp}" + (f"_eta{eta}" if eta else "")
+    ref = np.load(os.path.join(golden_dir, f"loop_{tag}.npz"))["result"]
+    got = od.ddim_sample_loop(fn, inp["x"], eta=eta, noise_tape=inp["noise_tape"]) if kind == "ddim" else \
+        od.p_sample_loop(fn, inp["x"], inp["noise_tape"])
+    _check(got, ref, atol=3e-4, rtol=1e-4)
+
+
+def test_oracle_fp64_agrees_with_fp32():
+    case = CASES["pose_small"]
+    inp, sd = make_inputs(case), weights_of(case)
+    a = (sd, case.fmt, case.H, inp["x"], inp["times"], inp["feats"], inp["keyframes"], inp["mask"], 0.0)
+    _check(O.denoiser_forward(*a, dtype=torch.float64).float(), O.denoiser_forward(*a).numpy(), atol=2e-5)
