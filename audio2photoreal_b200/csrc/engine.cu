@@ -176,9 +176,25 @@ __global__ void pad_copy_kernel(const float* __restrict__ src, float* __restrict
   reinterpret_cast<float4*>(dst)[idx] = v;
 }
 
+// optional per-category CUDA-event profiler (bench.py's live roofline measurement; never used inside a capture)
+enum Cat : int { CAT_COND = 0, CAT_LN, CAT_PROJ, CAT_ATT_SELF, CAT_ATT_CROSS, CAT_ATT_CROSS2, CAT_FFN, CAT_IO_TCN, CAT_MISC, CAT_N };
+struct Prof {
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> cat;
+};
 struct Ctx {
   a2p_denoiser* h;
   cudaStream_t st;
+  Prof* prof = nullptr;
+  int cat = CAT_MISC;
+  void begin() {
+    if (!prof) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); prof->ev.push_back(e); prof->cat.push_back(cat);
+  }
+  void end() {
+    if (!prof) return;
+    cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); prof->ev.push_back(e);
+  }
 };
 
 int gemm(Ctx& c, const float* A, long long lda, int M, const float* W, long long ldw, const float* bias, int N, int K,
@@ -189,7 +205,10 @@ int gemm(Ctx& c, const float* A, long long lda, int M, const float* W, long long
   if (p.taps == 0) { p.taps = 1; p.dil = 0; p.Kc = K; }
   p.epi = epi;
   c.h->launches++;
-  return launch_sgemm(p, c.st);
+  c.begin();
+  int rc = launch_sgemm(p, c.st);
+  c.end();
+  return rc;
 }
 
 int film_gemm(Ctx& c, const float* A, long long lda, int M, const float* W, const float* bias, int N, int K, float* x,
@@ -256,6 +275,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   cudaStream_t st = c.st;
 
   // --- time conditioning (model/diffusion.py:384-389, model/utils.py:67-79)
+  c.cat = CAT_COND;
   time_embed_kernel<<<ceil_div(R * D / 2, 256), 256, 0, st>>>(ts, counter, B, R, D, h->time_freqs, e);
   h->launches++;
   A2P_TRY(gemm(c, e, D, R, h->time_w1, D, h->time_b1, 4 * D, D, th, 4 * D, EPI_MISH));
@@ -268,13 +288,14 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   }
   A2P_TRY(gemm(c, th, 4 * D, R, h->time_w3, 4 * D, h->time_b3, 2 * D, 4 * D, ttok, 2 * D));
   // time tokens -> norm_cond rows at positions S, S+1 (model/diffusion.py:392-393) -> per-layer K/V rows
-  A2P_TRY(launch_ln_rope(D, ttok, D, h->normc_w, h->normc_b, tt, ttr, D, h->rope_tab, 2, S, 2 * R, st));
+  { int _c = c.cat; c.cat = CAT_LN; c.begin(); A2P_TRY(launch_ln_rope(D, ttok, D, h->normc_w, h->normc_b, tt, ttr, D, h->rope_tab, 2, S, 2 * R, st)); c.end(); c.cat = _c; }
   h->launches++;
   A2P_TRY(gemm(c, ttr, D, 2 * R, h->ttk_w, D, h->ttk_b, L * D, D, ktt, (long long)L * D));
   A2P_TRY(gemm(c, tt, D, 2 * R, h->ttv_w, D, h->ttv_b, L * D, D, vtt, (long long)L * D));
   // all FiLM (scale, shift) pairs of all layers in one GEMM (transformer_modules.py:105-119)
   A2P_TRY(gemm(c, mt, D, R, h->film_w, D, h->film_b, (int)film_ld, D, film, film_ld));
   // --- input projection (identical for both branches: computed once, duplicated)
+  c.cat = CAT_IO_TCN;
   A2P_TRY(gemm(c, xin, C, B * T, h->inp_w, C, h->inp_b, D, C, x, D));
   if (nb == 2) {
     A2P_CUDA(cudaMemcpyAsync(x + (size_t)B * T * D, x, sizeof(float) * (size_t)B * T * D, cudaMemcpyDeviceToDevice, st));
@@ -285,7 +306,8 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     const LayerW& lw = h->lw[l];
     const int fo = l * nf * 2 * D;
     // ---- self attention: q = k = rot(LN1 x), v = LN1 x  (transformer_modules.py:237-247)
-    A2P_TRY(launch_ln_rope(D, x, D, lw.n1w, lw.n1b, hh, hr, D, h->rope_tab, T, 0, R * T, st));
+    c.cat = CAT_PROJ;
+    { int _c = c.cat; c.cat = CAT_LN; c.begin(); A2P_TRY(launch_ln_rope(D, x, D, lw.n1w, lw.n1b, hh, hr, D, h->rope_tab, T, 0, R * T, st)); c.end(); c.cat = _c; }
     h->launches++;
     A2P_TRY(gemm(c, hr, D, R * T, lw.sa.in_w, D, lw.sa.in_b, 2 * D, D, qkv, 3 * D));
     A2P_TRY(gemm(c, hh, D, R * T, lw.sa.in_w + (size_t)2 * D * D, D, lw.sa.in_b + 2 * D, D, D, qkv + 2 * D, 3 * D));
@@ -296,12 +318,14 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       a.V = a.K; a.V.base[0] = qkv + 2 * D;
       a.kv_ld = 3 * D; a.S_main = T; a.S_extra = 0;
       a.O = att; a.o_ld = D; a.o_sample_stride = sT; a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
-      A2P_TRY(launch_attn_simt(a, dh, st));
+      c.cat = CAT_ATT_SELF;
+      c.begin(); A2P_TRY(launch_attn_simt(a, dh, st)); c.end();
+      c.cat = CAT_PROJ;
       h->launches++;
     }
     A2P_TRY(film_gemm(c, att, D, R * T, lw.sa.out_w, lw.sa.out_b, D, D, x, D, film, film_ld, fo + 0 * 2 * D, D, T));
     // ---- cross attention over [audio tokens | 2 time tokens]  (transformer_modules.py:251-262)
-    A2P_TRY(launch_ln_rope(D, x, D, lw.n2w, lw.n2b, nullptr, hr, D, h->rope_tab, T, 0, R * T, st));
+    { int _c = c.cat; c.cat = CAT_LN; c.begin(); A2P_TRY(launch_ln_rope(D, x, D, lw.n2w, lw.n2b, nullptr, hr, D, h->rope_tab, T, 0, R * T, st)); c.end(); c.cat = _c; }
     h->launches++;
     A2P_TRY(gemm(c, hr, D, R * T, lw.ca.in_w, D, lw.ca.in_b, D, D, qkv, 3 * D));
     {
@@ -316,13 +340,15 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       a.kv_ld = D; a.S_main = S;
       a.Kx = ktt + (size_t)l * D; a.Vx = vtt + (size_t)l * D; a.x_ld = (long long)L * D; a.x_sample_stride = 2LL * L * D; a.S_extra = 2;
       a.O = att; a.o_ld = D; a.o_sample_stride = sT; a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
-      A2P_TRY(launch_attn_simt(a, dh, st));
+      c.cat = CAT_ATT_CROSS;
+      c.begin(); A2P_TRY(launch_attn_simt(a, dh, st)); c.end();
+      c.cat = CAT_PROJ;
       h->launches++;
     }
     A2P_TRY(film_gemm(c, att, D, R * T, lw.ca.out_w, lw.ca.out_b, D, D, x, D, film, film_ld, fo + 1 * 2 * D, D, T));
     // ---- cross attention over keyframe tokens (pose; transformer_modules.py:204-214)
     if (cf.fmt == A2P_FMT_POSE) {
-      A2P_TRY(launch_ln_rope(D, x, D, lw.n2aw, lw.n2ab, nullptr, hr, D, h->rope_tab, T, 0, R * T, st));
+      { int _c = c.cat; c.cat = CAT_LN; c.begin(); A2P_TRY(launch_ln_rope(D, x, D, lw.n2aw, lw.n2ab, nullptr, hr, D, h->rope_tab, T, 0, R * T, st)); c.end(); c.cat = _c; }
       h->launches++;
       A2P_TRY(gemm(c, hr, D, R * T, lw.c2.in_w, D, lw.c2.in_b, D, D, qkv, 3 * D));
       AttnParams a{};
@@ -335,17 +361,21 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       a.V.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.v2 : nullptr;
       a.kv_ld = D; a.S_main = S2; a.S_extra = 0;
       a.O = att; a.o_ld = D; a.o_sample_stride = sT; a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
-      A2P_TRY(launch_attn_simt(a, dh, st));
+      c.cat = CAT_ATT_CROSS2;
+      c.begin(); A2P_TRY(launch_attn_simt(a, dh, st)); c.end();
+      c.cat = CAT_PROJ;
       h->launches++;
       A2P_TRY(film_gemm(c, att, D, R * T, lw.c2.out_w, lw.c2.out_b, D, D, x, D, film, film_ld, fo + 2 * 2 * D, D, T));
     }
     // ---- feed forward (transformer_modules.py:265-267)
-    A2P_TRY(launch_ln_rope(D, x, D, lw.n3w, lw.n3b, hh, nullptr, D, h->rope_tab, T, 0, R * T, st));
+    c.cat = CAT_FFN;
+    { int _c = c.cat; c.cat = CAT_LN; c.begin(); A2P_TRY(launch_ln_rope(D, x, D, lw.n3w, lw.n3b, hh, nullptr, D, h->rope_tab, T, 0, R * T, st)); c.end(); c.cat = _c; }
     h->launches++;
     A2P_TRY(gemm(c, hh, D, R * T, lw.l1w, D, lw.l1b, cf.FF, D, u, cf.FF, EPI_GELU));
     A2P_TRY(film_gemm(c, u, cf.FF, R * T, lw.l2w, lw.l2b, D, cf.FF, x, D, film, film_ld, fo + (nf - 1) * 2 * D, D, T));
   }
   // ---- final projection (+ causal TCN for pose; model/diffusion.py:397-402)
+  c.cat = CAT_IO_TCN;
   A2P_TRY(gemm(c, x, D, R * T, h->fin_w, D, h->fin_b, C, D, out, C));
   if (cf.fmt == A2P_FMT_POSE) {
     const int cm = C > 256 ? C : 256;
@@ -546,7 +576,7 @@ int a2p_denoiser_set_conditioning(a2p_denoiser_t* h, int branch, int Bc, int S, 
   float* mem_r = mem_n + align_up((size_t)Bc * S * D, 64);
   float* pose_buf = mem_r + align_up((size_t)Bc * S * D, 64);
   // norm_cond on the audio rows + rotation at positions 0..S-1 (model/diffusion.py:392-393; transformer_modules.py:253)
-  A2P_TRY(launch_ln_rope(cf.D, cond_tokens, D, h->normc_w, h->normc_b, mem_n, mem_r, D, h->rope_tab, S, 0, Bc * S, c.st));
+  { int _c = c.cat; c.cat = CAT_LN; c.begin(); A2P_TRY(launch_ln_rope(cf.D, cond_tokens, D, h->normc_w, h->normc_b, mem_n, mem_r, D, h->rope_tab, S, 0, Bc * S, c.st)); c.end(); c.cat = _c; }
   h->launches++;
   float* pose_r = pose_buf;
   for (int l = 0; l < cf.L; ++l) {
@@ -685,6 +715,29 @@ int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, cons
   }
   for (int i = 0; i < n_steps; ++i) A2P_CUDA(cudaGraphLaunch(h->gexec, c.st));
   h->launches += h->graph_nodes * n_steps;
+  return 0;
+}
+
+int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, const int64_t* timesteps, int branch_mask,
+                        void* ws, size_t ws_bytes, void* stream, float* ms_by_cat, int64_t* launches_by_cat, int ncat) {
+  if (!h || !h->bound) A2P_FAIL("profile_forward: weights not bound");
+  if (ncat < CAT_N || !ms_by_cat || !launches_by_cat) A2P_FAIL("profile_forward: need %d categories", (int)CAT_N);
+  const WsLayout w = ws_layout(h->cfg, B, T);
+  if (ws_bytes < w.total) A2P_FAIL("profile_forward: workspace too small");
+  Prof prof;
+  Ctx c{h, (cudaStream_t)stream};
+  c.prof = &prof;
+  const float *x0c, *x0u; long long ss;
+  A2P_TRY(forward_core(c, B, T, x_btc, (const long long*)timesteps, nullptr, branch_mask, (char*)ws, &x0c, &x0u, &ss));
+  A2P_CUDA(cudaStreamSynchronize(c.st));
+  for (int i = 0; i < ncat; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
+  for (size_t i = 0; i < prof.cat.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
+    ms_by_cat[prof.cat[i]] += ms;
+    launches_by_cat[prof.cat[i]]++;
+  }
+  for (auto e : prof.ev) cudaEventDestroy(e);
   return 0;
 }
 

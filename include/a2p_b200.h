@@ -154,6 +154,14 @@ int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, cons
                     const float* noise_tape, int clip_denoised, int branch_mask, int use_graph, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* Measurement aid (bench.py roofline): one un-captured denoiser evaluation with a CUDA-event pair around
+ * every kernel; ms_by_cat / launches_by_cat are HOST arrays of ncat >= 9 entries, categories:
+ * 0 time-conditioning GEMMs, 1 LayerNorm+RoPE, 2 attention projections, 3 self-attention core,
+ * 4 audio cross-attention core, 5 keyframe cross-attention core, 6 feed-forward, 7 in/out projection + TCN,
+ * 8 misc.  x_btc: [B,T,C].  Synchronises the stream. */
+int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, const int64_t* timesteps, int branch_mask,
+                        void* ws, size_t ws_bytes, void* stream, float* ms_by_cat, int64_t* launches_by_cat, int ncat);
+
 /* kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t a2p_launch_count(const a2p_denoiser_t* h);
 
