@@ -7,6 +7,7 @@
 #pragma once
 #include <math.h>
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace a2p {
 
@@ -15,6 +16,7 @@ struct AttnParams {
   BranchPtr K, V; long long kv_ld; int S_main;
   const float* Kx; const float* Vx; long long x_ld; long long x_sample_stride; int S_extra;
   float* O; long long o_ld; long long o_sample_stride;
+  __nv_bfloat16* Op; long long op_plane_stride; int op_terms;   // optional split-bf16 planes output [terms][R*T][o_ld]
   int T, H, R;
   float scale_log2e;
 };
@@ -151,6 +153,22 @@ __global__ void __launch_bounds__(256) attn_simt_kernel(AttnParams p) {
     const int row = q0 + ty + 16 * i;
     if (row >= p.T) continue;
     const float inv = 1.f / l[i];
+    if (p.Op) {
+      __nv_bfloat16* dst = p.Op + (long long)r * p.o_sample_stride + (long long)row * p.o_ld + h * DH + tx * NV;
+      for (int t = 0; t < p.op_terms; ++t) {
+        __nv_bfloat16 pl[NV];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          float val = o[i][j] * inv;
+          __nv_bfloat16 sp[3];
+          umma::split_bf16<3>(val, sp);
+          pl[j] = sp[t];
+        }
+        if constexpr (NV == 2) *reinterpret_cast<uint32_t*>(dst + t * p.op_plane_stride) = *reinterpret_cast<const uint32_t*>(pl);
+        else *reinterpret_cast<uint2*>(dst + t * p.op_plane_stride) = *reinterpret_cast<const uint2*>(pl);
+      }
+      continue;
+    }
     if constexpr (NV == 2) {
       *reinterpret_cast<float2*>(Og + (long long)row * p.o_ld + tx * 2) = make_float2(o[i][0] * inv, o[i][1] * inv);
     } else {

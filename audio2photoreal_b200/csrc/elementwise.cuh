@@ -2,6 +2,7 @@
 // sampler epilogue.  All are one-pass, 128-bit vectorised where the layout allows.
 #pragma once
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace a2p {
 
@@ -63,6 +64,85 @@ __global__ void __launch_bounds__(256) ln_rope_kernel(const float* __restrict__ 
       *reinterpret_cast<float4*>(out_r + (long long)warp * ldo + col) = make_float4(r0, r1, r2, r3);
     }
   }
+}
+
+// Same LayerNorm(+RoPE) but the outputs are written as TERMS split-bf16 planes [TERMS][rows][D] -- the A operand
+// of the tensor-core GEMMs (LN / RoPE stay in fp32 registers; only the GEMM input is split).
+template <int D, int TERMS>
+__global__ void __launch_bounds__(256) ln_rope_planes_kernel(const float* __restrict__ x, long long ldx,
+                                                             const float* __restrict__ w, const float* __restrict__ b,
+                                                             __nv_bfloat16* __restrict__ out_h, __nv_bfloat16* __restrict__ out_r,
+                                                             long long plane_stride, const float2* __restrict__ tab, int half,
+                                                             int pos_mod, int pos_base, int rows) {
+  constexpr int PER = D / 32;
+  constexpr int NV = PER / 4;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (long long)warp * ldx;
+  float v[PER];
+#pragma unroll
+  for (int c = 0; c < NV; ++c) *reinterpret_cast<float4*>(v + 4 * c) = *reinterpret_cast<const float4*>(xr + (c * 32 + lane) * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) s += v[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { float d = v[i] - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / D + 1e-5f);
+  const int pos = pos_base + (pos_mod > 0 ? warp % pos_mod : 0);
+#pragma unroll
+  for (int c = 0; c < NV; ++c) {
+    const int col = (c * 32 + lane) * 4;
+    float4 ww = *reinterpret_cast<const float4*>(w + col), bb = *reinterpret_cast<const float4*>(b + col);
+    float h[4];
+    h[0] = (v[4 * c + 0] - mean) * rstd * ww.x + bb.x;
+    h[1] = (v[4 * c + 1] - mean) * rstd * ww.y + bb.y;
+    h[2] = (v[4 * c + 2] - mean) * rstd * ww.z + bb.z;
+    h[3] = (v[4 * c + 3] - mean) * rstd * ww.w + bb.w;
+    auto emit = [&](const float* val, __nv_bfloat16* dst) {
+      __nv_bfloat16 pl[TERMS][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __nv_bfloat16 sp[TERMS];
+        umma::split_bf16<TERMS>(val[j], sp);
+#pragma unroll
+        for (int i = 0; i < TERMS; ++i) pl[i][j] = sp[i];
+      }
+#pragma unroll
+      for (int i = 0; i < TERMS; ++i)
+        *reinterpret_cast<uint2*>(dst + i * plane_stride + (long long)warp * D + col) = *reinterpret_cast<const uint2*>(pl[i]);
+    };
+    if (out_h) emit(h, out_h);
+    if (out_r) {
+      float2 cs0 = tab[(long long)pos * half + col / 2], cs1 = tab[(long long)pos * half + col / 2 + 1];
+      float r[4];
+      r[0] = h[0] * cs0.x - h[1] * cs0.y; r[1] = h[1] * cs0.x + h[0] * cs0.y;
+      r[2] = h[2] * cs1.x - h[3] * cs1.y; r[3] = h[3] * cs1.x + h[2] * cs1.y;
+      emit(r, out_r);
+    }
+  }
+}
+
+inline int launch_ln_rope_planes(int D, int terms, const float* x, long long ldx, const float* w, const float* b,
+                                 __nv_bfloat16* out_h, __nv_bfloat16* out_r, long long plane_stride, const float2* tab,
+                                 int pos_mod, int pos_base, int rows, cudaStream_t st) {
+  int blocks = ceil_div(rows, 8);
+#define A2P_LNP(DD, TT) ln_rope_planes_kernel<DD, TT><<<blocks, 256, 0, st>>>(x, ldx, w, b, out_h, out_r, plane_stride, tab, DD / 2, pos_mod, pos_base, rows)
+  if (D == 256 && terms == 1) A2P_LNP(256, 1);
+  else if (D == 256 && terms == 2) A2P_LNP(256, 2);
+  else if (D == 256 && terms == 3) A2P_LNP(256, 3);
+  else if (D == 512 && terms == 1) A2P_LNP(512, 1);
+  else if (D == 512 && terms == 2) A2P_LNP(512, 2);
+  else if (D == 512 && terms == 3) A2P_LNP(512, 3);
+  else A2P_FAIL("ln_rope_planes: D=%d terms=%d unsupported", D, terms);
+#undef A2P_LNP
+  A2P_CUDA(cudaGetLastError());
+  return 0;
 }
 
 inline int launch_ln_rope(int D, const float* x, long long ldx, const float* w, const float* b, float* out_h,

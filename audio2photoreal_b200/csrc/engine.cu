@@ -17,6 +17,8 @@
 #include "common.cuh"
 #include "elementwise.cuh"
 #include "sgemm.cuh"
+#include "umma_gemm.cuh"
+#include "../../include/a2p_b200_testing.h"
 
 using namespace a2p;
 
@@ -66,10 +68,14 @@ struct a2p_denoiser {
   float *film_w = nullptr, *film_b = nullptr, *ttk_w = nullptr, *ttk_b = nullptr, *ttv_w = nullptr, *ttv_b = nullptr;
   float* conv_w[6]{};
   float2* rope_tab = nullptr;
+  std::map<const float*, __nv_bfloat16*> wplanes;  // fp32 weight -> split-bf16 planes [P][rows][cols] (plane stride = numel)
+  std::map<const float*, long long> wnumel;
+  int num_sms = 148;
   CondSet cond[2];
   int64_t launches = 0;
   int64_t graph_nodes = 0;
   cudaGraphExec_t gexec = nullptr;
+  cudaStream_t cap_stream = nullptr;  // private stream used only to CAPTURE a step (the legacy default stream cannot capture)
   GraphKey gkey{};
   bool gvalid = false;
 };
@@ -78,8 +84,14 @@ namespace {
 
 // ---------------------------------------------------------------- arena layouts
 struct PackedLayout {
-  size_t film_w, film_b, ttk_w, ttk_b, ttv_w, ttv_b, conv_w[6], rope, total;
+  size_t film_w, film_b, ttk_w, ttk_b, ttv_w, ttv_b, conv_w[6], rope, planes, planes_bytes, total;
 };
+// elements of every weight that gets split-bf16 planes
+size_t split_weight_elems(const a2p_model_cfg& c) {
+  const size_t D = c.D, FF = c.FF, C = c.C;
+  size_t per_layer = 2 * (3 * D * D + D * D) + 2 * FF * D + (c.fmt == A2P_FMT_POSE ? 4 * D * D : 0);
+  return per_layer * c.L + 2 * D * C;
+}
 PackedLayout packed_layout(const a2p_model_cfg& c) {
   PackedLayout p{};
   size_t off = 0;
@@ -97,6 +109,9 @@ PackedLayout packed_layout(const a2p_model_cfg& c) {
     for (int i = 0; i < 6; ++i) p.conv_w[i] = take((size_t)chans[i][0] * chans[i][1] * 3);
   }
   p.rope = take((size_t)c.max_pos * (c.D / 2) * 2);
+  p.planes = off;
+  p.planes_bytes = c.split_terms > 0 ? align_up(split_weight_elems(c) * 2 * c.split_terms + 64 * 256, 256) : 0;
+  off += p.planes_bytes;
   p.total = off;
   return p;
 }
@@ -116,6 +131,7 @@ KvLayout kv_layout(const a2p_model_cfg& c, int Bc, int S, int S2) {
 
 struct WsLayout {
   size_t counter, e, th, mt, ttok, tt, ttr, ktt, vtt, film, xin, x, h, hr, qkv, att, u, out, tcnA, tcnB, tcnC, total;
+  size_t hP, hrP, attP, uP, xinP;   // split-bf16 activation planes (tensor-core arm)
 };
 WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
   WsLayout w{};
@@ -135,6 +151,11 @@ WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
   if (c.fmt == A2P_FMT_POSE) {
     const size_t cm = c.C > 256 ? c.C : 256;
     w.tcnA = take(R * (T + TCN_PAD) * c.C); w.tcnB = take(R * (T + TCN_PAD) * cm); w.tcnC = take(R * (T + TCN_PAD) * c.C);
+  }
+  if (c.split_terms > 0) {
+    const size_t P = c.split_terms;   // bf16 = half a float
+    w.hP = take(P * R * T * D / 2 + 64); w.hrP = take(P * R * T * D / 2 + 64); w.attP = take(P * R * T * D / 2 + 64);
+    w.uP = take(P * R * T * c.FF / 2 + 64); w.xinP = take(P * R * T * (D > c.C ? D : c.C) / 2 + 64);
   }
   w.total = off;
   return w;
@@ -219,6 +240,30 @@ int film_gemm(Ctx& c, const float* A, long long lda, int M, const float* W, cons
   return gemm(c, A, lda, M, W, K, bias, N, K, x, ldx, EPI_FILM_RESID, &e);
 }
 
+// tensor-core GEMM on pre-split operands: A planes [P][M][K]; W = rows [w_row0, w_row0+N) of the fp32 weight `wkey` [*,K]
+int tc_gemm(Ctx& c, const __nv_bfloat16* Ap, int M, int K, const float* wkey, long long w_row0, int N, const float* bias, int epi,
+            TcGemmParams p) {
+  a2p_denoiser* h = c.h;
+  auto it = h->wplanes.find(wkey);
+  if (it == h->wplanes.end()) A2P_FAIL("tc_gemm: weight has no split planes");
+  TcOperands o{Ap, K, (long long)M * K, it->second + w_row0 * K, K, h->wnumel[wkey]};
+  p.M = M; p.N = N; p.K = K; p.taps = 1; p.dil = 0; p.bias = bias;
+  if (p.out_scale == 0.f) p.out_scale = 1.f;
+  h->launches++;
+  c.begin();
+  int rc = launch_umma_gemm(h->cfg.split_terms, o, p, epi, h->num_sms, c.st);
+  c.end();
+  return rc;
+}
+
+int tc_film_gemm(Ctx& c, const __nv_bfloat16* Ap, int M, int K, const float* wkey, const float* bias, int N, float* x, long long ldx,
+                 const float* film, long long film_ld, int film_off, int D, int rows_per_sample) {
+  TcGemmParams p{};
+  p.C = x; p.ldc = ldx; p.film = film; p.film_ld = film_ld; p.film_scale_off = film_off; p.film_shift_off = film_off + D;
+  p.rows_per_sample = rows_per_sample;
+  return tc_gemm(c, Ap, M, K, wkey, 0, N, bias, TC_FILM, p);
+}
+
 const float* find(const std::map<std::string, std::pair<const float*, int64_t>>& m, const std::string& k, int64_t numel,
                   std::string& err) {
   auto it = m.find(k);
@@ -241,7 +286,7 @@ int check_cfg(const a2p_model_cfg* c) {
   if (c->C % 8 || c->FF % 8) A2P_FAIL("cfg.C/FF must be multiples of 8");
   if (c->fmt == A2P_FMT_POSE && c->S2 <= 0) A2P_FAIL("pose needs S2 > 0");
   if (c->fmt == A2P_FMT_FACE && c->S2 != 0) A2P_FAIL("face must have S2 == 0");
-  if (c->split_terms != 0) A2P_FAIL("split_terms=%d: tensor-core arm not built in this version", c->split_terms);
+  if (c->split_terms < 0 || c->split_terms > 3) A2P_FAIL("split_terms=%d must be 0 (exact fp32) or 1..3 bf16 planes", c->split_terms);
   if (c->max_pos < 2) A2P_FAIL("cfg.max_pos too small");
   return 0;
 }
@@ -302,7 +347,86 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   }
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
   const long long sT = (long long)T * D;
-  for (int l = 0; l < L; ++l) {
+  const int P = cf.split_terms;
+  __nv_bfloat16* hP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.hP) : nullptr;
+  __nv_bfloat16* hrP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.hrP) : nullptr;
+  __nv_bfloat16* attP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.attP) : nullptr;
+  __nv_bfloat16* uP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.uP) : nullptr;
+  const int MT = R * T;
+  const long long pstrideD = (long long)MT * D;
+  for (int l = 0; P > 0 && l < L; ++l) {
+    // ===== tensor-core arm: every [R*T, *] linear runs as a split-bf16 tcgen05 GEMM; LN / RoPE / softmax stay fp32 =====
+    const LayerW& lw = h->lw[l];
+    const int fo = l * nf * 2 * D;
+    auto lnp = [&](const float* nw, const float* nb, __nv_bfloat16* oh, __nv_bfloat16* orr) -> int {
+      int _c = c.cat; c.cat = CAT_LN; c.begin();
+      int rc = launch_ln_rope_planes(D, P, x, D, nw, nb, oh, orr, pstrideD, h->rope_tab, T, 0, MT, st);
+      c.end(); c.cat = _c; h->launches++;
+      return rc;
+    };
+    auto attn = [&](AttnParams& a, int cat) -> int {
+      a.Q = qkv; a.q_ld = 3 * D; a.q_sample_stride = 3 * sT;
+      a.O = nullptr; a.Op = attP; a.op_plane_stride = pstrideD; a.op_terms = P; a.o_ld = D; a.o_sample_stride = sT;
+      a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
+      c.cat = cat; c.begin();
+      int rc = launch_attn_simt(a, dh, st);
+      c.end(); c.cat = CAT_PROJ; h->launches++;
+      return rc;
+    };
+    TcGemmParams f32out{};
+    f32out.C = qkv; f32out.ldc = 3 * D;
+    c.cat = CAT_PROJ;
+    // ---- self attention
+    A2P_TRY(lnp(lw.n1w, lw.n1b, hP, hrP));
+    A2P_TRY(tc_gemm(c, hrP, MT, D, lw.sa.in_w, 0, 2 * D, lw.sa.in_b, TC_F32, f32out));
+    { TcGemmParams v = f32out; v.C = qkv + 2 * D; A2P_TRY(tc_gemm(c, hP, MT, D, lw.sa.in_w, 2 * D, D, lw.sa.in_b + 2 * D, TC_F32, v)); }
+    {
+      AttnParams a{};
+      a.K.base[0] = qkv + D; a.K.stride[0] = 3 * sT; a.K.base[1] = nullptr; a.K.stride[1] = 0; a.K.rows_per_branch = R;
+      a.V = a.K; a.V.base[0] = qkv + 2 * D;
+      a.kv_ld = 3 * D; a.S_main = T; a.S_extra = 0;
+      A2P_TRY(attn(a, CAT_ATT_SELF));
+    }
+    A2P_TRY(tc_film_gemm(c, attP, MT, D, lw.sa.out_w, lw.sa.out_b, D, x, D, film, film_ld, fo + 0 * 2 * D, D, T));
+    // ---- audio cross attention
+    A2P_TRY(lnp(lw.n2w, lw.n2b, nullptr, hrP));
+    A2P_TRY(tc_gemm(c, hrP, MT, D, lw.ca.in_w, 0, D, lw.ca.in_b, TC_F32, f32out));
+    {
+      AttnParams a{};
+      a.K.base[0] = c0.base + k0.per_layer * l + k0.ka; a.K.stride[0] = c0.Bc == 1 ? 0 : (long long)S * D;
+      a.K.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.ka : nullptr; a.K.stride[1] = c1.Bc == 1 ? 0 : (long long)S * D;
+      a.K.rows_per_branch = B;
+      a.V = a.K;
+      a.V.base[0] = c0.base + k0.per_layer * l + k0.va;
+      a.V.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.va : nullptr;
+      a.kv_ld = D; a.S_main = S;
+      a.Kx = ktt + (size_t)l * D; a.Vx = vtt + (size_t)l * D; a.x_ld = (long long)L * D; a.x_sample_stride = 2LL * L * D; a.S_extra = 2;
+      A2P_TRY(attn(a, CAT_ATT_CROSS));
+    }
+    A2P_TRY(tc_film_gemm(c, attP, MT, D, lw.ca.out_w, lw.ca.out_b, D, x, D, film, film_ld, fo + 1 * 2 * D, D, T));
+    // ---- keyframe cross attention (pose)
+    if (cf.fmt == A2P_FMT_POSE) {
+      A2P_TRY(lnp(lw.n2aw, lw.n2ab, nullptr, hrP));
+      A2P_TRY(tc_gemm(c, hrP, MT, D, lw.c2.in_w, 0, D, lw.c2.in_b, TC_F32, f32out));
+      AttnParams a{};
+      a.K.base[0] = c0.base + k0.per_layer * l + k0.k2; a.K.stride[0] = c0.Bc == 1 ? 0 : (long long)S2 * D;
+      a.K.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.k2 : nullptr; a.K.stride[1] = c1.Bc == 1 ? 0 : (long long)S2 * D;
+      a.K.rows_per_branch = B;
+      a.V = a.K;
+      a.V.base[0] = c0.base + k0.per_layer * l + k0.v2;
+      a.V.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.v2 : nullptr;
+      a.kv_ld = D; a.S_main = S2; a.S_extra = 0;
+      A2P_TRY(attn(a, CAT_ATT_CROSS2));
+      A2P_TRY(tc_film_gemm(c, attP, MT, D, lw.c2.out_w, lw.c2.out_b, D, x, D, film, film_ld, fo + 2 * 2 * D, D, T));
+    }
+    // ---- feed forward: GELU output goes straight to split planes
+    c.cat = CAT_FFN;
+    A2P_TRY(lnp(lw.n3w, lw.n3b, hP, nullptr));
+    { TcGemmParams g{}; g.Cp = uP; g.cp_plane_stride = (long long)MT * cf.FF; g.ldcp = cf.FF;
+      A2P_TRY(tc_gemm(c, hP, MT, D, lw.l1w, 0, cf.FF, lw.l1b, TC_GELU_PLANES, g)); }
+    A2P_TRY(tc_film_gemm(c, uP, MT, cf.FF, lw.l2w, lw.l2b, D, x, D, film, film_ld, fo + (nf - 1) * 2 * D, D, T));
+  }
+  for (int l = 0; P == 0 && l < L; ++l) {
     const LayerW& lw = h->lw[l];
     const int fo = l * nf * 2 * D;
     // ---- self attention: q = k = rot(LN1 x), v = LN1 x  (transformer_modules.py:237-247)
@@ -431,7 +555,7 @@ extern "C" {
 
 int a2p_abi_version(void) { return A2P_ABI_VERSION; }
 const char* a2p_last_error(void) { return a2p::last_error().c_str(); }
-int a2p_has_tcgen05(void) { return 0; }
+int a2p_has_tcgen05(void) { return 1; }
 
 int a2p_denoiser_create(a2p_denoiser_t** out, const a2p_model_cfg* cfg) {
   if (!out) A2P_FAIL("null out");
@@ -451,6 +575,7 @@ int a2p_denoiser_create(a2p_denoiser_t** out, const a2p_model_cfg* cfg) {
 void a2p_denoiser_destroy(a2p_denoiser_t* h) {
   if (!h) return;
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   delete h;
 }
 
@@ -532,6 +657,33 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
     h->fconv_w = W("final_conv.weight", C * C); h->fconv_b = W("final_conv.bias", C);
   }
   if (!err.empty()) A2P_FAIL("bind_weights: %s", err.c_str());
+  h->wplanes.clear(); h->wnumel.clear();
+  if (cf.split_terms > 0) {
+    __nv_bfloat16* cur = reinterpret_cast<__nv_bfloat16*>(pb + pl.planes);
+    const __nv_bfloat16* endp = reinterpret_cast<__nv_bfloat16*>(pb + pl.planes + pl.planes_bytes);
+    auto split_w = [&](const float* wsrc, long long rows, long long cols) -> int {
+      const long long numel = rows * cols;
+      if (cur + numel * cf.split_terms > endp) A2P_FAIL("bind_weights: plane arena overflow");
+      A2P_TRY(launch_split_planes(cf.split_terms, wsrc, cols, cur, numel, rows, (int)cols, 1.f, st));
+      h->wplanes[wsrc] = cur; h->wnumel[wsrc] = numel;
+      cur += align_up((size_t)numel * cf.split_terms, 64);
+      return 0;
+    };
+    for (int l = 0; l < cf.L; ++l) {
+      const LayerW& lw = h->lw[l];
+      A2P_TRY(split_w(lw.sa.in_w, 3 * D, D)); A2P_TRY(split_w(lw.sa.out_w, D, D));
+      A2P_TRY(split_w(lw.ca.in_w, 3 * D, D)); A2P_TRY(split_w(lw.ca.out_w, D, D));
+      if (cf.fmt == A2P_FMT_POSE) { A2P_TRY(split_w(lw.c2.in_w, 3 * D, D)); A2P_TRY(split_w(lw.c2.out_w, D, D)); }
+      A2P_TRY(split_w(lw.l1w, FF, D)); A2P_TRY(split_w(lw.l2w, D, FF));
+    }
+    A2P_TRY(split_w(h->inp_w, D, C)); A2P_TRY(split_w(h->fin_w, C, D));
+    A2P_TRY(init_umma_gemm());
+  }
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
   rope_table_kernel<<<ceil_div(cf.max_pos * (int)(D / 2), 256), 256, 0, st>>>(freqs, h->rope_tab, cf.max_pos, (int)(D / 2));
   A2P_CUDA(cudaGetLastError());
   h->bound = true;
@@ -697,9 +849,13 @@ int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, cons
     h->gvalid = false;
     cudaGraph_t graph = nullptr;
     int64_t before = h->launches;
+    if (!h->cap_stream) A2P_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t user = c.st;
+    c.st = h->cap_stream;
     A2P_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeRelaxed));
     int rc = step_body();
     cudaError_t ce = cudaStreamEndCapture(c.st, &graph);
+    c.st = user;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (ce != cudaSuccess) A2P_FAIL("graph capture failed: %s", cudaGetErrorString(ce));
     h->launches = before;  // captured launches are counted per replay below
@@ -742,5 +898,59 @@ int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, con
 }
 
 int64_t a2p_launch_count(const a2p_denoiser_t* h) { return h ? h->launches : 0; }
+
+// ------------------------------------------------------------------ testing hooks (include/a2p_b200_testing.h)
+size_t a2p_test_tc_gemm_scratch_bytes(int M, int N, int K, int taps) {
+  return ((size_t)3 * M * K + (size_t)3 * taps * N * K) * 2 + 1024;
+}
+
+int a2p_test_tc_gemm(int terms, int M, int N, int K, int taps, int dil, const float* A, const float* W, const float* bias,
+                     float* C, void* scratch, size_t scratch_bytes, int iters, float* ms_out, void* stream) {
+  if (scratch_bytes < a2p_test_tc_gemm_scratch_bytes(M, N, K, taps)) A2P_FAIL("test_tc_gemm: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  A2P_TRY(init_umma_gemm());
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  __nv_bfloat16* Ap = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* Wp = Ap + align_up((size_t)3 * M * K, 64);
+  A2P_TRY(launch_split_planes(terms, A, K, Ap, (long long)M * K, M, K, 1.f, st));
+  A2P_TRY(launch_split_planes(terms, W, K, Wp, (long long)taps * N * K, (long long)taps * N, K, 1.f, st));
+  TcOperands o{Ap, K, (long long)M * K, Wp, K, (long long)N * K};
+  TcGemmParams p{};
+  p.M = M; p.N = N; p.K = K; p.taps = taps; p.dil = dil; p.bias = bias; p.C = C; p.ldc = N; p.out_scale = 1.f;
+  A2P_TRY(launch_umma_gemm(terms, o, p, TC_F32, sms, st));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) A2P_TRY(launch_umma_gemm(terms, o, p, TC_F32, sms, st));
+  cudaEventRecord(e1, st);
+  A2P_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int a2p_test_sgemm(int M, int N, int K, int taps, int dil, const float* A, const float* W, const float* bias, float* C,
+                   int iters, float* ms_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  GemmParams p{};
+  p.A = A; p.lda = K; p.W = W; p.ldw = (long long)taps * K; p.bias = bias; p.C = C; p.ldc = N; p.M = M; p.N = N; p.K = taps * K;
+  p.taps = taps; p.dil = dil; p.Kc = K; p.epi = EPI_BIAS;
+  A2P_TRY(launch_sgemm(p, st));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) A2P_TRY(launch_sgemm(p, st));
+  cudaEventRecord(e1, st);
+  A2P_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
 
 }  // extern "C"

@@ -1,0 +1,23 @@
+/* Test / measurement hooks of liba2p_b200.so (NOT part of the drop-in ABI; used by tests/ and scripts/). */
+#ifndef A2P_B200_TESTING_H
+#define A2P_B200_TESTING_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* C[M,N] = A[M,K] * W[taps][N][K]^T (+ bias) with the split-bf16 tcgen05 GEMM (terms 1..3); fp32 in/out.
+ * scratch holds the bf16 planes (size from a2p_test_tc_gemm_scratch_bytes).  Runs `iters` timed launches
+ * after one warm-up and returns the average kernel time (CUDA events) in *ms_out.  Synchronises. */
+size_t a2p_test_tc_gemm_scratch_bytes(int M, int N, int K, int taps);
+int a2p_test_tc_gemm(int terms, int M, int N, int K, int taps, int dil, const float* A, const float* W, const float* bias,
+                     float* C, void* scratch, size_t scratch_bytes, int iters, float* ms_out, void* stream);
+/* same product with the exact-fp32 FFMA GEMM (W as [N][taps*K]) */
+int a2p_test_sgemm(int M, int N, int K, int taps, int dil, const float* A, const float* W, const float* bias, float* C,
+                   int iters, float* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
