@@ -18,6 +18,7 @@
 #include "elementwise.cuh"
 #include "sgemm.cuh"
 #include "umma_gemm.cuh"
+#include "umma_attention.cuh"
 #include "../../include/a2p_b200_testing.h"
 
 using namespace a2p;
@@ -118,12 +119,24 @@ PackedLayout packed_layout(const a2p_model_cfg& c) {
 
 struct KvLayout {
   size_t per_layer, ka, va, k2, v2, hidden, total;  // float offsets
+  size_t kaP, vtaP, k2P, vt2P;                      // tensor-core arm: split-bf16 K planes / V^T planes (float offsets)
+  size_t Sp, S2p;                                   // per-sample column pitch of the V^T planes (multiple of 8)
 };
 KvLayout kv_layout(const a2p_model_cfg& c, int Bc, int S, int S2) {
   KvLayout k{};
   size_t a = (size_t)Bc * S * c.D, b = (size_t)Bc * S2 * c.D;
   k.ka = 0; k.va = a; k.k2 = 2 * a; k.v2 = 2 * a + b;
   k.per_layer = 2 * a + 2 * b;
+  k.Sp = align_up((size_t)S, 8); k.S2p = align_up((size_t)(S2 > 0 ? S2 : 1), 8);
+  if (c.split_terms > 0) {
+    const size_t P = c.split_terms;
+    auto take = [&](size_t bf16s) { size_t o = k.per_layer; k.per_layer += align_up(bf16s / 2 + 1, 64); return o; };
+    k.per_layer = align_up(k.per_layer, 64);
+    k.kaP = take(P * Bc * S * c.D);
+    k.vtaP = take(P * c.D * Bc * k.Sp);
+    k.k2P = take(P * (b ? b : 1));
+    k.vt2P = take(P * c.D * Bc * k.S2p);
+  }
   k.hidden = k.per_layer * c.L;
   k.total = k.hidden + (size_t)Bc * c.D;
   return k;
@@ -132,6 +145,7 @@ KvLayout kv_layout(const a2p_model_cfg& c, int Bc, int S, int S2) {
 struct WsLayout {
   size_t counter, e, th, mt, ttok, tt, ttr, ktt, vtt, film, xin, x, h, hr, qkv, att, u, out, tcnA, tcnB, tcnC, total;
   size_t hP, hrP, attP, uP, xinP;   // split-bf16 activation planes (tensor-core arm)
+  size_t qkP, vtS, kttP, vttT;      // tensor-core attention operands: Q|K planes, self V^T planes, time-token K / V^T planes
 };
 WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
   WsLayout w{};
@@ -156,6 +170,8 @@ WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
     const size_t P = c.split_terms;   // bf16 = half a float
     w.hP = take(P * R * T * D / 2 + 64); w.hrP = take(P * R * T * D / 2 + 64); w.attP = take(P * R * T * D / 2 + 64);
     w.uP = take(P * R * T * c.FF / 2 + 64); w.xinP = take(P * R * T * (D > c.C ? D : c.C) / 2 + 64);
+    w.qkP = take(P * R * T * 2 * D / 2 + 64); w.vtS = take(P * D * align_up(R * T, 8) / 2 + 64);
+    w.kttP = take(P * (2 * R + 64) * c.L * D / 2 + 64); w.vttT = take(P * c.L * D * align_up(2 * R, 8) / 2 + 64);
   }
   w.total = off;
   return w;
@@ -354,17 +370,76 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   __nv_bfloat16* uP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.uP) : nullptr;
   const int MT = R * T;
   const long long pstrideD = (long long)MT * D;
+  // ---- tensor-core attention operands (needs T % 8 == 0 for the 16-byte TMA strides of the V^T planes)
+  const bool tc_attn = P > 0 && (T % 8 == 0);
+  __nv_bfloat16* qkP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.qkP) : nullptr;
+  __nv_bfloat16* vtS = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.vtS) : nullptr;
+  __nv_bfloat16* kttP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.kttP) : nullptr;
+  __nv_bfloat16* vttT = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.vttT) : nullptr;
+  const long long MT8 = (long long)align_up((size_t)MT, 8), XP = (long long)align_up((size_t)2 * R, 8);
+  if (tc_attn) {
+    c.cat = CAT_COND;
+    c.begin();
+    A2P_TRY(launch_split_planes(P, ktt, (long long)L * D, kttP, (long long)2 * R * L * D, 2 * R, L * D, 1.f, st));
+    A2P_CUDA(cudaMemsetAsync(vttT, 0, sizeof(__nv_bfloat16) * (size_t)P * L * D * XP, st));
+    A2P_TRY(launch_transpose_split(P, vtt, (long long)L * D, vttT, (long long)L * D * XP, XP, 2 * R, L * D, 2 * R, 0, 1.f, st));
+    c.end();
+    h->launches += 3;
+  }
+  auto attn_tc = [&](int l, int kind) -> int {   // kind 0 self, 1 audio cross (+2 time tokens), 2 keyframe cross
+    TcAttnOperands o{};
+    TcAttnParams ap{};
+    o.Q = qkP; o.q_rows = MT; o.q_ld = 2 * D; o.q_plane_stride = (long long)MT * 2 * D;
+    o.vt_rows = D;
+    ap.T = T; ap.R = R; ap.D = D; ap.dh = dh; ap.q_col0 = 0; ap.Op = attP; ap.op_plane_stride = pstrideD; ap.o_ld = D; ap.O = nullptr;
+    if (kind == 0) {
+      o.K[0] = qkP; o.k_rows[0] = MT; o.k_ld[0] = 2 * D; o.k_plane_stride[0] = (long long)MT * 2 * D;
+      o.Vt[0] = vtS; o.vt_cols[0] = MT; o.vt_ld[0] = MT8; o.vt_plane_stride[0] = (long long)D * MT8;
+      ap.rows_per_branch = R; ap.k_col0 = D; ap.n_keys = T; ap.n_extra = 0; ap.k_row_stride[0] = T; ap.v_col_stride[0] = T;
+    } else {
+      const CondSet* cs[2] = {&c0, &c1};
+      const KvLayout* kl[2] = {&k0, &k1};
+      for (int b = 0; b < nb; ++b) {
+        float* base = cs[b]->base + kl[b]->per_layer * l;
+        const long long Bc = cs[b]->Bc;
+        if (kind == 1) {
+          o.K[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->kaP); o.k_rows[b] = Bc * S; o.k_ld[b] = D; o.k_plane_stride[b] = Bc * S * D;
+          o.Vt[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->vtaP); o.vt_cols[b] = Bc * (long long)kl[b]->Sp; o.vt_ld[b] = o.vt_cols[b];
+          o.vt_plane_stride[b] = (long long)D * o.vt_cols[b];
+          ap.k_row_stride[b] = Bc == 1 ? 0 : S; ap.v_col_stride[b] = Bc == 1 ? 0 : (long long)kl[b]->Sp;
+        } else {
+          o.K[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->k2P); o.k_rows[b] = Bc * S2; o.k_ld[b] = D; o.k_plane_stride[b] = Bc * S2 * D;
+          o.Vt[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->vt2P); o.vt_cols[b] = Bc * (long long)kl[b]->S2p; o.vt_ld[b] = o.vt_cols[b];
+          o.vt_plane_stride[b] = (long long)D * o.vt_cols[b];
+          ap.k_row_stride[b] = Bc == 1 ? 0 : S2; ap.v_col_stride[b] = Bc == 1 ? 0 : (long long)kl[b]->S2p;
+        }
+      }
+      ap.rows_per_branch = B; ap.k_col0 = 0; ap.n_keys = kind == 1 ? S : S2; ap.n_extra = 0;
+      if (kind == 1) {
+        o.Kx = kttP; o.kx_rows = 2 * R; o.kx_ld = (long long)L * D; o.kx_plane_stride = (long long)2 * R * L * D;
+        o.Vx = vttT; o.vx_rows = (long long)L * D; o.vx_cols = XP; o.vx_ld = XP; o.vx_plane_stride = (long long)L * D * XP;
+        ap.n_extra = 2; ap.kx_col0 = l * D; ap.kx_row_stride = 2; ap.vx_row0 = l * D; ap.vx_col_stride = 2;
+      }
+    }
+    c.cat = kind == 0 ? CAT_ATT_SELF : (kind == 1 ? CAT_ATT_CROSS : CAT_ATT_CROSS2);
+    c.begin();
+    int rc = launch_umma_attn(P, o, ap, st);
+    c.end();
+    c.cat = CAT_PROJ;
+    h->launches++;
+    return rc;
+  };
   for (int l = 0; P > 0 && l < L; ++l) {
     // ===== tensor-core arm: every [R*T, *] linear runs as a split-bf16 tcgen05 GEMM; LN / RoPE / softmax stay fp32 =====
     const LayerW& lw = h->lw[l];
     const int fo = l * nf * 2 * D;
-    auto lnp = [&](const float* nw, const float* nb, __nv_bfloat16* oh, __nv_bfloat16* orr) -> int {
+    auto lnp = [&](const float* nw, const float* nb_, __nv_bfloat16* oh, __nv_bfloat16* orr) -> int {
       int _c = c.cat; c.cat = CAT_LN; c.begin();
-      int rc = launch_ln_rope_planes(D, P, x, D, nw, nb, oh, orr, pstrideD, h->rope_tab, T, 0, MT, st);
+      int rc = launch_ln_rope_planes(D, P, x, D, nw, nb_, oh, orr, pstrideD, h->rope_tab, T, 0, MT, st);
       c.end(); c.cat = _c; h->launches++;
       return rc;
     };
-    auto attn = [&](AttnParams& a, int cat) -> int {
+    auto attn = [&](AttnParams& a, int cat) -> int {   // exact-fp32 attention core (used when T % 8 != 0)
       a.Q = qkv; a.q_ld = 3 * D; a.q_sample_stride = 3 * sT;
       a.O = nullptr; a.Op = attP; a.op_plane_stride = pstrideD; a.op_terms = P; a.o_ld = D; a.o_sample_stride = sT;
       a.T = T; a.H = H; a.R = R; a.scale_log2e = scale_log2e;
@@ -375,12 +450,27 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     };
     TcGemmParams f32out{};
     f32out.C = qkv; f32out.ldc = 3 * D;
+    TcGemmParams qplanes{};
+    qplanes.Cp = qkP; qplanes.cp_plane_stride = (long long)MT * 2 * D; qplanes.ldcp = 2 * D; qplanes.out_scale = scale_log2e;
     c.cat = CAT_PROJ;
     // ---- self attention
     A2P_TRY(lnp(lw.n1w, lw.n1b, hP, hrP));
-    A2P_TRY(tc_gemm(c, hrP, MT, D, lw.sa.in_w, 0, 2 * D, lw.sa.in_b, TC_F32, f32out));
-    { TcGemmParams v = f32out; v.C = qkv + 2 * D; A2P_TRY(tc_gemm(c, hP, MT, D, lw.sa.in_w, 2 * D, D, lw.sa.in_b + 2 * D, TC_F32, v)); }
-    {
+    if (tc_attn) {
+      { TcGemmParams q = qplanes; q.scale_ncols = D; A2P_TRY(tc_gemm(c, hrP, MT, D, lw.sa.in_w, 0, 2 * D, lw.sa.in_b, TC_PLANES, q)); }
+      {  // V^T = Wv * LN(x)^T  (swapped operands: the result is already transposed for the PV product)
+        TcOperands o{h->wplanes[lw.sa.in_w] + (size_t)2 * D * D, D, h->wnumel[lw.sa.in_w], hP, D, pstrideD};
+        TcGemmParams v{};
+        v.M = D; v.N = MT; v.K = D; v.taps = 1; v.bias = lw.sa.in_b + 2 * D; v.bias_per_row = 1; v.out_scale = 1.f;
+        v.Cp = vtS; v.cp_plane_stride = (long long)D * MT8; v.ldcp = MT8;
+        h->launches++;
+        c.begin();
+        A2P_TRY(launch_umma_gemm(P, o, v, TC_PLANES, h->num_sms, st));
+        c.end();
+      }
+      A2P_TRY(attn_tc(l, 0));
+    } else {
+      A2P_TRY(tc_gemm(c, hrP, MT, D, lw.sa.in_w, 0, 2 * D, lw.sa.in_b, TC_F32, f32out));
+      { TcGemmParams v = f32out; v.C = qkv + 2 * D; A2P_TRY(tc_gemm(c, hP, MT, D, lw.sa.in_w, 2 * D, D, lw.sa.in_b + 2 * D, TC_F32, v)); }
       AttnParams a{};
       a.K.base[0] = qkv + D; a.K.stride[0] = 3 * sT; a.K.base[1] = nullptr; a.K.stride[1] = 0; a.K.rows_per_branch = R;
       a.V = a.K; a.V.base[0] = qkv + 2 * D;
@@ -390,8 +480,11 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     A2P_TRY(tc_film_gemm(c, attP, MT, D, lw.sa.out_w, lw.sa.out_b, D, x, D, film, film_ld, fo + 0 * 2 * D, D, T));
     // ---- audio cross attention
     A2P_TRY(lnp(lw.n2w, lw.n2b, nullptr, hrP));
-    A2P_TRY(tc_gemm(c, hrP, MT, D, lw.ca.in_w, 0, D, lw.ca.in_b, TC_F32, f32out));
-    {
+    if (tc_attn) {
+      A2P_TRY(tc_gemm(c, hrP, MT, D, lw.ca.in_w, 0, D, lw.ca.in_b, TC_PLANES, qplanes));
+      A2P_TRY(attn_tc(l, 1));
+    } else {
+      A2P_TRY(tc_gemm(c, hrP, MT, D, lw.ca.in_w, 0, D, lw.ca.in_b, TC_F32, f32out));
       AttnParams a{};
       a.K.base[0] = c0.base + k0.per_layer * l + k0.ka; a.K.stride[0] = c0.Bc == 1 ? 0 : (long long)S * D;
       a.K.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.ka : nullptr; a.K.stride[1] = c1.Bc == 1 ? 0 : (long long)S * D;
@@ -407,16 +500,21 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     // ---- keyframe cross attention (pose)
     if (cf.fmt == A2P_FMT_POSE) {
       A2P_TRY(lnp(lw.n2aw, lw.n2ab, nullptr, hrP));
-      A2P_TRY(tc_gemm(c, hrP, MT, D, lw.c2.in_w, 0, D, lw.c2.in_b, TC_F32, f32out));
-      AttnParams a{};
-      a.K.base[0] = c0.base + k0.per_layer * l + k0.k2; a.K.stride[0] = c0.Bc == 1 ? 0 : (long long)S2 * D;
-      a.K.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.k2 : nullptr; a.K.stride[1] = c1.Bc == 1 ? 0 : (long long)S2 * D;
-      a.K.rows_per_branch = B;
-      a.V = a.K;
-      a.V.base[0] = c0.base + k0.per_layer * l + k0.v2;
-      a.V.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.v2 : nullptr;
-      a.kv_ld = D; a.S_main = S2; a.S_extra = 0;
-      A2P_TRY(attn(a, CAT_ATT_CROSS2));
+      if (tc_attn) {
+        A2P_TRY(tc_gemm(c, hrP, MT, D, lw.c2.in_w, 0, D, lw.c2.in_b, TC_PLANES, qplanes));
+        A2P_TRY(attn_tc(l, 2));
+      } else {
+        A2P_TRY(tc_gemm(c, hrP, MT, D, lw.c2.in_w, 0, D, lw.c2.in_b, TC_F32, f32out));
+        AttnParams a{};
+        a.K.base[0] = c0.base + k0.per_layer * l + k0.k2; a.K.stride[0] = c0.Bc == 1 ? 0 : (long long)S2 * D;
+        a.K.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.k2 : nullptr; a.K.stride[1] = c1.Bc == 1 ? 0 : (long long)S2 * D;
+        a.K.rows_per_branch = B;
+        a.V = a.K;
+        a.V.base[0] = c0.base + k0.per_layer * l + k0.v2;
+        a.V.base[1] = c1.base ? c1.base + k1.per_layer * l + k1.v2 : nullptr;
+        a.kv_ld = D; a.S_main = S2; a.S_extra = 0;
+        A2P_TRY(attn(a, CAT_ATT_CROSS2));
+      }
       A2P_TRY(tc_film_gemm(c, attP, MT, D, lw.c2.out_w, lw.c2.out_b, D, x, D, film, film_ld, fo + 2 * 2 * D, D, T));
     }
     // ---- feed forward: GELU output goes straight to split planes
@@ -678,6 +776,7 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
     }
     A2P_TRY(split_w(h->inp_w, D, C)); A2P_TRY(split_w(h->fin_w, C, D));
     A2P_TRY(init_umma_gemm());
+    A2P_TRY(init_umma_attn());
   }
   {
     int dev = 0;
@@ -746,6 +845,29 @@ int a2p_denoiser_set_conditioning(a2p_denoiser_t* h, int branch, int Bc, int S, 
       float* lb = base + kl.per_layer * l;
       A2P_TRY(gemm(c, pose_r, D, (int)rows, lw.c2.in_w + D * D, D, lw.c2.in_b + D, cf.D, cf.D, lb + kl.k2, D));
       A2P_TRY(gemm(c, pose_tokens, D, (int)rows, lw.c2.in_w + 2 * D * D, D, lw.c2.in_b + 2 * D, cf.D, cf.D, lb + kl.v2, D));
+    }
+  }
+  if (cf.split_terms > 0) {
+    // tensor-core attention operands: split-bf16 K planes [P][Bc*S][D] and V^T planes [P][D][Bc*Sp] (pad columns zero)
+    const int P = cf.split_terms;
+    for (int l = 0; l < cf.L; ++l) {
+      float* lb = base + kl.per_layer * l;
+      __nv_bfloat16* kaP = reinterpret_cast<__nv_bfloat16*>(lb + kl.kaP);
+      __nv_bfloat16* vtaP = reinterpret_cast<__nv_bfloat16*>(lb + kl.vtaP);
+      A2P_TRY(launch_split_planes(P, lb + kl.ka, D, kaP, (long long)Bc * S * D, (long long)Bc * S, cf.D, 1.f, c.st));
+      A2P_CUDA(cudaMemsetAsync(vtaP, 0, sizeof(__nv_bfloat16) * (size_t)P * D * Bc * kl.Sp, c.st));
+      A2P_TRY(launch_transpose_split(P, lb + kl.va, D, vtaP, (long long)D * Bc * kl.Sp, (long long)Bc * kl.Sp, Bc * S, cf.D, S,
+                                     (long long)kl.Sp, 1.f, c.st));
+      h->launches += 3;
+      if (cf.fmt == A2P_FMT_POSE) {
+        __nv_bfloat16* k2P = reinterpret_cast<__nv_bfloat16*>(lb + kl.k2P);
+        __nv_bfloat16* vt2P = reinterpret_cast<__nv_bfloat16*>(lb + kl.vt2P);
+        A2P_TRY(launch_split_planes(P, lb + kl.k2, D, k2P, (long long)Bc * S2 * D, (long long)Bc * S2, cf.D, 1.f, c.st));
+        A2P_CUDA(cudaMemsetAsync(vt2P, 0, sizeof(__nv_bfloat16) * (size_t)P * D * Bc * kl.S2p, c.st));
+        A2P_TRY(launch_transpose_split(P, lb + kl.v2, D, vt2P, (long long)D * Bc * kl.S2p, (long long)Bc * kl.S2p, Bc * S2, cf.D, S2,
+                                       (long long)kl.S2p, 1.f, c.st));
+        h->launches += 3;
+      }
     }
   }
   A2P_CUDA(cudaMemcpyAsync(base + kl.hidden, cond_hidden, sizeof(float) * Bc * D, cudaMemcpyDeviceToDevice, c.st));
@@ -924,6 +1046,87 @@ int a2p_test_tc_gemm(int terms, int M, int N, int K, int taps, int dil, const fl
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
   for (int i = 0; i < iters; ++i) A2P_TRY(launch_umma_gemm(terms, o, p, TC_F32, sms, st));
+  cudaEventRecord(e1, st);
+  A2P_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_extra) {
+  const size_t Sp = align_up((size_t)S, 8), Xp = 8;
+  return (align_up((size_t)3 * R * T * D, 512) + align_up((size_t)3 * R * S * D, 512) + align_up((size_t)3 * D * R * Sp, 512) +
+          align_up((size_t)3 * R * 8 * D, 512) + align_up((size_t)3 * D * R * Xp, 512)) * 2 + 8192;
+}
+
+int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K,
+                          const float* V, const float* Kx, const float* Vx, float* O, void* scratch, size_t scratch_bytes,
+                          int iters, float* ms_out, void* stream) {
+  if (scratch_bytes < a2p_test_tc_attention_scratch_bytes(R, T, D, S, n_extra)) A2P_FAIL("test_tc_attention: scratch too small");
+  if (n_extra > 8) A2P_FAIL("test_tc_attention: n_extra <= 8");
+  cudaStream_t st = (cudaStream_t)stream;
+  A2P_TRY(init_umma_attn());
+  const long long Sp = (long long)align_up((size_t)S, 8), Xp = 8;
+  __nv_bfloat16* Qp = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* Kp = Qp + align_up((size_t)3 * R * T * D, 512);
+  __nv_bfloat16* Vt = Kp + align_up((size_t)3 * R * S * D, 512);
+  __nv_bfloat16* Kxp = Vt + align_up((size_t)3 * D * R * Sp, 512);
+  __nv_bfloat16* Vxt = Kxp + align_up((size_t)3 * R * 8 * D, 512);
+  A2P_CUDA(cudaMemsetAsync(scratch, 0, scratch_bytes, st));
+  const float sc = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+  A2P_TRY(launch_split_planes(terms, Q, D, Qp, (long long)R * T * D, (long long)R * T, D, sc, st));
+  A2P_TRY(launch_split_planes(terms, K, D, Kp, (long long)R * S * D, (long long)R * S, D, 1.f, st));
+  A2P_TRY(launch_transpose_split(terms, V, D, Vt, (long long)D * R * Sp, (long long)R * Sp, R * S, D, S, Sp, 1.f, st));
+  if (n_extra > 0) {
+    for (int r = 0; r < R; ++r)
+      A2P_TRY(launch_split_planes(terms, Kx + (size_t)r * n_extra * D, D, Kxp + (size_t)r * 8 * D, (long long)R * 8 * D, n_extra, D, 1.f, st));
+    A2P_TRY(launch_transpose_split(terms, Vx, D, Vxt, (long long)D * R * Xp, (long long)R * Xp, R * n_extra, D, n_extra, Xp, 1.f, st));
+  }
+  TcAttnOperands o{};
+  o.Q = Qp; o.q_rows = (long long)R * T; o.q_ld = D; o.q_plane_stride = (long long)R * T * D;
+  o.K[0] = Kp; o.k_rows[0] = (long long)R * S; o.k_ld[0] = D; o.k_plane_stride[0] = (long long)R * S * D; o.K[1] = nullptr;
+  o.Vt[0] = Vt; o.vt_cols[0] = (long long)R * Sp; o.vt_ld[0] = (long long)R * Sp; o.vt_plane_stride[0] = (long long)D * R * Sp; o.Vt[1] = nullptr;
+  o.vt_rows = D;
+  if (n_extra > 0) {
+    o.Kx = Kxp; o.kx_rows = (long long)R * 8; o.kx_ld = D; o.kx_plane_stride = (long long)R * 8 * D;
+    o.Vx = Vxt; o.vx_rows = D; o.vx_cols = (long long)R * Xp; o.vx_ld = (long long)R * Xp; o.vx_plane_stride = (long long)D * R * Xp;
+  }
+  TcAttnParams p{};
+  p.T = T; p.R = R; p.D = D; p.dh = dh; p.rows_per_branch = R; p.q_col0 = 0; p.k_col0 = 0; p.n_keys = S; p.n_extra = n_extra;
+  p.k_row_stride[0] = S; p.v_col_stride[0] = Sp; p.kx_col0 = 0; p.kx_row_stride = 8; p.vx_row0 = 0; p.vx_col_stride = (int)Xp;
+  p.O = O; p.o_ld = D; p.Op = nullptr;
+  A2P_TRY(launch_umma_attn(terms, o, p, st));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) A2P_TRY(launch_umma_attn(terms, o, p, st));
+  cudaEventRecord(e1, st);
+  A2P_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+int a2p_test_simt_attention(int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K, const float* V,
+                            const float* Kx, const float* Vx, float* O, int iters, float* ms_out, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  A2P_TRY(init_attn_simt());
+  AttnParams a{};
+  a.Q = Q; a.q_ld = D; a.q_sample_stride = (long long)T * D;
+  a.K.base[0] = K; a.K.stride[0] = (long long)S * D; a.K.rows_per_branch = R; a.V = a.K; a.V.base[0] = V;
+  a.kv_ld = D; a.S_main = S; a.Kx = n_extra ? Kx : nullptr; a.Vx = n_extra ? Vx : nullptr; a.x_ld = D;
+  a.x_sample_stride = (long long)n_extra * D; a.S_extra = n_extra;
+  a.O = O; a.o_ld = D; a.o_sample_stride = (long long)T * D; a.T = T; a.H = D / dh; a.R = R;
+  a.scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
+  A2P_TRY(launch_attn_simt(a, dh, st));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) A2P_TRY(launch_attn_simt(a, dh, st));
   cudaEventRecord(e1, st);
   A2P_CUDA(cudaStreamSynchronize(st));
   float ms = 0.f;

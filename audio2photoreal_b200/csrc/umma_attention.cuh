@@ -1,0 +1,391 @@
+// K1 core on the 5th-gen tensor cores: softmax(Q K^T) V for one (sample-row, 64-column head group, 128-query
+// tile) per CTA, split-bf16 operands (TERMS planes), fp32 accumulation in TMEM, fp32 online softmax in registers.
+//
+//   warp 0    TMA producer : Q tile once; per 64-key block the K tile [64 keys][64 cols] and the V^T tile
+//                            [64 cols][64 keys] of every plane (SWIZZLE_128B), 2-stage ring
+//   warp 1    MMA issuer   : S = Q K^T (M128 x N64, K = dh) into one of 2 TMEM S buffers, then O_blk = P V
+//                            (M128 x N=dh, K = 64 keys) into one of 2 TMEM PV buffers; S(i+1) is issued before
+//                            PV(i) so the tensor pipe works while the softmax warps process S(i)
+//   warp 2    TMEM alloc   : 256 columns (2 x 64 S + 2 x 64 PV)
+//   warps 4-7 softmax      : thread = query row; tcgen05.ld S -> running max / exp2 / sum -> P split into bf16
+//                            planes written to smem in the UMMA K-major SWIZZLE_128B layout -> after PV(i):
+//                            O = O * alpha + PV (O lives in registers, so no TMEM read-modify-write)
+// A head group is 64 consecutive model columns (2 heads at dh = 32, 1 head at dh = 64): the heads of a group
+// share the K / V^T tiles and are processed back to back.  Keys come from a cached "main" memory plus an
+// optional "extra" source (the 2 per-step time tokens, model/diffusion.py:392-393).
+// Q must be pre-scaled by log2(e)/sqrt(dh) (done by the Q-projection GEMM epilogue).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+#include "umma_gemm.cuh"
+
+namespace a2p {
+
+struct TcAttnParams {
+  int T, R, D, dh, rows_per_branch;
+  int q_col0;                 // column of head-group 0 inside the Q tensor
+  int k_col0;                 // column of head-group 0 inside the main K tensor (self-attn: D)
+  int n_keys, n_extra;
+  long long k_row_stride[2];  // rows between consecutive samples in the main K tensor per branch (0 = shared)
+  long long v_col_stride[2];  // columns between consecutive samples in the main V^T tensor per branch
+  int kx_col0, kx_row_stride; // extra K tensor: column of group 0 (= layer * D), rows per sample (2)
+  int vx_row0, vx_col_stride; // extra V^T tensor: row of group 0 (= layer * D), columns per sample (2)
+  __nv_bfloat16* Op; long long op_plane_stride; long long o_ld;   // output planes [TERMS][R*T][o_ld]
+  float* O;                                                       // optional fp32 output [R*T][o_ld] (tests)
+};
+
+template <int TERMS>
+struct TcAttnCfg {
+  static constexpr int NPROD = TERMS == 1 ? 1 : (TERMS == 2 ? 3 : 6);
+  static constexpr int NPBUF = TERMS == 3 ? 1 : 2;
+  static constexpr int Q_BYTES = TERMS * 128 * 128;            // [128 rows][64 cols] bf16 per plane
+  static constexpr int KV_STAGE_BYTES = TERMS * 2 * 64 * 128;  // K tile + V^T tile per plane (8 KB each)
+  static constexpr int P_BYTES = TERMS * 128 * 128;            // [128 rows][64 keys] bf16 per plane
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGE_BYTES + NPBUF * P_BYTES + 1024 + 256;
+};
+
+template <int TERMS, int DH>
+__global__ void __launch_bounds__(256, 1)
+umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                 const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV0,
+                 const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmKx,
+                 const __grid_constant__ CUtensorMap tmVx, TcAttnParams p) {
+  using Cfg = TcAttnCfg<TERMS>;
+  constexpr int G = 64 / DH;          // heads per group
+  constexpr int NPB = Cfg::NPBUF;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::Q_BYTES;
+  uint8_t* sP = sKV + 2 * Cfg::KV_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NPB * Cfg::P_BYTES);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* kv_full = bars + 1;       // [2]
+  uint64_t* kv_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;        // [2]
+  uint64_t* s_empty = bars + 7;       // [2]
+  uint64_t* p_full = bars + 9;        // [2]
+  uint64_t* p_empty = bars + 11;      // [2]
+  uint64_t* pv_full = bars + 13;      // [2]
+  uint64_t* pv_empty = bars + 15;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, g = blockIdx.y, r = blockIdx.z;
+  const int br = r >= p.rows_per_branch ? 1 : 0;
+  const int rr = r - br * p.rows_per_branch;
+  const int nb_main = ceil_div(p.n_keys, 64);
+  const int n_blocks = nb_main + (p.n_extra > 0 ? 1 : 0);
+  const int n_iter = n_blocks * G;
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmQ);
+    umma::prefetch_tmap(br ? &tmK1 : &tmK0);
+    umma::prefetch_tmap(br ? &tmV1 : &tmV0);
+  }
+  if (warp == 1 && lane == 0) {
+    umma::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      umma::mbar_init(&kv_full[i], 1); umma::mbar_init(&kv_empty[i], 1);
+      umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 128);
+      umma::mbar_init(&p_full[i], 128); umma::mbar_init(&p_empty[i], 1);
+      umma::mbar_init(&pv_full[i], 1); umma::mbar_init(&pv_empty[i], 128);
+    }
+    umma::fence_barrier_init();
+  }
+  if (warp == 2) umma::tmem_alloc<256>(tmem_slot);
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmS = tmem_base, tmPV = tmem_base + 128;   // S buffers: +0, +64 ; PV buffers: +128, +192
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      umma::mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int i = 0; i < TERMS; ++i)
+        umma::tma_load_3d(&tmQ, q_full, sQ + i * 16384, p.q_col0 + g * 64, r * p.T + q0, i);
+      const CUtensorMap* tK = br ? &tmK1 : &tmK0;
+      const CUtensorMap* tV = br ? &tmV1 : &tmV0;
+      const int k_row_base = (int)(rr * p.k_row_stride[br]);
+      const int v_col_base = (int)(rr * p.v_col_stride[br]);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int st = j & 1;
+        umma::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+        umma::mbar_expect_tx(&kv_full[st], Cfg::KV_STAGE_BYTES);
+        uint8_t* sk = sKV + st * Cfg::KV_STAGE_BYTES;
+        uint8_t* sv = sk + TERMS * 8192;
+        if (j < nb_main) {
+#pragma unroll
+          for (int i = 0; i < TERMS; ++i) umma::tma_load_3d(tK, &kv_full[st], sk + i * 8192, p.k_col0 + g * 64, k_row_base + j * 64, i);
+#pragma unroll
+          for (int i = 0; i < TERMS; ++i) umma::tma_load_3d(tV, &kv_full[st], sv + i * 8192, v_col_base + j * 64, g * 64, i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < TERMS; ++i) umma::tma_load_3d(&tmKx, &kv_full[st], sk + i * 8192, p.kx_col0 + g * 64, r * p.kx_row_stride, i);
+#pragma unroll
+          for (int i = 0; i < TERMS; ++i) umma::tma_load_3d(&tmVx, &kv_full[st], sv + i * 8192, r * p.vx_col_stride, p.vx_row0 + g * 64, i);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);
+      constexpr uint32_t idPV = umma::idesc_bf16_f32(128, DH);
+      const uint32_t aQ = umma::smem_u32(sQ);
+      auto issue_pv = [&](int i) {
+        const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
+        const uint32_t sv = umma::smem_u32(sKV + (j & 1) * Cfg::KV_STAGE_BYTES + TERMS * 8192);
+        const uint32_t sp = umma::smem_u32(sP + pb * Cfg::P_BYTES);
+        umma::mbar_wait(&p_full[pb], (i / NPB) & 1);
+        umma::mbar_wait(&pv_empty[b], ((i >> 1) & 1) ^ 1);
+        umma::fence_after();
+#pragma unroll
+        for (int pr = 0; pr < Cfg::NPROD; ++pr) {
+          const uint64_t da = umma::smem_desc_sw128(sp + kProdA[pr] * 16384);
+          const uint64_t db = umma::smem_desc_sw128(sv + kProdB[pr] * 8192 + hh * DH * 128);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma::mma_bf16(tmPV + b * 64, da + 2 * k, db + 2 * k, idPV, (pr | k) != 0 ? 1u : 0u);
+        }
+        umma::mma_commit(&pv_full[b]);
+        umma::mma_commit(&p_empty[pb]);
+        if (hh == G - 1) umma::mma_commit(&kv_empty[j & 1]);
+      };
+      umma::mbar_wait(q_full, 0);
+      for (int i = 0; i < n_iter; ++i) {
+        const int j = i / G, hh = i - j * G, b = i & 1;
+        if (hh == 0) umma::mbar_wait(&kv_full[j & 1], (j >> 1) & 1);
+        umma::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
+        umma::fence_after();
+        const uint32_t sk = umma::smem_u32(sKV + (j & 1) * Cfg::KV_STAGE_BYTES);
+#pragma unroll
+        for (int pr = 0; pr < Cfg::NPROD; ++pr) {
+          const uint64_t da = umma::smem_desc_sw128(aQ + kProdA[pr] * 16384) + hh * (DH / 8);
+          const uint64_t db = umma::smem_desc_sw128(sk + kProdB[pr] * 8192) + hh * (DH / 8);
+#pragma unroll
+          for (int k = 0; k < DH / 16; ++k) umma::mma_bf16(tmS + b * 64, da + 2 * k, db + 2 * k, idS, (pr | k) != 0 ? 1u : 0u);
+        }
+        umma::mma_commit(&s_full[b]);
+        if (i > 0) issue_pv(i - 1);
+      }
+      issue_pv(n_iter - 1);
+    }
+  } else if (warp >= 4) {
+    // ================= softmax / output =================
+    const int wq = warp & 3;
+    const int trow = wq * 32 + lane;                 // query row inside the tile == TMEM lane
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    float m[G], l[G], o[G][DH];
+#pragma unroll
+    for (int h = 0; h < G; ++h) {
+      m[h] = -INFINITY; l[h] = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) o[h][c] = 0.f;
+    }
+    float alpha_pend = 1.f;
+    auto consume_pv = [&](int i, float alpha) {
+      const int b = i & 1, hh = i % G;
+      umma::mbar_wait(&pv_full[b], (i >> 1) & 1);
+      umma::fence_after();
+      float v[DH];
+      umma::tmem_ld32(tmPV + lane_addr + b * 64, v);
+      if (DH == 64) umma::tmem_ld32(tmPV + lane_addr + b * 64 + 32, v + (DH == 64 ? 32 : 0));
+      umma::tmem_ld_wait();
+      umma::fence_before();
+      umma::mbar_arrive(&pv_empty[b]);
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+        if (h == hh) {
+#pragma unroll
+          for (int c = 0; c < DH; ++c) o[h][c] = o[h][c] * alpha + v[c];
+        }
+    };
+    for (int i = 0; i < n_iter; ++i) {
+      const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
+      umma::mbar_wait(&s_full[b], (i >> 1) & 1);
+      umma::fence_after();
+      float s[64];
+      umma::tmem_ld32(tmS + lane_addr + b * 64, s);
+      umma::tmem_ld32(tmS + lane_addr + b * 64 + 32, s + 32);
+      umma::tmem_ld_wait();
+      umma::fence_before();
+      umma::mbar_arrive(&s_empty[b]);
+      const int nvalid = (j < nb_main) ? ::min(64, p.n_keys - j * 64) : p.n_extra;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        s[c] = c < nvalid ? s[c] : -INFINITY;
+        mx = fmaxf(mx, s[c]);
+      }
+      float mold = 0.f, mnew = 0.f;
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+        if (h == hh) { mold = m[h]; mnew = fmaxf(mold, mx); m[h] = mnew; }
+      const float alpha = exp2f(mold - mnew);
+      float rs = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) { s[c] = exp2f(s[c] - mnew); rs += s[c]; }
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+        if (h == hh) l[h] = l[h] * alpha + rs;
+      // P planes -> smem (K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7))
+      umma::mbar_wait(&p_empty[pb], ((i / NPB) & 1) ^ 1);
+      uint8_t* pbase = sP + pb * Cfg::P_BYTES + trow * 128;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        __nv_bfloat16 pl[TERMS][8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          __nv_bfloat16 sp[TERMS];
+          umma::split_bf16<TERMS>(s[ch * 8 + e], sp);
+#pragma unroll
+          for (int t = 0; t < TERMS; ++t) pl[t][e] = sp[t];
+        }
+#pragma unroll
+        for (int t = 0; t < TERMS; ++t)
+          *reinterpret_cast<uint4*>(pbase + t * 16384 + ((ch ^ (trow & 7)) << 4)) = *reinterpret_cast<const uint4*>(pl[t]);
+      }
+      umma::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      umma::mbar_arrive(&p_full[pb]);
+      if (i > 0) consume_pv(i - 1, alpha_pend);
+      alpha_pend = alpha;
+    }
+    consume_pv(n_iter - 1, alpha_pend);
+    // ---- normalise and store
+    const int row = q0 + trow;
+    if (row < p.T) {
+      const long long grow = (long long)r * p.T + row;
+#pragma unroll
+      for (int h = 0; h < G; ++h) {
+        const float inv = 1.f / l[h];
+        const int col = g * 64 + h * DH;
+        if (p.O) {
+          float* dst = p.O + grow * p.o_ld + col;
+#pragma unroll
+          for (int c = 0; c < DH; c += 4)
+            *reinterpret_cast<float4*>(dst + c) = make_float4(o[h][c] * inv, o[h][c + 1] * inv, o[h][c + 2] * inv, o[h][c + 3] * inv);
+        }
+        if (p.Op) {
+#pragma unroll
+          for (int c = 0; c < DH; c += 8) {
+            __nv_bfloat16 pl[TERMS][8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              __nv_bfloat16 sp[TERMS];
+              umma::split_bf16<TERMS>(o[h][c + e] * inv, sp);
+#pragma unroll
+              for (int t = 0; t < TERMS; ++t) pl[t][e] = sp[t];
+            }
+#pragma unroll
+            for (int t = 0; t < TERMS; ++t)
+              *reinterpret_cast<uint4*>(p.Op + t * p.op_plane_stride + grow * p.o_ld + col + c) = *reinterpret_cast<const uint4*>(pl[t]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    umma::fence_after();
+    umma::tmem_dealloc<256>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct TcAttnOperands {
+  const __nv_bfloat16* Q; long long q_rows, q_ld, q_plane_stride;                 // [P][q_rows][q_ld]
+  const __nv_bfloat16* K[2]; long long k_rows[2], k_ld[2], k_plane_stride[2];     // main K per branch
+  const __nv_bfloat16* Vt[2]; long long vt_cols[2], vt_ld[2], vt_plane_stride[2]; // main V^T per branch: [P][vt_rows][vt_ld]
+  long long vt_rows;
+  const __nv_bfloat16* Kx; long long kx_rows, kx_ld, kx_plane_stride;             // extra K  [P][kx_rows][kx_ld]
+  const __nv_bfloat16* Vx; long long vx_rows, vx_cols, vx_ld, vx_plane_stride;    // extra V^T [P][vx_rows][vx_ld]
+};
+
+template <int TERMS, int DH>
+int launch_umma_attn_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
+  using Cfg = TcAttnCfg<TERMS>;
+  CUtensorMap tq, tk[2], tv[2], tkx, tvx;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  A2P_TRY(make_tmap_bf16_3d(&tq, o.Q, o.q_ld, o.q_rows, TERMS, o.q_ld, o.q_plane_stride, 64, 128, sw));
+  for (int b = 0; b < 2; ++b) {
+    const int s = o.K[b] ? b : 0;
+    A2P_TRY(make_tmap_bf16_3d(&tk[b], o.K[s], o.k_ld[s], o.k_rows[s], TERMS, o.k_ld[s], o.k_plane_stride[s], 64, 64, sw));
+    A2P_TRY(make_tmap_bf16_3d(&tv[b], o.Vt[s], o.vt_cols[s], o.vt_rows, TERMS, o.vt_ld[s], o.vt_plane_stride[s], 64, 64, sw));
+  }
+  if (o.Kx) {
+    A2P_TRY(make_tmap_bf16_3d(&tkx, o.Kx, o.kx_ld, o.kx_rows, TERMS, o.kx_ld, o.kx_plane_stride, 64, 64, sw));
+    A2P_TRY(make_tmap_bf16_3d(&tvx, o.Vx, o.vx_cols, o.vx_rows, TERMS, o.vx_ld, o.vx_plane_stride, 64, 64, sw));
+  } else {
+    tkx = tk[0]; tvx = tv[0];
+  }
+  dim3 grid(ceil_div(p.T, 128), p.D / 64, p.R);
+  umma_attn_kernel<TERMS, DH><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tq, tk[0], tk[1], tv[0], tv[1], tkx, tvx, p);
+  A2P_CUDA(cudaGetLastError());
+  return 0;
+}
+
+inline int launch_umma_attn(int terms, const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
+  if (p.dh == 32) {
+    if (terms == 2) return launch_umma_attn_t<2, 32>(o, p, st);
+    if (terms == 3) return launch_umma_attn_t<3, 32>(o, p, st);
+    if (terms == 1) return launch_umma_attn_t<1, 32>(o, p, st);
+  } else if (p.dh == 64) {
+    if (terms == 2) return launch_umma_attn_t<2, 64>(o, p, st);
+    if (terms == 3) return launch_umma_attn_t<3, 64>(o, p, st);
+    if (terms == 1) return launch_umma_attn_t<1, 64>(o, p, st);
+  }
+  A2P_FAIL("umma_attn: unsupported terms=%d dh=%d", terms, p.dh);
+}
+
+inline int init_umma_attn() {
+#define A2P_SET(T, H) A2P_CUDA(cudaFuncSetAttribute(umma_attn_kernel<T, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcAttnCfg<T>::SMEM_BYTES));
+  A2P_SET(1, 32) A2P_SET(2, 32) A2P_SET(3, 32) A2P_SET(1, 64) A2P_SET(2, 64) A2P_SET(3, 64)
+#undef A2P_SET
+  return 0;
+}
+
+// fp32 [rows][cols] (row stride ld)  ->  bf16 planes of the TRANSPOSE: dst[t][c][col_base(r)] with
+// column index = (r / rows_per_sample) * sample_col_stride + r % rows_per_sample; untouched pad columns must be
+// zeroed by the caller once (P = 0 times non-finite garbage would poison the PV product).
+template <int TERMS>
+__global__ void transpose_split_kernel(const float* __restrict__ src, long long ld, __nv_bfloat16* __restrict__ dst,
+                                       long long plane_stride, long long dst_ld, int rows, int cols, int rows_per_sample,
+                                       long long sample_col_stride, float scale) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[(long long)r * ld + c] * scale : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      __nv_bfloat16 sp[TERMS];
+      umma::split_bf16<TERMS>(tile[threadIdx.x][i], sp);
+      const long long col = (long long)(r / rows_per_sample) * sample_col_stride + (r % rows_per_sample);
+#pragma unroll
+      for (int t = 0; t < TERMS; ++t) dst[t * plane_stride + (long long)c * dst_ld + col] = sp[t];
+    }
+  }
+}
+
+inline int launch_transpose_split(int terms, const float* src, long long ld, __nv_bfloat16* dst, long long plane_stride,
+                                  long long dst_ld, int rows, int cols, int rows_per_sample, long long sample_col_stride,
+                                  float scale, cudaStream_t st) {
+  dim3 grid(ceil_div(rows, 32), ceil_div(cols, 32)), block(32, 8);
+  if (terms == 1) transpose_split_kernel<1><<<grid, block, 0, st>>>(src, ld, dst, plane_stride, dst_ld, rows, cols, rows_per_sample, sample_col_stride, scale);
+  else if (terms == 2) transpose_split_kernel<2><<<grid, block, 0, st>>>(src, ld, dst, plane_stride, dst_ld, rows, cols, rows_per_sample, sample_col_stride, scale);
+  else if (terms == 3) transpose_split_kernel<3><<<grid, block, 0, st>>>(src, ld, dst, plane_stride, dst_ld, rows, cols, rows_per_sample, sample_col_stride, scale);
+  else A2P_FAIL("transpose_split: terms must be 1..3");
+  A2P_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace a2p

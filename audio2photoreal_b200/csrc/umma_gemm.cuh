@@ -36,6 +36,8 @@ struct TcGemmParams {
   const float* film; long long film_ld; int film_scale_off, film_shift_off, rows_per_sample;
   const float* skip; long long ldskip;
   float out_scale, slope;
+  int scale_ncols;   // out_scale applies to columns < scale_ncols (0 = all columns)
+  int bias_per_row;  // bias indexed by output row (swapped-operand GEMMs producing a transposed result)
 };
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
@@ -46,7 +48,7 @@ struct TcCfg {
   static constexpr int NPROD = TERMS == 1 ? 1 : (TERMS == 2 ? 3 : 6);
   static constexpr int STAGES = TERMS == 1 ? 6 : (TERMS == 2 ? 3 : 2);
   static constexpr int STAGE_BYTES = 2 * TERMS * TC_TILE_BYTES;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
 };
 
 __device__ __constant__ int8_t kProdA[6] = {0, 0, 1, 0, 2, 1};
@@ -64,6 +66,7 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
   uint64_t* tfull = bars + 2 * Cfg::STAGES;    // [2]
   uint64_t* tempty = tfull + 2;                // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* stage_tile = reinterpret_cast<float*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256);   // 4 warps x [32][36] fp32
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = ceil_div(p.N, TC_BN), tiles_m = ceil_div(p.M, TC_BM);
@@ -144,78 +147,78 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
       const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * TC_BN;
       umma::mbar_wait(&tfull[acc], acc_phase);
       umma::fence_after();
-      const int row = m0 + wq * 32 + lane;
-      const bool row_ok = row < p.M;
-      const float* fs = nullptr;
-      if (EPI == TC_FILM && row_ok) fs = p.film + (long long)(row / p.rows_per_sample) * p.film_ld;
+      // TMEM gives each thread one ROW (32 consecutive columns).  Storing that way touches 32 different 128-B
+      // lines per instruction, so the 32x32 chunk is transposed through a per-warp smem staging tile
+      // ([32][36] floats, 128-bit accesses conflict-free both ways) and written 4 rows x 128 B per instruction.
+      float* tw = stage_tile + wq * (32 * 36);
+      const int rsub = lane >> 3, c4 = (lane & 7) * 4;
 #pragma unroll 1
       for (int c = 0; c < TC_BN / 32; ++c) {
-        float v[32];
-        umma::tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * TC_BN + c * 32, v);
-        umma::tmem_ld_wait();
-        const int col0 = n0 + c * 32;
-        if (row_ok && col0 < p.N) {
-          // N is a multiple of 8, so 8-wide groups are either fully inside or fully outside
+        const int col = n0 + c * 32 + c4;
+        if (n0 + c * 32 >= p.N) break;   // warp-uniform
+        {
+          float v[32];
+          umma::tmem_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + acc * TC_BN + c * 32, v);
+          umma::tmem_ld_wait();
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = col0 + g * 8;
-            if (col >= p.N) break;
-            float o[8];
+          for (int q = 0; q < 8; ++q)
+            *reinterpret_cast<float4*>(tw + lane * 36 + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        __syncwarp();
+        const bool col_ok = col < p.N;
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias && col_ok && !p.bias_per_row) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        const float oscale = (p.scale_ncols == 0 || col < p.scale_ncols) ? p.out_scale : 1.f;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) o[j] = v[g * 8 + j] + (p.bias ? __ldg(p.bias + col + j) : 0.f);
-            if (EPI == TC_F32) {
-              float* cp = p.C + (long long)row * p.ldc + col;
-              *reinterpret_cast<float4*>(cp) = make_float4(o[0] * p.out_scale, o[1] * p.out_scale, o[2] * p.out_scale, o[3] * p.out_scale);
-              *reinterpret_cast<float4*>(cp + 4) = make_float4(o[4] * p.out_scale, o[5] * p.out_scale, o[6] * p.out_scale, o[7] * p.out_scale);
-            } else if (EPI == TC_FILM) {
-              float* cp = p.C + (long long)row * p.ldc + col;
-              float4 x0 = *reinterpret_cast<const float4*>(cp), x1 = *reinterpret_cast<const float4*>(cp + 4);
-              const float xs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + rsub;
+          const int row = m0 + wq * 32 + r;
+          if (row >= p.M || !col_ok) continue;
+          const float4 a = *reinterpret_cast<const float4*>(tw + r * 36 + c4);
+          if (p.bias_per_row && p.bias) { const float br_ = __ldg(p.bias + row); bb = make_float4(br_, br_, br_, br_); }
+          float o[4] = {a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w};
+          if (EPI == TC_F32) {
+            *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) =
+                make_float4(o[0] * oscale, o[1] * oscale, o[2] * oscale, o[3] * oscale);
+          } else if (EPI == TC_FILM) {
+            const float* fs = p.film + (long long)(row / p.rows_per_sample) * p.film_ld;
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(fs + p.film_scale_off + col));
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(fs + p.film_shift_off + col));
+            float* cp = p.C + (long long)row * p.ldc + col;
+            const float4 x = *reinterpret_cast<const float4*>(cp);
+            *reinterpret_cast<float4*>(cp) = make_float4(x.x + ((sc.x + 1.f) * o[0] + sh.x), x.y + ((sc.y + 1.f) * o[1] + sh.y),
+                                                         x.z + ((sc.z + 1.f) * o[2] + sh.z), x.w + ((sc.w + 1.f) * o[3] + sh.w));
+          } else {
+            if (EPI == TC_GELU_PLANES) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float sc = __ldg(fs + p.film_scale_off + col + j), sh = __ldg(fs + p.film_shift_off + col + j);
-                o[j] = xs[j] + ((sc + 1.f) * o[j] + sh);
+              for (int j = 0; j < 4; ++j) o[j] = gelu_erf(o[j]);
+            } else if (EPI == TC_LRELU_PLANES) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * p.slope;
+              if (p.skip) {
+                const float4 sk = *reinterpret_cast<const float4*>(p.skip + (long long)row * p.ldskip + col);
+                o[0] = (sk.x + o[0]) / 2.0f; o[1] = (sk.y + o[1]) / 2.0f; o[2] = (sk.z + o[2]) / 2.0f; o[3] = (sk.w + o[3]) / 2.0f;
               }
-              *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<float4*>(cp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              if (p.C) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
             } else {
-              if (EPI == TC_GELU_PLANES) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = gelu_erf(o[j]);
-              } else if (EPI == TC_LRELU_PLANES) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * p.slope;
-                if (p.skip) {
-                  const float* sp = p.skip + (long long)row * p.ldskip + col;
-                  float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
-                  const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                  for (int j = 0; j < 8; ++j) o[j] = (ss[j] + o[j]) / 2.0f;
-                }
-                if (p.C) {
-                  float* cp = p.C + (long long)row * p.ldc + col;
-                  *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
-                  *reinterpret_cast<float4*>(cp + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] *= p.out_scale;
-              }
-              __nv_bfloat16 pl[TERMS][8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                __nv_bfloat16 s[TERMS];
-                umma::split_bf16<TERMS>(o[j], s);
-#pragma unroll
-                for (int i = 0; i < TERMS; ++i) pl[i][j] = s[i];
-              }
-#pragma unroll
-              for (int i = 0; i < TERMS; ++i)
-                *reinterpret_cast<uint4*>(p.Cp + i * p.cp_plane_stride + (long long)row * p.ldcp + col) =
-                    *reinterpret_cast<const uint4*>(pl[i]);
+              for (int j = 0; j < 4; ++j) o[j] *= oscale;
             }
+            __nv_bfloat16 pl[TERMS][4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              __nv_bfloat16 sp[TERMS];
+              umma::split_bf16<TERMS>(o[j], sp);
+#pragma unroll
+              for (int i = 0; i < TERMS; ++i) pl[i][j] = sp[i];
+            }
+#pragma unroll
+            for (int i = 0; i < TERMS; ++i)
+              *reinterpret_cast<uint2*>(p.Cp + i * p.cp_plane_stride + (long long)row * p.ldcp + col) =
+                  *reinterpret_cast<const uint2*>(pl[i]);
           }
         }
+        __syncwarp();
       }
       umma::fence_before();
       umma::mbar_arrive(&tempty[acc]);

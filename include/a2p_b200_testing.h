@@ -17,6 +17,17 @@ int a2p_test_tc_gemm(int terms, int M, int N, int K, int taps, int dil, const fl
 int a2p_test_sgemm(int M, int N, int K, int taps, int dil, const float* A, const float* W, const float* bias, float* C,
                    int iters, float* ms_out, void* stream);
 
+/* softmax(QK^T/sqrt(dh))V with the split-bf16 tcgen05 attention kernel.  fp32 inputs Q [R,T,D], K,V [R,S,D],
+ * optional extra keys Kx,Vx [R,n_extra,D]; fp32 output O [R,T,D].  The hook does the splits / transposes the
+ * engine does (Q pre-scaled).  Average kernel time over `iters` launches in *ms_out. */
+size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_extra);
+int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K,
+                          const float* V, const float* Kx, const float* Vx, float* O, void* scratch, size_t scratch_bytes,
+                          int iters, float* ms_out, void* stream);
+/* the exact-fp32 FFMA attention on the same inputs */
+int a2p_test_simt_attention(int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K, const float* V,
+                            const float* Kx, const float* Vx, float* O, int iters, float* ms_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,61 @@
+"""On-GPU unit test + timing of the split-bf16 tcgen05 attention against fp64 torch and the FFMA kernel."""
+import ctypes as C, os, sys, math
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from audio2photoreal_b200 import _lib
+
+lib = _lib.load()
+vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+lib.a2p_test_tc_attention_scratch_bytes.argtypes = [i32] * 5
+lib.a2p_test_tc_attention_scratch_bytes.restype = sz
+lib.a2p_test_tc_attention.argtypes = [i32] * 7 + [vp] * 7 + [sz, i32, C.POINTER(C.c_float), vp]
+lib.a2p_test_simt_attention.argtypes = [i32] * 6 + [vp] * 6 + [i32, C.POINTER(C.c_float), vp]
+
+def run(terms, R, T, D, dh, S, nx, iters=5, qscale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(R * 1000 + T + S)
+    Q = torch.randn(R, T, D, device="cuda", generator=g) * qscale
+    K = torch.randn(R, S, D, device="cuda", generator=g)
+    V = torch.randn(R, S, D, device="cuda", generator=g)
+    Kx = torch.randn(R, max(nx, 1), D, device="cuda", generator=g)
+    Vx = torch.randn(R, max(nx, 1), D, device="cuda", generator=g)
+    O = torch.full((R, T, D), float("nan"), device="cuda")
+    nb = lib.a2p_test_tc_attention_scratch_bytes(R, T, D, S, nx)
+    scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    ms = C.c_float()
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(),
+                                         Vx.data_ptr(), O.data_ptr(), scratch.data_ptr(), nb, iters, C.byref(ms), st))
+    H = D // dh
+    Kf = torch.cat([K, Kx[:, :nx]], 1) if nx else K
+    Vf = torch.cat([V, Vx[:, :nx]], 1) if nx else V
+    sp = lambda t: t.double().view(R, -1, H, dh).transpose(1, 2)
+    att = torch.softmax(sp(Q) @ sp(Kf).transpose(-1, -2) / math.sqrt(dh), -1) @ sp(Vf)
+    ref = att.transpose(1, 2).reshape(R, T, D)
+    err = (O.double() - ref).abs().max().item()
+    O2 = torch.empty_like(O)
+    ms2 = C.c_float()
+    _lib.check(lib.a2p_test_simt_attention(R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(), Vx.data_ptr(),
+                                           O2.data_ptr(), iters, C.byref(ms2), st))
+    err2 = (O2.double() - ref).abs().max().item()
+    fl = 4.0 * R * T * (S + nx) * D
+    print(f"terms={terms} R={R} T={T} D={D} dh={dh} S={S}+{nx}: tc max|d|={err:.3e} {ms.value*1e3:.1f}us {fl/ms.value/1e9:.1f} TF/s alg | "
+          f"ffma max|d|={err2:.3e} {ms2.value*1e3:.1f}us {fl/ms2.value/1e9:.1f} TF/s", flush=True)
+
+if __name__ == "__main__":
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if which in ("all", "small"):
+        run(2, 1, 128, 64, 32, 64, 0, iters=1)       # one CTA, one key block, one group (2 heads)
+        run(2, 1, 128, 64, 64, 64, 0, iters=1)       # dh = 64
+        run(2, 1, 128, 64, 32, 200, 0, iters=1)      # several key blocks + ragged tail
+        run(2, 2, 100, 256, 32, 77, 2, iters=1)      # ragged T, extra keys
+        run(3, 2, 100, 256, 32, 77, 2, iters=1)
+        run(1, 2, 100, 256, 32, 77, 2, iters=1)
+        run(2, 2, 200, 512, 64, 211, 2, iters=1)     # face geometry
+    if which in ("all", "big"):
+        for terms in (2, 3):
+            run(terms, 16, 600, 256, 32, 1998, 2)      # audio cross-attention, B=8 CFG
+            run(terms, 16, 600, 256, 32, 600, 0)       # self-attention
+            run(terms, 16, 600, 256, 32, 20, 0)        # keyframe cross-attention
+            run(terms, 4, 600, 512, 64, 1998, 2)       # face
+        run(2, 16, 600, 256, 32, 1998, 2, qscale=4.0)  # peaky softmax
+    print("DONE")
