@@ -68,6 +68,7 @@ struct a2p_denoiser {
   // derived arena
   float *film_w = nullptr, *film_b = nullptr, *ttk_w = nullptr, *ttk_b = nullptr, *ttv_w = nullptr, *ttv_b = nullptr;
   float* conv_w[6]{};
+  float* conv_t[6]{};   // tap-major fp32 copies, keys of the split planes
   float2* rope_tab = nullptr;
   std::map<const float*, __nv_bfloat16*> wplanes;  // fp32 weight -> split-bf16 planes [P][rows][cols] (plane stride = numel)
   std::map<const float*, long long> wnumel;
@@ -85,13 +86,18 @@ namespace {
 
 // ---------------------------------------------------------------- arena layouts
 struct PackedLayout {
-  size_t film_w, film_b, ttk_w, ttk_b, ttv_w, ttv_b, conv_w[6], rope, planes, planes_bytes, total;
+  size_t film_w, film_b, ttk_w, ttk_b, ttv_w, ttv_b, conv_w[6], conv_t[6], rope, planes, planes_bytes, total;
 };
 // elements of every weight that gets split-bf16 planes
 size_t split_weight_elems(const a2p_model_cfg& c) {
   const size_t D = c.D, FF = c.FF, C = c.C;
   size_t per_layer = 2 * (3 * D * D + D * D) + 2 * FF * D + (c.fmt == A2P_FMT_POSE ? 4 * D * D : 0);
-  return per_layer * c.L + 2 * D * C;
+  size_t conv = 0;
+  if (c.fmt == A2P_FMT_POSE) {
+    const size_t cm = C > 256 ? C : 256;
+    conv = 3 * (cm * C * 2 + C * C * 4) + C * C;   // [3][Cout][Cin] per TCN layer + the 1x1 final conv
+  }
+  return per_layer * c.L + 2 * D * C + conv;
 }
 PackedLayout packed_layout(const a2p_model_cfg& c) {
   PackedLayout p{};
@@ -108,6 +114,7 @@ PackedLayout packed_layout(const a2p_model_cfg& c) {
     const int cm = c.C > 256 ? c.C : 256;
     const int chans[6][2] = {{cm, c.C}, {c.C, cm}, {c.C, c.C}, {c.C, c.C}, {c.C, c.C}, {c.C, c.C}};
     for (int i = 0; i < 6; ++i) p.conv_w[i] = take((size_t)chans[i][0] * chans[i][1] * 3);
+    for (int i = 0; i < 6; ++i) p.conv_t[i] = take((size_t)chans[i][0] * chans[i][1] * 3);   // tap-major [3][Cout][Cin] copy (TC arm)
   }
   p.rope = take((size_t)c.max_pos * (c.D / 2) * 2);
   p.planes = off;
@@ -145,6 +152,7 @@ KvLayout kv_layout(const a2p_model_cfg& c, int Bc, int S, int S2) {
 struct WsLayout {
   size_t counter, e, th, mt, ttok, tt, ttr, ktt, vtt, film, xin, x, h, hr, qkv, att, u, out, tcnA, tcnB, tcnC, total;
   size_t hP, hrP, attP, uP, xinP;   // split-bf16 activation planes (tensor-core arm)
+  size_t tcnUP, tcnVP;              // TCN activation planes in the left-padded layout
   size_t qkP, vtS, kttP, vttT;      // tensor-core attention operands: Q|K planes, self V^T planes, time-token K / V^T planes
 };
 WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
@@ -171,7 +179,11 @@ WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
     w.hP = take(P * R * T * D / 2 + 64); w.hrP = take(P * R * T * D / 2 + 64); w.attP = take(P * R * T * D / 2 + 64);
     w.uP = take(P * R * T * c.FF / 2 + 64); w.xinP = take(P * R * T * (D > c.C ? D : c.C) / 2 + 64);
     w.qkP = take(P * R * T * 2 * D / 2 + 64); w.vtS = take(P * D * align_up(R * T, 8) / 2 + 64);
-    w.kttP = take(P * (2 * R + 64) * c.L * D / 2 + 64); w.vttT = take(P * c.L * D * align_up(2 * R, 8) / 2 + 64);
+    w.kttP = take(P * (2 * R + 64) * c.L * D / 2 + 64); w.vttT = take(P * c.L * D * (8 * R) / 2 + 64);
+    if (c.fmt == A2P_FMT_POSE) {
+      const size_t cm = c.C > 256 ? c.C : 256;
+      w.tcnUP = take(P * R * (T + TCN_PAD) * cm / 2 + 64); w.tcnVP = take(P * R * (T + TCN_PAD) * cm / 2 + 64);
+    }
   }
   w.total = off;
   return w;
@@ -197,6 +209,14 @@ __global__ void permute_conv_w_kernel(const float* __restrict__ w, float* __rest
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= Cout * Cin * 3) return;
   int co = idx / (Cin * 3), rem = idx - co * Cin * 3, tap = rem / Cin, ci = rem - tap * Cin;
+  out[idx] = w[((long long)co * Cin + ci) * 3 + tap];
+}
+
+// conv weight [Cout, Cin, 3] -> tap-major [3][Cout][Cin]
+__global__ void permute_conv_w_tapmajor_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= Cout * Cin * 3) return;
+  int tap = idx / (Cout * Cin), rem = idx - tap * Cout * Cin, co = rem / Cin, ci = rem - co * Cin;
   out[idx] = w[((long long)co * Cin + ci) * 3 + tap];
 }
 
@@ -243,7 +263,7 @@ int gemm(Ctx& c, const float* A, long long lda, int M, const float* W, long long
   p.epi = epi;
   c.h->launches++;
   c.begin();
-  int rc = launch_sgemm(p, c.st);
+  int rc = skinny_ok(p) ? launch_skinny_gemm(p, c.st) : launch_sgemm(p, c.st);
   c.end();
   return rc;
 }
@@ -262,8 +282,9 @@ int tc_gemm(Ctx& c, const __nv_bfloat16* Ap, int M, int K, const float* wkey, lo
   a2p_denoiser* h = c.h;
   auto it = h->wplanes.find(wkey);
   if (it == h->wplanes.end()) A2P_FAIL("tc_gemm: weight has no split planes");
-  TcOperands o{Ap, K, (long long)M * K, it->second + w_row0 * K, K, h->wnumel[wkey]};
-  p.M = M; p.N = N; p.K = K; p.taps = 1; p.dil = 0; p.bias = bias;
+  if (p.taps <= 0) { p.taps = 1; p.dil = 0; }
+  TcOperands o{Ap, K, (long long)M * K, it->second + w_row0 * K, K, h->wnumel[wkey] / p.taps};
+  p.M = M; p.N = N; p.K = K; p.bias = bias;
   if (p.out_scale == 0.f) p.out_scale = 1.f;
   h->launches++;
   c.begin();
@@ -357,7 +378,16 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   A2P_TRY(gemm(c, mt, D, R, h->film_w, D, h->film_b, (int)film_ld, D, film, film_ld));
   // --- input projection (identical for both branches: computed once, duplicated)
   c.cat = CAT_IO_TCN;
-  A2P_TRY(gemm(c, xin, C, B * T, h->inp_w, C, h->inp_b, D, C, x, D));
+  if (cf.split_terms > 0) {
+    __nv_bfloat16* xinP = reinterpret_cast<__nv_bfloat16*>(wsb + w.xinP);
+    A2P_TRY(launch_split_planes(cf.split_terms, xin, C, xinP, (long long)B * T * C, (long long)B * T, C, 1.f, st));
+    h->launches++;
+    TcGemmParams g{};
+    g.C = x; g.ldc = D;
+    A2P_TRY(tc_gemm(c, xinP, B * T, C, h->inp_w, 0, D, h->inp_b, TC_F32, g));
+  } else {
+    A2P_TRY(gemm(c, xin, C, B * T, h->inp_w, C, h->inp_b, D, C, x, D));
+  }
   if (nb == 2) {
     A2P_CUDA(cudaMemcpyAsync(x + (size_t)B * T * D, x, sizeof(float) * (size_t)B * T * D, cudaMemcpyDeviceToDevice, st));
   }
@@ -376,13 +406,14 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   __nv_bfloat16* vtS = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.vtS) : nullptr;
   __nv_bfloat16* kttP = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.kttP) : nullptr;
   __nv_bfloat16* vttT = P ? reinterpret_cast<__nv_bfloat16*>(wsb + w.vttT) : nullptr;
-  const long long MT8 = (long long)align_up((size_t)MT, 8), XP = (long long)align_up((size_t)2 * R, 8);
+  const long long MT8 = (long long)align_up((size_t)MT, 8);
+  const long long XP = 8LL * R;   // time-token V^T: 8 columns per sample (TMA needs 16-byte aligned box starts), 2 used
   if (tc_attn) {
     c.cat = CAT_COND;
     c.begin();
     A2P_TRY(launch_split_planes(P, ktt, (long long)L * D, kttP, (long long)2 * R * L * D, 2 * R, L * D, 1.f, st));
     A2P_CUDA(cudaMemsetAsync(vttT, 0, sizeof(__nv_bfloat16) * (size_t)P * L * D * XP, st));
-    A2P_TRY(launch_transpose_split(P, vtt, (long long)L * D, vttT, (long long)L * D * XP, XP, 2 * R, L * D, 2 * R, 0, 1.f, st));
+    A2P_TRY(launch_transpose_split(P, vtt, (long long)L * D, vttT, (long long)L * D * XP, XP, 2 * R, L * D, 2, 8, 1.f, st));
     c.end();
     h->launches += 3;
   }
@@ -418,7 +449,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       if (kind == 1) {
         o.Kx = kttP; o.kx_rows = 2 * R; o.kx_ld = (long long)L * D; o.kx_plane_stride = (long long)2 * R * L * D;
         o.Vx = vttT; o.vx_rows = (long long)L * D; o.vx_cols = XP; o.vx_ld = XP; o.vx_plane_stride = (long long)L * D * XP;
-        ap.n_extra = 2; ap.kx_col0 = l * D; ap.kx_row_stride = 2; ap.vx_row0 = l * D; ap.vx_col_stride = 2;
+        ap.n_extra = 2; ap.kx_col0 = l * D; ap.kx_row_stride = 2; ap.vx_row0 = l * D; ap.vx_col_stride = 8;
       }
     }
     c.cat = kind == 0 ? CAT_ATT_SELF : (kind == 1 ? CAT_ATT_CROSS : CAT_ATT_CROSS2);
@@ -598,7 +629,53 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   }
   // ---- final projection (+ causal TCN for pose; model/diffusion.py:397-402)
   c.cat = CAT_IO_TCN;
-  A2P_TRY(gemm(c, x, D, R * T, h->fin_w, D, h->fin_b, C, D, out, C));
+  if (P > 0 && cf.fmt == A2P_FMT_POSE) {
+    // tensor-core arm of final_layer + causal TCN: activations travel as split planes in the left-padded layout
+    // [R][T+24][C]; conv tap j reads rows shifted by (2-j)*dil (TMA zero-fills rows < 0); fp32 copies feed the skips.
+    const int cm = C > 256 ? C : 256;
+    const int Pl = T + TCN_PAD, Mp = R * Pl;
+    __nv_bfloat16* U = reinterpret_cast<__nv_bfloat16*>(wsb + w.tcnUP);
+    __nv_bfloat16* V = reinterpret_cast<__nv_bfloat16*>(wsb + w.tcnVP);
+    float *X = F(w.tcnA), *Y = F(w.tcnC);
+    A2P_TRY(launch_split_planes(P, x, D, hP, pstrideD, MT, D, 1.f, st));
+    A2P_CUDA(cudaMemset2DAsync(U, (size_t)Pl * C * 2, 0, (size_t)TCN_PAD * C * 2, (size_t)P * R, st));
+    h->launches += 2;
+    {
+      TcGemmParams g{};
+      g.Cp = U; g.cp_plane_stride = (long long)Mp * C; g.ldcp = C; g.remap_rps = T; g.remap_pad = TCN_PAD;
+      A2P_TRY(tc_gemm(c, hP, MT, D, h->fin_w, 0, C, h->fin_b, TC_PLANES, g));
+    }
+    struct St { __nv_bfloat16* in; int cin; __nv_bfloat16* outp; int cout; float* f32; const float* skip; };
+    St stg[6] = {{U, C, V, cm, nullptr, nullptr}, {V, cm, U, C, X, nullptr}, {U, C, V, C, Y, X},
+                 {V, C, U, C, X, Y},              {U, C, V, C, Y, X},        {V, C, U, C, nullptr, Y}};
+    for (int i = 0; i < 6; ++i) {
+      TcGemmParams g{};
+      g.taps = 3; g.dil = TCN_DIL[i]; g.slope = 0.2f;
+      g.Cp = stg[i].outp; g.cp_plane_stride = (long long)Mp * stg[i].cout; g.ldcp = stg[i].cout;
+      g.C = stg[i].f32; g.ldc = stg[i].cout;
+      g.skip = stg[i].skip; g.ldskip = stg[i].cout;
+      A2P_TRY(tc_gemm(c, stg[i].in, Mp, stg[i].cin, h->conv_t[i], 0, stg[i].cout, h->conv_b[i], TC_LRELU_PLANES, g));
+    }
+    {
+      TcGemmParams g{};
+      g.C = Y; g.ldc = C;
+      A2P_TRY(tc_gemm(c, U, Mp, C, h->fconv_w, 0, C, h->fconv_b, TC_F32, g));
+    }
+    *x0_sample_stride = (long long)Pl * C;
+    const float* o0 = Y + (size_t)TCN_PAD * C;
+    *x0_cond = (mask & A2P_MASK_COND) ? o0 : nullptr;
+    *x0_uncond = (mask == A2P_MASK_BOTH) ? o0 + (size_t)B * Pl * C : (mask == A2P_MASK_UNCOND ? o0 : nullptr);
+    return 0;
+  }
+  if (P > 0) {
+    A2P_TRY(launch_split_planes(P, x, D, hP, pstrideD, MT, D, 1.f, st));
+    h->launches++;
+    TcGemmParams g{};
+    g.C = out; g.ldc = C;
+    A2P_TRY(tc_gemm(c, hP, MT, D, h->fin_w, 0, C, h->fin_b, TC_F32, g));
+  } else {
+    A2P_TRY(gemm(c, x, D, R * T, h->fin_w, D, h->fin_b, C, D, out, C));
+  }
   if (cf.fmt == A2P_FMT_POSE) {
     const int cm = C > 256 ? C : 256;
     const int P = T + TCN_PAD;
@@ -662,6 +739,7 @@ int a2p_denoiser_create(a2p_denoiser_t** out, const a2p_model_cfg* cfg) {
   A2P_CUDA(cudaGetDeviceCount(&ndev));
   if (ndev <= 0) A2P_FAIL("no CUDA device: a2p_b200 has no CPU fallback");
   A2P_TRY(init_attn_simt());
+  A2P_TRY(init_skinny_gemm());
   a2p_denoiser* h = new a2p_denoiser();
   h->cfg = *cfg;
   h->dh = cfg->D / cfg->H;
@@ -749,8 +827,10 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
       h->conv_b[i] = W(p + "bias", chans[i][0]);
       if (!err.empty()) A2P_FAIL("bind_weights: %s", err.c_str());
       h->conv_w[i] = P(pl.conv_w[i]);
+      h->conv_t[i] = P(pl.conv_t[i]);
       int tot = (int)(chans[i][0] * chans[i][1] * 3);
       permute_conv_w_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(cw, h->conv_w[i], (int)chans[i][0], (int)chans[i][1]);
+      permute_conv_w_tapmajor_kernel<<<ceil_div(tot, 256), 256, 0, st>>>(cw, h->conv_t[i], (int)chans[i][0], (int)chans[i][1]);
     }
     h->fconv_w = W("final_conv.weight", C * C); h->fconv_b = W("final_conv.bias", C);
   }
@@ -775,6 +855,12 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
       A2P_TRY(split_w(lw.l1w, FF, D)); A2P_TRY(split_w(lw.l2w, D, FF));
     }
     A2P_TRY(split_w(h->inp_w, D, C)); A2P_TRY(split_w(h->fin_w, C, D));
+    if (cf.fmt == A2P_FMT_POSE) {
+      const int64_t cm = C > 256 ? C : 256;
+      const int64_t chans[6][2] = {{cm, C}, {C, cm}, {C, C}, {C, C}, {C, C}, {C, C}};
+      for (int i = 0; i < 6; ++i) A2P_TRY(split_w(h->conv_t[i], 3 * chans[i][0], chans[i][1]));   // planes [P][3][Cout][Cin]
+      A2P_TRY(split_w(h->fconv_w, C, C));
+    }
     A2P_TRY(init_umma_gemm());
     A2P_TRY(init_umma_attn());
   }

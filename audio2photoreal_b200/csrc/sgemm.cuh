@@ -160,3 +160,80 @@ inline int launch_sgemm(const GemmParams& p, cudaStream_t st) {
 }
 
 }  // namespace a2p
+
+// ------------------------------------------------------------------ skinny GEMM (M <= 64 rows)
+// The per-step conditioning linears (time MLP, FiLM table, time-token K/V rows) have M = 2B rows only: a
+// 128x128-tile kernel leaves the chip idle and crawls through K.  Here one warp owns one output column n:
+// it streams W[n,:] once (coalesced, read-only path) and keeps A (M x K fp32) in shared memory, so the
+// kernel is bound by reading W once from L2/HBM.  Same fused epilogues as sgemm_kernel (no FiLM / skip).
+namespace a2p {
+
+template <int MB>
+__global__ void __launch_bounds__(256) skinny_gemm_kernel(GemmParams p) {
+  extern __shared__ __align__(16) float sA[];   // [M][K]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < p.M * (p.K / 4); i += 256) {
+    const int r = i / (p.K / 4), c = i - r * (p.K / 4);
+    reinterpret_cast<float4*>(sA)[i] = *reinterpret_cast<const float4*>(p.A + (long long)r * p.lda + c * 4);
+  }
+  __syncthreads();
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= p.N) return;
+  float acc[MB];
+#pragma unroll
+  for (int m = 0; m < MB; ++m) acc[m] = 0.f;
+  const float* wr = p.W + (long long)n * p.ldw;
+  for (int k = lane * 4; k < p.K; k += 128) {
+    const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      if (m < p.M) {
+        const float4 a = *reinterpret_cast<const float4*>(sA + m * p.K + k);
+        acc[m] = fmaf(a.x, w.x, acc[m]); acc[m] = fmaf(a.y, w.y, acc[m]);
+        acc[m] = fmaf(a.z, w.z, acc[m]); acc[m] = fmaf(a.w, w.w, acc[m]);
+      }
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < MB; ++m) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+  }
+  if (lane == 0) {
+    const float b = p.bias ? p.bias[n] : 0.f;
+#pragma unroll
+    for (int m = 0; m < MB; ++m) {
+      if (m >= p.M) break;
+      float v = acc[m] + b;
+      if (p.epi == EPI_GELU) v = gelu_erf(v);
+      else if (p.epi == EPI_MISH) v = mishf(v);
+      else if (p.epi == EPI_ADDROW_MISH) v = mishf(v + p.rowvec.at(m)[n]);
+      p.C[(long long)m * p.ldc + n] = v;
+    }
+  }
+}
+
+inline int init_skinny_gemm() {
+  A2P_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  A2P_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  A2P_CUDA(cudaFuncSetAttribute(skinny_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return 0;
+}
+
+// true if the skinny kernel can (and should) take this GEMM
+inline bool skinny_ok(const GemmParams& p) {
+  return p.M <= 64 && p.taps <= 1 && p.K % 4 == 0 && (size_t)p.M * p.K * 4 <= 200 * 1024 &&
+         (p.epi == EPI_BIAS || p.epi == EPI_GELU || p.epi == EPI_MISH || p.epi == EPI_ADDROW_MISH);
+}
+
+inline int launch_skinny_gemm(const GemmParams& p, cudaStream_t st) {
+  const size_t sm = (size_t)p.M * p.K * 4;
+  const int grid = ceil_div(p.N, 8);
+  if (p.M <= 16) skinny_gemm_kernel<16><<<grid, 256, sm, st>>>(p);
+  else if (p.M <= 32) skinny_gemm_kernel<32><<<grid, 256, sm, st>>>(p);
+  else skinny_gemm_kernel<64><<<grid, 256, sm, st>>>(p);
+  A2P_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace a2p

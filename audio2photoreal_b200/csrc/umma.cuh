@@ -108,6 +108,13 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
+// The same descriptor split into 32-bit halves so that advancing along K (or to another tile) is ONE 32-bit add
+// on the low word: hi = SBO | version | layout (constant), lo = (addr >> 4) | LBO.  smem < 256 KB, so the
+// 14-bit address field never carries.
+constexpr uint32_t kDescHiSw128 = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+__device__ __forceinline__ uint64_t desc_make(uint32_t lo) { return ((uint64_t)kDescHiSw128 << 32) | (uint64_t)lo; }
+
 // same for 64-byte rows (SWIZZLE_64B: 8-row groups of 512 B), used when the K extent of a tile is 32 bf16
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   uint64_t d = 0;
@@ -157,6 +164,29 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16* out) {
     out[i] = b;
     r = r - __bfloat162float(b);
   }
+}
+
+// Pairwise split WITHOUT conversion instructions: on sm_100 both F2F and F2FP (cvt.rn.bf16x2.f32) issue on the
+// XU pipe (~8 lanes/clk/SM, shared with MUFU.EX2), which is the limiter of the softmax warps.  Rounding is done
+// with integer adds on the ALU pipe instead: u + 0x8000 rounds the upper 16 bits half-up (a tie happens with
+// probability 2^-16 and costs half a bf16 ulp of the LAST plane), PRMT packs the two upper halves.
+// out[t] holds plane t of (a, b) packed as bf16x2 (a in the low half = lower address).
+template <int P>
+__device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t* out) {
+#pragma unroll
+  for (int t = 0; t < P; ++t) {
+    const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+    out[t] = __byte_perm(ua, ub, 0x7632);
+    if (t + 1 < P) {
+      a = a - __uint_as_float(ua & 0xFFFF0000u);
+      b = b - __uint_as_float(ub & 0xFFFF0000u);
+    }
+  }
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 }  // namespace umma

@@ -103,20 +103,24 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmS = tmem_base, tmPV = tmem_base + 128;   // S buffers: +0, +64 ; PV buffers: +128, +192
 
+  // Single-thread roles run warp-uniformly with only the issuing instructions under elect.sync (see umma_gemm.cuh).
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
+    if (umma::elect_one()) {
       umma::mbar_expect_tx(q_full, Cfg::Q_BYTES);
 #pragma unroll
       for (int i = 0; i < TERMS; ++i)
         umma::tma_load_3d(&tmQ, q_full, sQ + i * 16384, p.q_col0 + g * 64, r * p.T + q0, i);
-      const CUtensorMap* tK = br ? &tmK1 : &tmK0;
-      const CUtensorMap* tV = br ? &tmV1 : &tmV0;
-      const int k_row_base = (int)(rr * p.k_row_stride[br]);
-      const int v_col_base = (int)(rr * p.v_col_stride[br]);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int st = j & 1;
-        umma::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+    }
+    __syncwarp();
+    const CUtensorMap* tK = br ? &tmK1 : &tmK0;
+    const CUtensorMap* tV = br ? &tmV1 : &tmV0;
+    const int k_row_base = (int)(rr * p.k_row_stride[br]);
+    const int v_col_base = (int)(rr * p.v_col_stride[br]);
+    for (int j = 0; j < n_blocks; ++j) {
+      const int st = j & 1;
+      umma::mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1);
+      if (umma::elect_one()) {
         umma::mbar_expect_tx(&kv_full[st], Cfg::KV_STAGE_BYTES);
         uint8_t* sk = sKV + st * Cfg::KV_STAGE_BYTES;
         uint8_t* sv = sk + TERMS * 8192;
@@ -132,50 +136,58 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int i = 0; i < TERMS; ++i) umma::tma_load_3d(&tmVx, &kv_full[st], sv + i * 8192, r * p.vx_col_stride, p.vx_row0 + g * 64, i);
         }
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);
-      constexpr uint32_t idPV = umma::idesc_bf16_f32(128, DH);
-      const uint32_t aQ = umma::smem_u32(sQ);
-      auto issue_pv = [&](int i) {
-        const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
-        const uint32_t sv = umma::smem_u32(sKV + (j & 1) * Cfg::KV_STAGE_BYTES + TERMS * 8192);
-        const uint32_t sp = umma::smem_u32(sP + pb * Cfg::P_BYTES);
-        umma::mbar_wait(&p_full[pb], (i / NPB) & 1);
-        umma::mbar_wait(&pv_empty[b], ((i >> 1) & 1) ^ 1);
-        umma::fence_after();
+    constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);
+    constexpr uint32_t idPV = umma::idesc_bf16_f32(128, DH);
+    const uint32_t loQ = umma::desc_lo(umma::smem_u32(sQ));
+    const uint32_t loKV = umma::desc_lo(umma::smem_u32(sKV));
+    const uint32_t loP = umma::desc_lo(umma::smem_u32(sP));
+    auto issue_pv = [&](int i) {
+      const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
+      umma::mbar_wait(&p_full[pb], (i / NPB) & 1);
+      umma::mbar_wait(&pv_empty[b], ((i >> 1) & 1) ^ 1);
+      umma::fence_after();
+      if (umma::elect_one()) {
+        const uint32_t lov = loKV + (j & 1) * (Cfg::KV_STAGE_BYTES >> 4) + TERMS * (8192 >> 4) + hh * (DH * 128 >> 4);
+        const uint32_t lop = loP + pb * (Cfg::P_BYTES >> 4);
 #pragma unroll
         for (int pr = 0; pr < Cfg::NPROD; ++pr) {
-          const uint64_t da = umma::smem_desc_sw128(sp + kProdA[pr] * 16384);
-          const uint64_t db = umma::smem_desc_sw128(sv + kProdB[pr] * 8192 + hh * DH * 128);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma::mma_bf16(tmPV + b * 64, da + 2 * k, db + 2 * k, idPV, (pr | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k)
+            umma::mma_bf16(tmPV + b * 64, umma::desc_make(lop + prod_a(pr) * (16384 >> 4) + 2 * k),
+                           umma::desc_make(lov + prod_b(pr) * (8192 >> 4) + 2 * k), idPV, (pr | k) != 0 ? 1u : 0u);
         }
         umma::mma_commit(&pv_full[b]);
         umma::mma_commit(&p_empty[pb]);
         if (hh == G - 1) umma::mma_commit(&kv_empty[j & 1]);
-      };
-      umma::mbar_wait(q_full, 0);
-      for (int i = 0; i < n_iter; ++i) {
-        const int j = i / G, hh = i - j * G, b = i & 1;
-        if (hh == 0) umma::mbar_wait(&kv_full[j & 1], (j >> 1) & 1);
-        umma::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
-        umma::fence_after();
-        const uint32_t sk = umma::smem_u32(sKV + (j & 1) * Cfg::KV_STAGE_BYTES);
+      }
+      __syncwarp();
+    };
+    umma::mbar_wait(q_full, 0);
+    for (int i = 0; i < n_iter; ++i) {
+      const int j = i / G, hh = i - j * G, b = i & 1;
+      if (hh == 0) umma::mbar_wait(&kv_full[j & 1], (j >> 1) & 1);
+      umma::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
+      umma::fence_after();
+      if (umma::elect_one()) {
+        const uint32_t lok = loKV + (j & 1) * (Cfg::KV_STAGE_BYTES >> 4) + hh * (DH / 8);
+        const uint32_t loq = loQ + hh * (DH / 8);
 #pragma unroll
         for (int pr = 0; pr < Cfg::NPROD; ++pr) {
-          const uint64_t da = umma::smem_desc_sw128(aQ + kProdA[pr] * 16384) + hh * (DH / 8);
-          const uint64_t db = umma::smem_desc_sw128(sk + kProdB[pr] * 8192) + hh * (DH / 8);
 #pragma unroll
-          for (int k = 0; k < DH / 16; ++k) umma::mma_bf16(tmS + b * 64, da + 2 * k, db + 2 * k, idS, (pr | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < DH / 16; ++k)
+            umma::mma_bf16(tmS + b * 64, umma::desc_make(loq + prod_a(pr) * (16384 >> 4) + 2 * k),
+                           umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
         }
         umma::mma_commit(&s_full[b]);
-        if (i > 0) issue_pv(i - 1);
       }
-      issue_pv(n_iter - 1);
+      __syncwarp();
+      if (i > 0) issue_pv(i - 1);
     }
+    issue_pv(n_iter - 1);
   } else if (warp >= 4) {
     // ================= softmax / output =================
     const int wq = warp & 3;
@@ -217,40 +229,49 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       umma::fence_before();
       umma::mbar_arrive(&s_empty[b]);
       const int nvalid = (j < nb_main) ? ::min(64, p.n_keys - j * 64) : p.n_extra;
-      float mx = -INFINITY;
+      if (nvalid < 64) {   // warp-uniform: only the ragged last block (and the 2-key extra block) is masked
 #pragma unroll
-      for (int c = 0; c < 64; ++c) {
-        s[c] = c < nvalid ? s[c] : -INFINITY;
-        mx = fmaxf(mx, s[c]);
+        for (int c = 0; c < 64; ++c) s[c] = c < nvalid ? s[c] : -INFINITY;
       }
+      float mx = s[0];
+#pragma unroll
+      for (int c = 1; c < 64; ++c) mx = fmaxf(mx, s[c]);
       float mold = 0.f, mnew = 0.f;
 #pragma unroll
       for (int h = 0; h < G; ++h)
         if (h == hh) { mold = m[h]; mnew = fmaxf(mold, mx); m[h] = mnew; }
-      const float alpha = exp2f(mold - mnew);
-      float rs = 0.f;
-#pragma unroll
-      for (int c = 0; c < 64; ++c) { s[c] = exp2f(s[c] - mnew); rs += s[c]; }
-#pragma unroll
-      for (int h = 0; h < G; ++h)
-        if (h == hh) l[h] = l[h] * alpha + rs;
-      // P planes -> smem (K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7))
+      const float alpha = umma::ex2_approx(mold - mnew);
+      // P planes -> smem (K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7)); exp2 + split fused per chunk
       umma::mbar_wait(&p_empty[pb], ((i / NPB) & 1) ^ 1);
       uint8_t* pbase = sP + pb * Cfg::P_BYTES + trow * 128;
+      float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
-        __nv_bfloat16 pl[TERMS][8];
+        uint32_t pk[TERMS][4];
+        if (ch * 8 < nvalid) {   // warp-uniform: fully masked 8-key chunks cost no exp2
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          __nv_bfloat16 sp[TERMS];
-          umma::split_bf16<TERMS>(s[ch * 8 + e], sp);
+          for (int e = 0; e < 4; ++e) {
+            const float a = umma::ex2_approx(s[ch * 8 + 2 * e] - mnew);
+            const float b = umma::ex2_approx(s[ch * 8 + 2 * e + 1] - mnew);
+            rs0 += a; rs1 += b;
+            uint32_t sp[TERMS];
+            umma::split_bf16_pair<TERMS>(a, b, sp);
 #pragma unroll
-          for (int t = 0; t < TERMS; ++t) pl[t][e] = sp[t];
+            for (int t = 0; t < TERMS; ++t) pk[t][e] = sp[t];
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+#pragma unroll
+            for (int t = 0; t < TERMS; ++t) pk[t][e] = 0u;
         }
 #pragma unroll
         for (int t = 0; t < TERMS; ++t)
-          *reinterpret_cast<uint4*>(pbase + t * 16384 + ((ch ^ (trow & 7)) << 4)) = *reinterpret_cast<const uint4*>(pl[t]);
+          *reinterpret_cast<uint4*>(pbase + t * 16384 + ((ch ^ (trow & 7)) << 4)) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
       }
+#pragma unroll
+      for (int h = 0; h < G; ++h)
+        if (h == hh) l[h] = l[h] * alpha + (rs0 + rs1);
       umma::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       umma::mbar_arrive(&p_full[pb]);
       if (i > 0) consume_pv(i - 1, alpha_pend);

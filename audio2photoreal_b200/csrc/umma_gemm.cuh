@@ -38,6 +38,7 @@ struct TcGemmParams {
   float out_scale, slope;
   int scale_ncols;   // out_scale applies to columns < scale_ncols (0 = all columns)
   int bias_per_row;  // bias indexed by output row (swapped-operand GEMMs producing a transposed result)
+  int remap_rps, remap_pad;  // if remap_rps > 0: output row = row + (row / remap_rps + 1) * remap_pad (write into a per-sample left-padded layout)
 };
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
@@ -51,8 +52,9 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
 };
 
-__device__ __constant__ int8_t kProdA[6] = {0, 0, 1, 0, 2, 1};
-__device__ __constant__ int8_t kProdB[6] = {0, 1, 0, 2, 0, 1};
+// plane pairs (i, j) with i + j < TERMS, most significant first (compile-time tables: indices fold into immediates)
+__host__ __device__ constexpr int prod_a(int pr) { return pr == 0 ? 0 : pr == 1 ? 0 : pr == 2 ? 1 : pr == 3 ? 0 : pr == 4 ? 2 : 1; }
+__host__ __device__ constexpr int prod_b(int pr) { return pr == 0 ? 0 : pr == 1 ? 1 : pr == 2 ? 0 : pr == 3 ? 2 : pr == 4 ? 0 : 1; }
 
 template <int TERMS, int EPI>
 __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -89,16 +91,19 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
   umma::fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // NOTE on the two single-thread roles: the whole warp runs the loops (all values stay warp-uniform, so the
+  // compiler keeps descriptors / TMEM addresses in uniform registers) and only the issuing instructions sit under
+  // elect.sync -- an `if (lane == 0)` region makes ptxas wrap every UTCHMMA / UTMALDG in an ELECT/R2UR waterfall loop.
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * TC_BN;
-        for (int kb = 0; kb < n_kb; ++kb) {
-          const int tap = kb / kb_per_tap, k0 = (kb - tap * kb_per_tap) * TC_BK;
-          const int shift = (p.taps - 1 - tap) * p.dil;
-          umma::mbar_wait(&empty[stage], phase ^ 1);
+    int stage = 0; uint32_t phase = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * TC_BN;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int tap = kb / kb_per_tap, k0 = (kb - tap * kb_per_tap) * TC_BK;
+        const int shift = (p.taps - 1 - tap) * p.dil;
+        umma::mbar_wait(&empty[stage], phase ^ 1);
+        if (umma::elect_one()) {
           umma::mbar_expect_tx(&full[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
 #pragma unroll
@@ -106,38 +111,41 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
 #pragma unroll
           for (int i = 0; i < TERMS; ++i)
             umma::tma_load_3d(&tmW, &full[stage], sa + (TERMS + i) * TC_TILE_BYTES, k0, n0, i * p.taps + tap);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma::idesc_bf16_f32(TC_BM, TC_BN);
-      int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        umma::mbar_wait(&tempty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = umma::idesc_bf16_f32(TC_BM, TC_BN);
+    const uint32_t lo0 = umma::desc_lo(umma::smem_u32(smem));
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      umma::mbar_wait(&tempty[acc], acc_phase ^ 1);
+      umma::fence_after();
+      const uint32_t d = tmem_base + acc * TC_BN;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        umma::mbar_wait(&full[stage], phase);
         umma::fence_after();
-        const uint32_t d = tmem_base + acc * TC_BN;
-        for (int kb = 0; kb < n_kb; ++kb) {
-          umma::mbar_wait(&full[stage], phase);
-          umma::fence_after();
-          const uint32_t sa = umma::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        if (umma::elect_one()) {
+          const uint32_t lo = lo0 + stage * (Cfg::STAGE_BYTES >> 4);
 #pragma unroll
           for (int pr = 0; pr < Cfg::NPROD; ++pr) {
-            const uint64_t da = umma::smem_desc_sw128(sa + kProdA[pr] * TC_TILE_BYTES);
-            const uint64_t db = umma::smem_desc_sw128(sa + (TERMS + kProdB[pr]) * TC_TILE_BYTES);
 #pragma unroll
             for (int k = 0; k < TC_BK / 16; ++k)
-              umma::mma_bf16(d, da + 2 * k, db + 2 * k, idesc, (kb | pr | k) != 0 ? 1u : 0u);
+              umma::mma_bf16(d, umma::desc_make(lo + prod_a(pr) * (TC_TILE_BYTES >> 4) + 2 * k),
+                             umma::desc_make(lo + (TERMS + prod_b(pr)) * (TC_TILE_BYTES >> 4) + 2 * k), idesc,
+                             (kb | pr | k) != 0 ? 1u : 0u);
           }
           umma::mma_commit(&empty[stage]);
-          if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+          if (kb == n_kb - 1) umma::mma_commit(&tfull[acc]);
         }
-        umma::mma_commit(&tfull[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4) {
     // ================= epilogue =================
@@ -172,11 +180,12 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int r = it * 4 + rsub;
-          const int row = m0 + wq * 32 + r;
+          int row = m0 + wq * 32 + r;
           if (row >= p.M || !col_ok) continue;
           const float4 a = *reinterpret_cast<const float4*>(tw + r * 36 + c4);
           if (p.bias_per_row && p.bias) { const float br_ = __ldg(p.bias + row); bb = make_float4(br_, br_, br_, br_); }
           float o[4] = {a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w};
+          if (p.remap_rps > 0) row += (row / p.remap_rps + 1) * p.remap_pad;
           if (EPI == TC_F32) {
             *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) =
                 make_float4(o[0] * oscale, o[1] * oscale, o[2] * oscale, o[3] * oscale);

@@ -37,8 +37,11 @@ UNIT = "frames/s"
 WORKLOAD = dict(fmt="pose", layers=6, heads=8, T=600, S=1998, C=104, B=8, guidance=2.0, respacing="")
 
 
+SPLIT_TERMS = 3
+
+
 def model_args(respacing):
-    return Namespace(data_format="pose", add_frame_cond=1, max_seq_length=600, layers=WORKLOAD["layers"],
+    return Namespace(split_terms=SPLIT_TERMS, data_format="pose", add_frame_cond=1, max_seq_length=600, layers=WORKLOAD["layers"],
                      heads=WORKLOAD["heads"], not_rotary=False, unconstrained=False, device="cuda",
                      timestep_respacing=respacing, noise_schedule="cosine", sigma_small=True, lambda_vel=0.0,
                      model_path="synthetic", resume_trans=None)
@@ -163,7 +166,10 @@ def main():
     ap.add_argument("--diffusion-steps", type=int, default=1000, help="debug only; anything but 1000 is not the benchmark")
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="debug only; per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--split-terms", type=int, default=3, help="0: exact-fp32 FFMA arm; 2|3: split-bf16 tcgen05 arm")
     a = ap.parse_args()
+    global SPLIT_TERMS
+    SPLIT_TERMS = a.split_terms
     if a.impl == "reference":
         return run_reference_arm(a)
 
@@ -292,7 +298,9 @@ def main():
                     "frac": achieved / peak_tf, "traffic": None, "peak_source": f"bf16_tflops burst, of {peak_src}",
                     "ms_per_launch": per_launch_ms, "launches_per_forward": int(n_cat[dom]),
                     "forward_ms_by_kernel": {n: round(float(v), 4) for n, v in zip(names, acc)},
-                    "note": "exact-fp32 FFMA kernels (split_terms=0): tensor pipe unused in this round-1 build"}
+                    "split_terms": SPLIT_TERMS,
+                    "note": ("algorithmic FLOPs (one product per MAC) over measured time; the split-bf16 arm spends %d tensor-core "
+                             "products per MAC for fp32-level parity" % {0: 0, 1: 1, 2: 3, 3: 6}[SPLIT_TERMS])}
         if not a.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, dt = cpu_port_frames_per_s(2, threads)
@@ -301,7 +309,8 @@ def main():
         f_fwd = flops_per_sample_forward()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if SPLIT_TERMS == 0 else f"bf16x{SPLIT_TERMS} split (fp32-equivalent), fp32 accumulate",
             "data": "synthetic",
             "config": {"workload": f"pose body diffusion, {n_diff} steps, T={T}, C=104, batch {B}/GPU, CFG g=2.0, "
                                    f"L=6 D=256 H=8, synthetic wav2vec features [B,{S},1024] (BASELINE configs[1])",

@@ -19,7 +19,7 @@ def report(tag, got, ref):
     viol = (d > 1e-4 + 1e-3 * ref.abs()).double().mean().item()
     print(f"{tag}: max|d|={d.max().item():.3e} |ref|max={ref.abs().max().item():.3f} viol={100*viol:.4f}%", flush=True)
 
-for terms in (3, 2, 1):
+for terms in (3, 2):
     for name in ["pose_small", "face_small", "pose_full"]:
         case = CASES[name]
         inp = make_inputs(case)
