@@ -19,6 +19,7 @@
 #include "sgemm.cuh"
 #include "umma_gemm.cuh"
 #include "umma_attention.cuh"
+#include "umma_microbench.cuh"
 #include "../../include/a2p_b200_testing.h"
 
 using namespace a2p;
@@ -1139,6 +1140,10 @@ int a2p_test_tc_gemm(int terms, int M, int N, int K, int taps, int dil, const fl
   if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
+}
+
+int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_dev, void* stream) {
+  return launch_mma_rate(N, a_from_tmem, n_mma, cycles_out_dev, (cudaStream_t)stream);
 }
 
 size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_extra) {

@@ -44,11 +44,21 @@ struct TcAttnCfg {
   static constexpr int Q_BYTES = TERMS * 128 * 128;            // [128 rows][64 cols] bf16 per plane
   static constexpr int KV_STAGE_BYTES = TERMS * 2 * 64 * 128;  // K tile + V^T tile per plane (8 KB each)
   static constexpr int P_BYTES = TERMS * 128 * 128;            // [128 rows][64 keys] bf16 per plane
-  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGE_BYTES + NPBUF * P_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = Q_BYTES + 2 * KV_STAGE_BYTES + NPBUF * P_BYTES + 1024 + 512;
+  static constexpr int THREADS = 384;                          // 4 role warps + 2 softmax warpgroups
 };
 
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// Softmax work split: TWO warpgroups per CTA.  Warpgroup w owns key columns [32w, 32w+32) of every 64-key block and
+// runs its own online softmax (running max / sum / O) over that key subset; the two partial results are merged
+// once at the end (flash-decoding style).  With one warp per SM sub-partition the softmax was latency-bound
+// (issue slots 36 % busy, ncu profiles/r01e); two warps per scheduler hide the TMEM / MUFU / mbarrier latencies
+// and halve the per-thread register footprint.
 template <int TERMS, int DH>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                  const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV0,
                  const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmKx,
@@ -66,12 +76,12 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   uint64_t* kv_full = bars + 1;       // [2]
   uint64_t* kv_empty = bars + 3;      // [2]
   uint64_t* s_full = bars + 5;        // [2]
-  uint64_t* s_empty = bars + 7;       // [2]
-  uint64_t* p_full = bars + 9;        // [2]
-  uint64_t* p_empty = bars + 11;      // [2]
-  uint64_t* pv_full = bars + 13;      // [2]
-  uint64_t* pv_empty = bars + 15;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* s_empty = bars + 7;       // [2]       256 arrivals
+  uint64_t* p_full = bars + 9;        // [2 wg][2]  128 arrivals each
+  uint64_t* p_empty = bars + 13;      // [2 wg][2]
+  uint64_t* pv_full = bars + 17;      // [2 wg][2]
+  uint64_t* pv_empty = bars + 21;     // [2 wg][2]  128 arrivals each
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, g = blockIdx.y, r = blockIdx.z;
@@ -90,18 +100,20 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     umma::mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       umma::mbar_init(&kv_full[i], 1); umma::mbar_init(&kv_empty[i], 1);
-      umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 128);
+      umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 256);
+    }
+    for (int i = 0; i < 4; ++i) {
       umma::mbar_init(&p_full[i], 128); umma::mbar_init(&p_empty[i], 1);
       umma::mbar_init(&pv_full[i], 1); umma::mbar_init(&pv_empty[i], 128);
     }
     umma::fence_barrier_init();
   }
-  if (warp == 2) umma::tmem_alloc<256>(tmem_slot);
+  if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmS = tmem_base, tmPV = tmem_base + 128;   // S buffers: +0, +64 ; PV buffers: +128, +192
+  const uint32_t tmS = tmem_base, tmPV = tmem_base + 128;   // S buffers: +0, +64 ; PV buffers [wg][b]: +128 + (wg*2+b)*64
 
   // Single-thread roles run warp-uniformly with only the issuing instructions under elect.sync (see umma_gemm.cuh).
   if (warp == 0) {
@@ -147,24 +159,27 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t loP = umma::desc_lo(umma::smem_u32(sP));
     auto issue_pv = [&](int i) {
       const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
-      umma::mbar_wait(&p_full[pb], (i / NPB) & 1);
-      umma::mbar_wait(&pv_empty[b], ((i >> 1) & 1) ^ 1);
-      umma::fence_after();
-      if (umma::elect_one()) {
-        const uint32_t lov = loKV + (j & 1) * (Cfg::KV_STAGE_BYTES >> 4) + TERMS * (8192 >> 4) + hh * (DH * 128 >> 4);
-        const uint32_t lop = loP + pb * (Cfg::P_BYTES >> 4);
 #pragma unroll
-        for (int pr = 0; pr < Cfg::NPROD; ++pr) {
+      for (int wg = 0; wg < 2; ++wg) {   // each warpgroup's 32 keys accumulate into their own PV buffer
+        umma::mbar_wait(&p_full[wg * 2 + pb], (i / NPB) & 1);
+        umma::mbar_wait(&pv_empty[wg * 2 + b], ((i >> 1) & 1) ^ 1);
+        umma::fence_after();
+        if (umma::elect_one()) {
+          const uint32_t lov = loKV + (j & 1) * (Cfg::KV_STAGE_BYTES >> 4) + TERMS * (8192 >> 4) + hh * (DH * 128 >> 4) + 4 * wg;
+          const uint32_t lop = loP + pb * (Cfg::P_BYTES >> 4) + 4 * wg;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma::mma_bf16(tmPV + b * 64, umma::desc_make(lop + prod_a(pr) * (16384 >> 4) + 2 * k),
-                           umma::desc_make(lov + prod_b(pr) * (8192 >> 4) + 2 * k), idPV, (pr | k) != 0 ? 1u : 0u);
+          for (int pr = 0; pr < Cfg::NPROD; ++pr) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              umma::mma_bf16(tmPV + (wg * 2 + b) * 64, umma::desc_make(lop + prod_a(pr) * (16384 >> 4) + 2 * k),
+                             umma::desc_make(lov + prod_b(pr) * (8192 >> 4) + 2 * k), idPV, (pr | k) != 0 ? 1u : 0u);
+          }
+          umma::mma_commit(&pv_full[wg * 2 + b]);
+          umma::mma_commit(&p_empty[wg * 2 + pb]);
+          if (wg == 1 && hh == G - 1) umma::mma_commit(&kv_empty[j & 1]);
         }
-        umma::mma_commit(&pv_full[b]);
-        umma::mma_commit(&p_empty[pb]);
-        if (hh == G - 1) umma::mma_commit(&kv_empty[j & 1]);
+        __syncwarp();
       }
-      __syncwarp();
     };
     umma::mbar_wait(q_full, 0);
     for (int i = 0; i < n_iter; ++i) {
@@ -189,7 +204,8 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     issue_pv(n_iter - 1);
   } else if (warp >= 4) {
-    // ================= softmax / output =================
+    // ================= softmax / output (2 warpgroups, key-column split) =================
+    const int wg = (warp - 4) >> 2;
     const int wq = warp & 3;
     const int trow = wq * 32 + lane;                 // query row inside the tile == TMEM lane
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
@@ -201,16 +217,17 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       for (int c = 0; c < DH; ++c) o[h][c] = 0.f;
     }
     float alpha_pend = 1.f;
+    const uint32_t sP_u32 = umma::smem_u32(sP);
     auto consume_pv = [&](int i, float alpha) {
       const int b = i & 1, hh = i % G;
-      umma::mbar_wait(&pv_full[b], (i >> 1) & 1);
+      umma::mbar_wait(&pv_full[wg * 2 + b], (i >> 1) & 1);
       umma::fence_after();
       float v[DH];
-      umma::tmem_ld32(tmPV + lane_addr + b * 64, v);
-      if (DH == 64) umma::tmem_ld32(tmPV + lane_addr + b * 64 + 32, v + (DH == 64 ? 32 : 0));
+      umma::tmem_ld32(tmPV + lane_addr + (wg * 2 + b) * 64, v);
+      if (DH == 64) umma::tmem_ld32(tmPV + lane_addr + (wg * 2 + b) * 64 + 32, v + (DH == 64 ? 32 : 0));
       umma::tmem_ld_wait();
       umma::fence_before();
-      umma::mbar_arrive(&pv_empty[b]);
+      umma::mbar_arrive(&pv_empty[wg * 2 + b]);
 #pragma unroll
       for (int h = 0; h < G; ++h)
         if (h == hh) {
@@ -222,40 +239,43 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
       umma::mbar_wait(&s_full[b], (i >> 1) & 1);
       umma::fence_after();
-      float s[64];
-      umma::tmem_ld32(tmS + lane_addr + b * 64, s);
-      umma::tmem_ld32(tmS + lane_addr + b * 64 + 32, s + 32);
+      float s[32];
+      umma::tmem_ld32(tmS + lane_addr + b * 64 + wg * 32, s);
       umma::tmem_ld_wait();
       umma::fence_before();
       umma::mbar_arrive(&s_empty[b]);
-      const int nvalid = (j < nb_main) ? ::min(64, p.n_keys - j * 64) : p.n_extra;
-      if (nvalid < 64) {   // warp-uniform: only the ragged last block (and the 2-key extra block) is masked
+      const int nv_blk = (j < nb_main) ? ::min(64, p.n_keys - j * 64) : p.n_extra;
+      const int nvalid = ::max(0, ::min(32, nv_blk - 32 * wg));   // valid keys among this warpgroup's 32 columns
+      float alpha = 1.f, mnew = 0.f;
+      if (nvalid > 0) {   // warp-uniform
+        if (nvalid < 32) {
 #pragma unroll
-        for (int c = 0; c < 64; ++c) s[c] = c < nvalid ? s[c] : -INFINITY;
+          for (int c = 0; c < 32; ++c) s[c] = c < nvalid ? s[c] : -INFINITY;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int c = 1; c < 32; ++c) mx = fmaxf(mx, s[c]);
+        float mold = 0.f;
+#pragma unroll
+        for (int h = 0; h < G; ++h)
+          if (h == hh) { mold = m[h]; mnew = fmaxf(mold, mx); m[h] = mnew; }
+        alpha = umma::ex2_approx(mold - mnew);
       }
-      float mx = s[0];
-#pragma unroll
-      for (int c = 1; c < 64; ++c) mx = fmaxf(mx, s[c]);
-      float mold = 0.f, mnew = 0.f;
-#pragma unroll
-      for (int h = 0; h < G; ++h)
-        if (h == hh) { mold = m[h]; mnew = fmaxf(mold, mx); m[h] = mnew; }
-      const float alpha = umma::ex2_approx(mold - mnew);
       // P planes -> smem (K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7)); exp2 + split fused per chunk
-      umma::mbar_wait(&p_empty[pb], ((i / NPB) & 1) ^ 1);
-      uint8_t* pbase = sP + pb * Cfg::P_BYTES + trow * 128;
+      umma::mbar_wait(&p_empty[wg * 2 + pb], ((i / NPB) & 1) ^ 1);
+      const uint32_t prow = sP_u32 + pb * Cfg::P_BYTES + trow * 128;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
+      for (int ch = 0; ch < 4; ++ch) {
         uint32_t pk[TERMS][4];
         if (ch * 8 < nvalid) {   // warp-uniform: fully masked 8-key chunks cost no exp2
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float a = umma::ex2_approx(s[ch * 8 + 2 * e] - mnew);
-            const float b = umma::ex2_approx(s[ch * 8 + 2 * e + 1] - mnew);
-            rs0 += a; rs1 += b;
+            const float bb = umma::ex2_approx(s[ch * 8 + 2 * e + 1] - mnew);
+            rs0 += a; rs1 += bb;
             uint32_t sp[TERMS];
-            umma::split_bf16_pair<TERMS>(a, b, sp);
+            umma::split_bf16_pair<TERMS>(a, bb, sp);
 #pragma unroll
             for (int t = 0; t < TERMS; ++t) pk[t][e] = sp[t];
           }
@@ -267,45 +287,63 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
 #pragma unroll
         for (int t = 0; t < TERMS; ++t)
-          *reinterpret_cast<uint4*>(pbase + t * 16384 + ((ch ^ (trow & 7)) << 4)) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
+          st_shared_v4(prow + t * 16384 + (((4 * wg + ch) ^ (trow & 7)) << 4), pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
       }
 #pragma unroll
       for (int h = 0; h < G; ++h)
         if (h == hh) l[h] = l[h] * alpha + (rs0 + rs1);
       umma::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      umma::mbar_arrive(&p_full[pb]);
+      umma::mbar_arrive(&p_full[wg * 2 + pb]);
       if (i > 0) consume_pv(i - 1, alpha_pend);
       alpha_pend = alpha;
     }
     consume_pv(n_iter - 1, alpha_pend);
-    // ---- normalise and store
+    // ---- merge the two key-subset partials (warpgroup 1 -> smem -> warpgroup 0), normalise, store
+    constexpr int XS = G * (DH + 2) + 2;             // floats per row in the exchange buffer (stride 68 or 70: 8-byte aligned)
+    float* xch = reinterpret_cast<float*>(sKV) + trow * XS;   // K/V stages are dead: every MMA has completed
+    if (wg == 1) {
+#pragma unroll
+      for (int h = 0; h < G; ++h) {
+        xch[h * (DH + 2)] = m[h];
+        xch[h * (DH + 2) + 1] = l[h];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) xch[h * (DH + 2) + 2 + c] = o[h][c];
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps only
     const int row = q0 + trow;
-    if (row < p.T) {
+    if (wg == 0 && row < p.T) {
       const long long grow = (long long)r * p.T + row;
 #pragma unroll
       for (int h = 0; h < G; ++h) {
-        const float inv = 1.f / l[h];
+        const float m1 = xch[h * (DH + 2)], l1 = xch[h * (DH + 2) + 1];
+        const float mm = fmaxf(m[h], m1);
+        const float w0 = umma::ex2_approx(m[h] - mm), w1 = umma::ex2_approx(m1 - mm);   // exp2(-inf) = 0 for an empty subset
+        const float inv = 1.f / (l[h] * w0 + l1 * w1);
+        const float f0 = w0 * inv, f1 = w1 * inv;
+#pragma unroll
+        for (int c = 0; c < DH; ++c) o[h][c] = o[h][c] * f0 + xch[h * (DH + 2) + 2 + c] * f1;
         const int col = g * 64 + h * DH;
         if (p.O) {
           float* dst = p.O + grow * p.o_ld + col;
 #pragma unroll
           for (int c = 0; c < DH; c += 4)
-            *reinterpret_cast<float4*>(dst + c) = make_float4(o[h][c] * inv, o[h][c + 1] * inv, o[h][c + 2] * inv, o[h][c + 3] * inv);
+            *reinterpret_cast<float4*>(dst + c) = make_float4(o[h][c], o[h][c + 1], o[h][c + 2], o[h][c + 3]);
         }
         if (p.Op) {
 #pragma unroll
           for (int c = 0; c < DH; c += 8) {
-            __nv_bfloat16 pl[TERMS][8];
+            uint32_t pk[TERMS][4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              __nv_bfloat16 sp[TERMS];
-              umma::split_bf16<TERMS>(o[h][c + e] * inv, sp);
+            for (int e = 0; e < 4; ++e) {
+              uint32_t sp[TERMS];
+              umma::split_bf16_pair<TERMS>(o[h][c + 2 * e], o[h][c + 2 * e + 1], sp);
 #pragma unroll
-              for (int t = 0; t < TERMS; ++t) pl[t][e] = sp[t];
+              for (int t = 0; t < TERMS; ++t) pk[t][e] = sp[t];
             }
 #pragma unroll
             for (int t = 0; t < TERMS; ++t)
-              *reinterpret_cast<uint4*>(p.Op + t * p.op_plane_stride + grow * p.o_ld + col + c) = *reinterpret_cast<const uint4*>(pl[t]);
+              *reinterpret_cast<uint4*>(p.Op + t * p.op_plane_stride + grow * p.o_ld + col + c) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
           }
         }
       }
@@ -314,7 +352,7 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   if (warp == 2) {
     umma::fence_after();
-    umma::tmem_dealloc<256>(tmem_base);
+    umma::tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -346,7 +384,7 @@ int launch_umma_attn_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStrea
     tkx = tk[0]; tvx = tv[0];
   }
   dim3 grid(ceil_div(p.T, 128), p.D / 64, p.R);
-  umma_attn_kernel<TERMS, DH><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tq, tk[0], tk[1], tv[0], tv[1], tkx, tvx, p);
+  umma_attn_kernel<TERMS, DH><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk[0], tk[1], tv[0], tv[1], tkx, tvx, p);
   A2P_CUDA(cudaGetLastError());
   return 0;
 }

@@ -28,6 +28,10 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
 int a2p_test_simt_attention(int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K, const float* V,
                             const float* Kx, const float* Vx, float* O, int iters, float* ms_out, void* stream);
 
+/* micro-benchmark: total SM cycles for n_mma back-to-back tcgen05.mma (M=128, K=16, bf16) with the given N, A operand
+ * from shared memory (0) or tensor memory (1); result written to the DEVICE pointer cycles_out_dev[0]. */
+int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

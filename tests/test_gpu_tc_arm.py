@@ -1,0 +1,125 @@
+"""-m gpu: the tensor-core arm (split-bf16 tcgen05 GEMM + attention, split_terms 2 and 3) against the reference's
+golden outputs, plus isolated unit tests of the two tcgen05 kernels against fp64 and the exact-fp32 FFMA kernels.
+Tolerance as in test_gpu_parity.py: rtol 1e-3 / atol 1e-4 elementwise for pose; face CFG (g=10) scaled by max|ref|."""
+import ctypes as C
+import math
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.cases import CASES, make_inputs, weights_of
+
+pytestmark = pytest.mark.gpu
+RTOL, ATOL = 1e-3, 1e-4
+
+
+def _build(case, resp, terms):
+    from audio2photoreal_b200.api import CFGDenoiser, create_model_and_diffusion, load_model
+    args = Namespace(data_format=case.fmt, add_frame_cond=1 if case.fmt == "pose" else None, max_seq_length=600,
+                     layers=case.L, heads=case.H, not_rotary=False, unconstrained=False, device="cuda",
+                     timestep_respacing=resp, noise_schedule="cosine", sigma_small=True, lambda_vel=0.0, model_path="x",
+                     resume_trans=None, split_terms=terms)
+    model, sampler = create_model_and_diffusion(args, "test")
+    load_model(model, weights_of(case))
+    model = model.cuda().eval()
+    return model, CFGDenoiser(model), sampler
+
+
+def _close(got, ref, strict, what):
+    got, ref = got.detach().double().cpu(), torch.as_tensor(ref).double()
+    d = (got - ref).abs()
+    scale = 1.0 if strict else max(1.0, ref.abs().max().item())
+    bad = d > ATOL * scale + RTOL * ref.abs()
+    assert not bad.any(), f"{what}: {bad.double().mean().item():.3%} outside tolerance, max|d|={d.max().item():.3e}"
+
+
+@pytest.mark.parametrize("terms", [2, 3])
+@pytest.mark.parametrize("name", ["pose_small", "face_small", "pose_full", "face_full"])
+def test_tc_forward_vs_reference_golden(golden_dir, name, terms):
+    case, g = CASES[name], np.load(os.path.join(golden_dir, f"fwd_{name}.npz"))
+    inp = make_inputs(case)
+    model, cfg, _ = _build(case, "ddim10", terms)
+    y = {"audio_embed": inp["feats"].cuda(), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"], "scale": inp["scale"].cuda()}
+    x, t = inp["x"].cuda(), inp["times"].cuda()
+    _close(model(x, t, y, cond_drop_prob=0.0), g["cond"], True, f"{name}/cond/terms{terms}")
+    _close(model(x, t, y, cond_drop_prob=1.0), g["uncond"], True, f"{name}/uncond/terms{terms}")
+    _close(cfg(x, t, y), g["cfg"], case.fmt == "pose", f"{name}/cfg/terms{terms}")
+
+
+@pytest.mark.parametrize("terms", [2, 3])
+@pytest.mark.parametrize("name,resp", [("pose_small", "ddim10"), ("pose_small", "ddim100"), ("pose_full", "ddim10"),
+                                       ("face_cfg1", "ddim10")])
+def test_tc_loops_vs_reference_golden(golden_dir, name, resp, terms):
+    case = CASES[name]
+    model, cfg, sampler = _build(case, resp, terms)
+    inp = make_inputs(case)
+    y = {"audio_embed": inp["feats"].cuda(), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"], "scale": inp["scale"].cuda()}
+    ref = np.load(os.path.join(golden_dir, f"loop_ddim_{name}_{resp}.npz"))["result"]
+    res = sampler.ddim_sample_loop(cfg, tuple(inp["x"].shape), noise=inp["x"].cuda(), clip_denoised=False, model_kwargs={"y": y})
+    _close(res, ref, case.fmt == "pose", f"{name}/{resp}/terms{terms}")
+    assert model.launch_count() > 0
+
+
+def _lib():
+    from audio2photoreal_b200 import _lib
+    lib = _lib.load()
+    vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
+    lib.a2p_test_tc_gemm_scratch_bytes.argtypes = [i32] * 4
+    lib.a2p_test_tc_gemm_scratch_bytes.restype = sz
+    lib.a2p_test_tc_gemm.argtypes = [i32] * 6 + [vp, vp, vp, vp, vp, sz, i32, C.POINTER(C.c_float), vp]
+    lib.a2p_test_tc_attention_scratch_bytes.argtypes = [i32] * 5
+    lib.a2p_test_tc_attention_scratch_bytes.restype = sz
+    lib.a2p_test_tc_attention.argtypes = [i32] * 7 + [vp] * 7 + [sz, i32, C.POINTER(C.c_float), vp]
+    return _lib, lib
+
+
+@pytest.mark.parametrize("terms,tol", [(1, 4e-3), (2, 2e-5), (3, 8e-6)])
+@pytest.mark.parametrize("M,N,K,taps,dil", [(128, 128, 64, 1, 0), (200, 104, 104, 1, 0), (300, 104, 104, 3, 2),
+                                            (1000, 256, 1024, 1, 0), (9600, 768, 256, 1, 0)])
+def test_tcgen05_gemm_unit(terms, tol, M, N, K, taps, dil):
+    """C = A W^T + b incl. ragged M, N=104, K tail (TMA zero fill) and the 3-tap dilated conv addressing."""
+    _l, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(taps, N, K, device="cuda", generator=g) / K ** 0.5
+    b = torch.randn(N, device="cuda", generator=g)
+    out = torch.full((M, N), float("nan"), device="cuda")
+    nb = lib.a2p_test_tc_gemm_scratch_bytes(M, N, K, taps)
+    scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    ms = C.c_float()
+    _l.check(lib.a2p_test_tc_gemm(terms, M, N, K, taps, dil, A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(),
+                                  scratch.data_ptr(), nb, 1, C.byref(ms), torch.cuda.current_stream().cuda_stream))
+    ref = b.double().expand(M, N).clone()
+    for j in range(taps):
+        sh = (taps - 1 - j) * dil
+        Ash = A.double() if sh == 0 else torch.cat([torch.zeros(sh, K, device="cuda", dtype=torch.float64), A.double()[:-sh]])
+        ref += Ash @ W[j].double().T
+    err = (out.double() - ref).abs().max().item() / ref.abs().max().item()
+    assert err < tol, err
+
+
+@pytest.mark.parametrize("terms,tol", [(2, 4e-5), (3, 8e-6)])
+@pytest.mark.parametrize("R,T,D,dh,S,nx", [(1, 128, 64, 32, 64, 0), (2, 100, 256, 32, 77, 2), (2, 200, 512, 64, 211, 2),
+                                           (4, 600, 256, 32, 1998, 2), (3, 600, 256, 32, 20, 0)])
+def test_tcgen05_attention_unit(terms, tol, R, T, D, dh, S, nx):
+    """softmax(QK^T/sqrt(dh))V incl. ragged query tile, ragged key block, the 2 extra keys and both head sizes."""
+    _l, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(R * 1000 + T + S)
+    Q, K, V = (torch.randn(R, n, D, device="cuda", generator=g) for n in (T, S, S))
+    Kx, Vx = (torch.randn(R, max(nx, 1), D, device="cuda", generator=g) for _ in range(2))
+    O = torch.full((R, T, D), float("nan"), device="cuda")
+    nb = lib.a2p_test_tc_attention_scratch_bytes(R, T, D, S, nx)
+    scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    ms = C.c_float()
+    _l.check(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(),
+                                       Vx.data_ptr(), O.data_ptr(), scratch.data_ptr(), nb, 1, C.byref(ms),
+                                       torch.cuda.current_stream().cuda_stream))
+    H = D // dh
+    Kf = torch.cat([K, Kx[:, :nx]], 1) if nx else K
+    Vf = torch.cat([V, Vx[:, :nx]], 1) if nx else V
+    sp = lambda t: t.double().view(R, -1, H, dh).transpose(1, 2)
+    ref = (torch.softmax(sp(Q) @ sp(Kf).transpose(-1, -2) / math.sqrt(dh), -1) @ sp(Vf)).transpose(1, 2).reshape(R, T, D)
+    assert (O.double() - ref).abs().max().item() < tol
