@@ -8,6 +8,7 @@
 //   diffusion/gaussian_diffusion.py:667-718,434-477  DDIM / ancestral update (K3)
 //   diffusion/respace.py:140-145                     timestep_map lookup (host builds the table)
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -74,6 +75,7 @@ struct a2p_denoiser {
   std::map<const float*, __nv_bfloat16*> wplanes;  // fp32 weight -> split-bf16 planes [P][rows][cols] (plane stride = numel)
   std::map<const float*, long long> wnumel;
   int num_sms = 148;
+  int attn_skew_ns = 0;   // measured: no effect (profiles/r01f_attention_experiments.txt)
   CondSet cond[2];
   int64_t launches = 0;
   int64_t graph_nodes = 0;
@@ -239,15 +241,18 @@ enum Cat : int { CAT_COND = 0, CAT_LN, CAT_PROJ, CAT_ATT_SELF, CAT_ATT_CROSS, CA
 struct Prof {
   std::vector<cudaEvent_t> ev;
   std::vector<int> cat;
+  std::vector<std::string> info;
 };
 struct Ctx {
   a2p_denoiser* h;
   cudaStream_t st;
   Prof* prof = nullptr;
   int cat = CAT_MISC;
+  std::string tag;
   void begin() {
     if (!prof) return;
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); prof->ev.push_back(e); prof->cat.push_back(cat);
+    prof->info.push_back(tag); tag.clear();
   }
   void end() {
     if (!prof) return;
@@ -263,6 +268,7 @@ int gemm(Ctx& c, const float* A, long long lda, int M, const float* W, long long
   if (p.taps == 0) { p.taps = 1; p.dil = 0; p.Kc = K; }
   p.epi = epi;
   c.h->launches++;
+  if (c.prof) { char b_[96]; snprintf(b_, sizeof(b_), "ffma_gemm M=%d N=%d K=%d epi=%d", M, N, K, epi); c.tag = b_; }
   c.begin();
   int rc = skinny_ok(p) ? launch_skinny_gemm(p, c.st) : launch_sgemm(p, c.st);
   c.end();
@@ -288,6 +294,7 @@ int tc_gemm(Ctx& c, const __nv_bfloat16* Ap, int M, int K, const float* wkey, lo
   p.M = M; p.N = N; p.K = K; p.bias = bias;
   if (p.out_scale == 0.f) p.out_scale = 1.f;
   h->launches++;
+  if (c.prof) { char b_[96]; snprintf(b_, sizeof(b_), "tc_gemm M=%d N=%d K=%d taps=%d epi=%d", M, N, K, p.taps, epi); c.tag = b_; }
   c.begin();
   int rc = launch_umma_gemm(h->cfg.split_terms, o, p, epi, h->num_sms, c.st);
   c.end();
@@ -423,6 +430,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     TcAttnParams ap{};
     o.Q = qkP; o.q_rows = MT; o.q_ld = 2 * D; o.q_plane_stride = (long long)MT * 2 * D;
     o.vt_rows = D;
+    ap.skew_ns = h->attn_skew_ns;
     ap.T = T; ap.R = R; ap.D = D; ap.dh = dh; ap.q_col0 = 0; ap.Op = attP; ap.op_plane_stride = pstrideD; ap.o_ld = D; ap.O = nullptr;
     if (kind == 0) {
       o.K[0] = qkP; o.k_rows[0] = MT; o.k_ld[0] = 2 * D; o.k_plane_stride[0] = (long long)MT * 2 * D;
@@ -745,6 +753,7 @@ int a2p_denoiser_create(a2p_denoiser_t** out, const a2p_model_cfg* cfg) {
   h->cfg = *cfg;
   h->dh = cfg->D / cfg->H;
   h->nf = cfg->fmt == A2P_FMT_POSE ? 4 : 3;
+  if (getenv("A2P_ATTN_SKEW_NS")) h->attn_skew_ns = atoi(getenv("A2P_ATTN_SKEW_NS"));
   *out = h;
   return 0;
 }
@@ -1096,11 +1105,13 @@ int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, con
   A2P_TRY(forward_core(c, B, T, x_btc, (const long long*)timesteps, nullptr, branch_mask, (char*)ws, &x0c, &x0u, &ss));
   A2P_CUDA(cudaStreamSynchronize(c.st));
   for (int i = 0; i < ncat; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
+  const bool dump = getenv("A2P_PROFILE_DUMP") != nullptr;
   for (size_t i = 0; i < prof.cat.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
     ms_by_cat[prof.cat[i]] += ms;
     launches_by_cat[prof.cat[i]]++;
+    if (dump) fprintf(stderr, "a2p_prof %3zu cat=%d %8.1f us  %s\n", i, prof.cat[i], ms * 1e3f, prof.info[i].c_str());
   }
   for (auto e : prof.ev) cudaEventDestroy(e);
   return 0;
@@ -1149,7 +1160,7 @@ int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_d
 size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_extra) {
   const size_t Sp = align_up((size_t)S, 8), Xp = 8;
   return (align_up((size_t)3 * R * T * D, 512) + align_up((size_t)3 * R * S * D, 512) + align_up((size_t)3 * D * R * Sp, 512) +
-          align_up((size_t)3 * R * 8 * D, 512) + align_up((size_t)3 * D * R * Xp, 512)) * 2 + 8192;
+          align_up((size_t)3 * R * 8 * D, 512) + align_up((size_t)3 * D * R * Xp, 512)) * 2 + 8192 + 64 * 16 * 8;
 }
 
 int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K,
@@ -1188,7 +1199,14 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   p.T = T; p.R = R; p.D = D; p.dh = dh; p.rows_per_branch = R; p.q_col0 = 0; p.k_col0 = 0; p.n_keys = S; p.n_extra = n_extra;
   p.k_row_stride[0] = S; p.v_col_stride[0] = Sp; p.kx_col0 = 0; p.kx_row_stride = 8; p.vx_row0 = 0; p.vx_col_stride = (int)Xp;
   p.O = O; p.o_ld = D; p.Op = nullptr;
+  p.skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : 0;
+  p.trace = (iters < 0) ? reinterpret_cast<long long*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) : nullptr;   // iters < 0: trace mode
   A2P_TRY(launch_umma_attn(terms, o, p, st));
+  if (iters < 0) {
+    A2P_CUDA(cudaStreamSynchronize(st));
+    A2P_CUDA(cudaMemcpy(O, p.trace, 64 * 16 * sizeof(long long), cudaMemcpyDeviceToDevice));   // trace returned in the O buffer
+    return 0;
+  }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);

@@ -189,5 +189,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exp2(x) for x <= 0 on the FMA/ALU pipes (no MUFU): round-to-nearest range reduction x = n + f, |f| <= 0.5,
+// degree-6 Taylor of 2^f (|rel err| < 1.3e-7), exponent patched in with an integer add.  Used for a fraction of the
+// softmax elements because MUFU.EX2 (8 lanes/clk/SM on B200) is the bottleneck of the dh = 32 attention.
+__device__ __forceinline__ float ex2_poly(float x) {
+  const float t = fmaxf(x, -125.f);
+  const float z = t + 12582912.f;                       // 1.5 * 2^23: the low mantissa bits of z hold round(t)
+  const float f = t - (z - 12582912.f);
+  float p = 1.5403530e-4f;
+  p = fmaf(p, f, 1.3333558e-3f);
+  p = fmaf(p, f, 9.6181291e-3f);
+  p = fmaf(p, f, 5.5504109e-2f);
+  p = fmaf(p, f, 2.4022651e-1f);
+  p = fmaf(p, f, 6.9314718e-1f);
+  p = fmaf(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(z) << 23));
+}
+
 }  // namespace umma
 }  // namespace a2p

@@ -22,6 +22,10 @@
 #include "umma.cuh"
 #include "umma_gemm.cuh"
 
+#ifndef A2P_POLY_OF_4
+#define A2P_POLY_OF_4 0
+#endif
+
 namespace a2p {
 
 struct TcAttnParams {
@@ -35,6 +39,8 @@ struct TcAttnParams {
   int vx_row0, vx_col_stride; // extra V^T tensor: row of group 0 (= layer * D), columns per sample (2)
   __nv_bfloat16* Op; long long op_plane_stride; long long o_ld;   // output planes [TERMS][R*T][o_ld]
   float* O;                                                       // optional fp32 output [R*T][o_ld] (tests)
+  int skew_ns;                                                    // start delay of softmax warpgroup 1 (see kernel)
+  long long* trace;                                               // optional [64 iters][16] clock64 timestamps of CTA (0,0,0) (diagnostics)
 };
 
 template <int TERMS>
@@ -181,10 +187,13 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
       }
     };
+    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
     umma::mbar_wait(q_full, 0);
     for (int i = 0; i < n_iter; ++i) {
       const int j = i / G, hh = i - j * G, b = i & 1;
+      if (tr && i < 64) p.trace[i * 16 + 8] = clock64();
       if (hh == 0) umma::mbar_wait(&kv_full[j & 1], (j >> 1) & 1);
+      if (tr && i < 64) p.trace[i * 16 + 9] = clock64();
       umma::mbar_wait(&s_empty[b], ((i >> 1) & 1) ^ 1);
       umma::fence_after();
       if (umma::elect_one()) {
@@ -200,7 +209,9 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         umma::mma_commit(&s_full[b]);
       }
       __syncwarp();
+      if (tr && i < 64) p.trace[i * 16 + 10] = clock64();
       if (i > 0) issue_pv(i - 1);
+      if (tr && i < 64) p.trace[i * 16 + 11] = clock64();
     }
     issue_pv(n_iter - 1);
   } else if (warp >= 4) {
@@ -218,6 +229,9 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     }
     float alpha_pend = 1.f;
     const uint32_t sP_u32 = umma::smem_u32(sP);
+    // optional start skew of warpgroup 1 (experiment knob; measured no effect -- the softmax is issue/latency bound,
+    // not MUFU bound: profiles/r01f_attention_experiments.txt)
+    if (wg == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);
     auto consume_pv = [&](int i, float alpha) {
       const int b = i & 1, hh = i % G;
       umma::mbar_wait(&pv_full[wg * 2 + b], (i >> 1) & 1);
@@ -235,13 +249,17 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int c = 0; c < DH; ++c) o[h][c] = o[h][c] * alpha + v[c];
         }
     };
+    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     for (int i = 0; i < n_iter; ++i) {
       const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
+      if (tr && i < 64) p.trace[i * 16 + 0] = clock64();
       umma::mbar_wait(&s_full[b], (i >> 1) & 1);
       umma::fence_after();
+      if (tr && i < 64) p.trace[i * 16 + 1] = clock64();
       float s[32];
       umma::tmem_ld32(tmS + lane_addr + b * 64 + wg * 32, s);
       umma::tmem_ld_wait();
+      if (tr && i < 64) p.trace[i * 16 + 2] = clock64();
       umma::fence_before();
       umma::mbar_arrive(&s_empty[b]);
       const int nv_blk = (j < nb_main) ? ::min(64, p.n_keys - j * 64) : p.n_extra;
@@ -262,7 +280,9 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         alpha = umma::ex2_approx(mold - mnew);
       }
       // P planes -> smem (K-major SWIZZLE_128B: 16-byte chunk index XOR (row & 7)); exp2 + split fused per chunk
+      if (tr && i < 64) p.trace[i * 16 + 3] = clock64();
       umma::mbar_wait(&p_empty[wg * 2 + pb], ((i / NPB) & 1) ^ 1);
+      if (tr && i < 64) p.trace[i * 16 + 4] = clock64();
       const uint32_t prow = sP_u32 + pb * Cfg::P_BYTES + trow * 128;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
@@ -271,8 +291,10 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (ch * 8 < nvalid) {   // warp-uniform: fully masked 8-key chunks cost no exp2
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = umma::ex2_approx(s[ch * 8 + 2 * e] - mnew);
-            const float bb = umma::ex2_approx(s[ch * 8 + 2 * e + 1] - mnew);
+            // A2P_POLY_OF_4 of every 4 pairs take the FMA-pipe polynomial, the rest MUFU.EX2
+            const bool poly = e < A2P_POLY_OF_4;
+            const float a = poly ? umma::ex2_poly(s[ch * 8 + 2 * e] - mnew) : umma::ex2_approx(s[ch * 8 + 2 * e] - mnew);
+            const float bb = poly ? umma::ex2_poly(s[ch * 8 + 2 * e + 1] - mnew) : umma::ex2_approx(s[ch * 8 + 2 * e + 1] - mnew);
             rs0 += a; rs1 += bb;
             uint32_t sp[TERMS];
             umma::split_bf16_pair<TERMS>(a, bb, sp);
@@ -292,9 +314,12 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
       for (int h = 0; h < G; ++h)
         if (h == hh) l[h] = l[h] * alpha + (rs0 + rs1);
+      if (tr && i < 64) p.trace[i * 16 + 5] = clock64();
       umma::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       umma::mbar_arrive(&p_full[wg * 2 + pb]);
+      if (tr && i < 64) p.trace[i * 16 + 6] = clock64();
       if (i > 0) consume_pv(i - 1, alpha_pend);
+      if (tr && i < 64) p.trace[i * 16 + 7] = clock64();
       alpha_pend = alpha;
     }
     consume_pv(n_iter - 1, alpha_pend);

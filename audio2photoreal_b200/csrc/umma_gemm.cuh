@@ -177,54 +177,78 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias && col_ok && !p.bias_per_row) bb = __ldg(reinterpret_cast<const float4*>(p.bias + col));
         const float oscale = (p.scale_ncols == 0 || col < p.scale_ncols) ? p.out_scale : 1.f;
+        // two groups of 4 row-slices: all global loads of a group (residual x / skip / FiLM vectors) are issued
+        // BEFORE any store, otherwise every load->store pair serialises on a ~1 us global-memory round trip
+        // (the compiler cannot hoist loads over the stores that may alias them).
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rsub;
-          int row = m0 + wq * 32 + r;
-          if (row >= p.M || !col_ok) continue;
-          const float4 a = *reinterpret_cast<const float4*>(tw + r * 36 + c4);
-          if (p.bias_per_row && p.bias) { const float br_ = __ldg(p.bias + row); bb = make_float4(br_, br_, br_, br_); }
-          float o[4] = {a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w};
-          if (p.remap_rps > 0) row += (row / p.remap_rps + 1) * p.remap_pad;
-          if (EPI == TC_F32) {
-            *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) =
-                make_float4(o[0] * oscale, o[1] * oscale, o[2] * oscale, o[3] * oscale);
-          } else if (EPI == TC_FILM) {
-            const float* fs = p.film + (long long)(row / p.rows_per_sample) * p.film_ld;
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(fs + p.film_scale_off + col));
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(fs + p.film_shift_off + col));
-            float* cp = p.C + (long long)row * p.ldc + col;
-            const float4 x = *reinterpret_cast<const float4*>(cp);
-            *reinterpret_cast<float4*>(cp) = make_float4(x.x + ((sc.x + 1.f) * o[0] + sh.x), x.y + ((sc.y + 1.f) * o[1] + sh.y),
-                                                         x.z + ((sc.z + 1.f) * o[2] + sh.z), x.w + ((sc.w + 1.f) * o[3] + sh.w));
-          } else {
-            if (EPI == TC_GELU_PLANES) {
+        for (int grp = 0; grp < 2; ++grp) {
+          float4 av[4], xv[4], scv[4], shv[4];
+          int rows[4];
+          bool ok[4];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = gelu_erf(o[j]);
-            } else if (EPI == TC_LRELU_PLANES) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * p.slope;
-              if (p.skip) {
-                const float4 sk = *reinterpret_cast<const float4*>(p.skip + (long long)row * p.ldskip + col);
-                o[0] = (sk.x + o[0]) / 2.0f; o[1] = (sk.y + o[1]) / 2.0f; o[2] = (sk.z + o[2]) / 2.0f; o[3] = (sk.w + o[3]) / 2.0f;
+          for (int q = 0; q < 4; ++q) {
+            const int r = (grp * 4 + q) * 4 + rsub;
+            rows[q] = m0 + wq * 32 + r;
+            ok[q] = rows[q] < p.M && col_ok;
+            av[q] = *reinterpret_cast<const float4*>(tw + r * 36 + c4);
+            xv[q] = scv[q] = shv[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ok[q]) {
+              if (EPI == TC_FILM) {
+                const float* fs = p.film + (long long)(rows[q] / p.rows_per_sample) * p.film_ld;
+                scv[q] = __ldg(reinterpret_cast<const float4*>(fs + p.film_scale_off + col));
+                shv[q] = __ldg(reinterpret_cast<const float4*>(fs + p.film_shift_off + col));
+                xv[q] = *reinterpret_cast<const float4*>(p.C + (long long)rows[q] * p.ldc + col);
+              } else if (EPI == TC_LRELU_PLANES) {
+                if (p.skip) xv[q] = *reinterpret_cast<const float4*>(p.skip + (long long)rows[q] * p.ldskip + col);
               }
-              if (p.C) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.bias_per_row && p.bias) { const float br_ = __ldg(p.bias + rows[q]); scv[q].x = br_; }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (!ok[q]) continue;
+            int row = rows[q];
+            const float4 a = av[q];
+            float4 bq = bb;
+            if (p.bias_per_row && p.bias) bq = make_float4(scv[q].x, scv[q].x, scv[q].x, scv[q].x);
+            float o[4] = {a.x + bq.x, a.y + bq.y, a.z + bq.z, a.w + bq.w};
+            if (p.remap_rps > 0) row += (row / p.remap_rps + 1) * p.remap_pad;
+            if (EPI == TC_F32) {
+              *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) =
+                  make_float4(o[0] * oscale, o[1] * oscale, o[2] * oscale, o[3] * oscale);
+            } else if (EPI == TC_FILM) {
+              const float4 sc = scv[q], sh = shv[q], x = xv[q];
+              *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) =
+                  make_float4(x.x + ((sc.x + 1.f) * o[0] + sh.x), x.y + ((sc.y + 1.f) * o[1] + sh.y),
+                              x.z + ((sc.z + 1.f) * o[2] + sh.z), x.w + ((sc.w + 1.f) * o[3] + sh.w));
             } else {
+              if (EPI == TC_GELU_PLANES) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] *= oscale;
+                for (int j = 0; j < 4; ++j) o[j] = gelu_erf(o[j]);
+              } else if (EPI == TC_LRELU_PLANES) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] = o[j] > 0.f ? o[j] : o[j] * p.slope;
+                if (p.skip) {
+                  const float4 sk = xv[q];
+                  o[0] = (sk.x + o[0]) / 2.0f; o[1] = (sk.y + o[1]) / 2.0f; o[2] = (sk.z + o[2]) / 2.0f; o[3] = (sk.w + o[3]) / 2.0f;
+                }
+                if (p.C) *reinterpret_cast<float4*>(p.C + (long long)row * p.ldc + col) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[j] *= oscale;
+              }
+              uint32_t pk[TERMS][2];
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                uint32_t sp[TERMS];
+                umma::split_bf16_pair<TERMS>(o[2 * e], o[2 * e + 1], sp);
+#pragma unroll
+                for (int t = 0; t < TERMS; ++t) pk[t][e] = sp[t];
+              }
+#pragma unroll
+              for (int t = 0; t < TERMS; ++t)
+                *reinterpret_cast<uint2*>(p.Cp + t * p.cp_plane_stride + (long long)row * p.ldcp + col) = make_uint2(pk[t][0], pk[t][1]);
             }
-            __nv_bfloat16 pl[TERMS][4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              __nv_bfloat16 sp[TERMS];
-              umma::split_bf16<TERMS>(o[j], sp);
-#pragma unroll
-              for (int i = 0; i < TERMS; ++i) pl[i][j] = sp[i];
-            }
-#pragma unroll
-            for (int i = 0; i < TERMS; ++i)
-              *reinterpret_cast<uint2*>(p.Cp + i * p.cp_plane_stride + (long long)row * p.ldcp + col) =
-                  *reinterpret_cast<const uint2*>(pl[i]);
           }
         }
         __syncwarp();
