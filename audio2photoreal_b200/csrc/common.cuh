@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string>
 
 namespace a2p {
@@ -49,6 +50,30 @@ struct BranchPtr {
     return base[br] + (long long)rr * stride[br];
   }
 };
+
+// ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl() may start while its stream
+// predecessor is still draining; it must call pdl_wait() before touching anything the predecessor wrote and
+// should call pdl_trigger() early so that ITS successor can be scheduled.  Only kernels containing pdl_wait()
+// may be launched with the attribute.  A2P_NO_PDL=1 in the environment disables the attribute (plain serialisation).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("A2P_NO_PDL") ? 0 : 1;
+  return v == 1;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float mishf(float x) {
   // x * tanh(softplus(x)); softplus threshold 20 like torch

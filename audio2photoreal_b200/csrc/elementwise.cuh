@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(256) ln_rope_planes_kernel(const float* __rest
   constexpr int PER = D / 32;
   constexpr int NV = PER / 4;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (warp >= rows) return;
   const float* xr = x + (long long)warp * ldx;
   float v[PER];
@@ -132,7 +134,7 @@ inline int launch_ln_rope_planes(int D, int terms, const float* x, long long ldx
                                  __nv_bfloat16* out_h, __nv_bfloat16* out_r, long long plane_stride, const float2* tab,
                                  int pos_mod, int pos_base, int rows, cudaStream_t st) {
   int blocks = ceil_div(rows, 8);
-#define A2P_LNP(DD, TT) ln_rope_planes_kernel<DD, TT><<<blocks, 256, 0, st>>>(x, ldx, w, b, out_h, out_r, plane_stride, tab, DD / 2, pos_mod, pos_base, rows)
+#define A2P_LNP(DD, TT) A2P_CUDA(launch_pdl(ln_rope_planes_kernel<DD, TT>, dim3(blocks), dim3(256), (size_t)0, st, x, ldx, w, b, out_h, out_r, plane_stride, tab, DD / 2, pos_mod, pos_base, rows))
   if (D == 256 && terms == 1) A2P_LNP(256, 1);
   else if (D == 256 && terms == 2) A2P_LNP(256, 2);
   else if (D == 256 && terms == 3) A2P_LNP(256, 3);

@@ -183,6 +183,21 @@ __device__ __forceinline__ void split_bf16_pair(float a, float b, uint32_t* out)
     }
   }
 }
+// Truncating variant for THREE planes: plane t = upper 16 bits of the running residual (PRMT picks them directly),
+// residual = x - (x & 0xFFFF0000) is exact.  Three truncated planes keep 3 x 7 = 21+ explicit mantissa bits
+// (|err| <= 2^-21 |x|, ~fp32 for softmax probabilities) for 2 ALU + 2 FMA-pipe ops per value instead of 7.
+__device__ __forceinline__ void split_bf16_pair_trunc3(float a, float b, uint32_t* out) {
+  const uint32_t a0 = __float_as_uint(a), b0 = __float_as_uint(b);
+  out[0] = __byte_perm(a0, b0, 0x7632);
+  a = a - __uint_as_float(a0 & 0xFFFF0000u);
+  b = b - __uint_as_float(b0 & 0xFFFF0000u);
+  const uint32_t a1 = __float_as_uint(a), b1 = __float_as_uint(b);
+  out[1] = __byte_perm(a1, b1, 0x7632);
+  a = a - __uint_as_float(a1 & 0xFFFF0000u);
+  b = b - __uint_as_float(b1 & 0xFFFF0000u);
+  out[2] = __byte_perm(__float_as_uint(a), __float_as_uint(b), 0x7632);
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

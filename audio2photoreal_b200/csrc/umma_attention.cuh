@@ -25,6 +25,9 @@
 #ifndef A2P_POLY_OF_4
 #define A2P_POLY_OF_4 0
 #endif
+#ifndef A2P_ATTN_TRACE
+#define A2P_ATTN_TRACE 0   // 1: clock64 timeline of CTA (0,0,0) into TcAttnParams::trace (scripts/gpu_attn_trace.py)
+#endif
 
 namespace a2p {
 
@@ -115,10 +118,12 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
+  pdl_trigger();
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
   const uint32_t tmS = tmem_base, tmPV = tmem_base + 128;   // S buffers: +0, +64 ; PV buffers [wg][b]: +128 + (wg*2+b)*64
 
   // Single-thread roles run warp-uniformly with only the issuing instructions under elect.sync (see umma_gemm.cuh).
@@ -187,7 +192,7 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         __syncwarp();
       }
     };
-    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
+    const bool tr = A2P_ATTN_TRACE && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && lane == 0;
     umma::mbar_wait(q_full, 0);
     for (int i = 0; i < n_iter; ++i) {
       const int j = i / G, hh = i - j * G, b = i & 1;
@@ -249,7 +254,7 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
           for (int c = 0; c < DH; ++c) o[h][c] = o[h][c] * alpha + v[c];
         }
     };
-    const bool tr = p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
+    const bool tr = A2P_ATTN_TRACE && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 128;
     for (int i = 0; i < n_iter; ++i) {
       const int j = i / G, hh = i - j * G, b = i & 1, pb = i % NPB;
       if (tr && i < 64) p.trace[i * 16 + 0] = clock64();
@@ -297,7 +302,8 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             const float bb = poly ? umma::ex2_poly(s[ch * 8 + 2 * e + 1] - mnew) : umma::ex2_approx(s[ch * 8 + 2 * e + 1] - mnew);
             rs0 += a; rs1 += bb;
             uint32_t sp[TERMS];
-            umma::split_bf16_pair<TERMS>(a, bb, sp);
+            if (TERMS == 3) umma::split_bf16_pair_trunc3(a, bb, sp);   // probabilities in [0,1]: 21+ bits are plenty
+            else umma::split_bf16_pair<TERMS>(a, bb, sp);
 #pragma unroll
             for (int t = 0; t < TERMS; ++t) pk[t][e] = sp[t];
           }
@@ -409,8 +415,8 @@ int launch_umma_attn_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStrea
     tkx = tk[0]; tvx = tv[0];
   }
   dim3 grid(ceil_div(p.T, 128), p.D / 64, p.R);
-  umma_attn_kernel<TERMS, DH><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tq, tk[0], tk[1], tv[0], tv[1], tkx, tvx, p);
-  A2P_CUDA(cudaGetLastError());
+  A2P_CUDA(launch_pdl(umma_attn_kernel<TERMS, DH>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0],
+                      tv[1], tkx, tvx, p));
   return 0;
 }
 

@@ -86,10 +86,12 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<2 * TC_BN>(tmem_slot);
+  pdl_trigger();   // the successor may be scheduled as soon as this CTA's resources free up
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   // NOTE on the two single-thread roles: the whole warp runs the loops (all values stay warp-uniform, so the
   // compiler keeps descriptors / TMEM addresses in uniform registers) and only the issuing instructions sit under
@@ -313,8 +315,7 @@ int launch_umma_gemm_t(const TcOperands& o, const TcGemmParams& p, int num_sms, 
                             CU_TENSOR_MAP_SWIZZLE_128B));
   const int n_tiles = ceil_div(p.M, TC_BM) * ceil_div(p.N, TC_BN);
   const int grid = n_tiles < num_sms ? n_tiles : num_sms;
-  umma_gemm_kernel<TERMS, EPI><<<grid, 256, Cfg::SMEM_BYTES, st>>>(tmA, tmW, p);
-  A2P_CUDA(cudaGetLastError());
+  A2P_CUDA(launch_pdl(umma_gemm_kernel<TERMS, EPI>, dim3(grid), dim3(256), (size_t)Cfg::SMEM_BYTES, st, tmA, tmW, p));
   return 0;
 }
 

@@ -251,10 +251,19 @@ class Denoiser(nn.Module):
             feats = torch.zeros(batch_size, T, self.cond_feature_dim, device=dev)
         else:
             feats = self._audio_features(y, dev)
-        tok = F.linear(feats, sd["cond_projection.weight"], sd["cond_projection.bias"])
-        if d.fmt == "face":
-            for i in range(2):
-                tok = self._encoder_layer(tok, sd, f"cond_encoder.{i}")
+        # One sample at a time: library GEMMs pick shape-dependent algorithms, and the result of a row must not
+        # depend on how the batch is sharded across GPUs (bit-identical 1-GPU vs W-GPU results, dist.py).
+        def per_sample(fn, t):
+            return torch.cat([fn(t[i:i + 1]) for i in range(t.shape[0])], dim=0)
+
+        def tokens_of(f1):
+            tk = F.linear(f1, sd["cond_projection.weight"], sd["cond_projection.bias"])
+            if d.fmt == "face":
+                for i in range(2):
+                    tk = self._encoder_layer(tk, sd, f"cond_encoder.{i}")
+            return tk
+
+        tok = per_sample(tokens_of, feats)
         S = tok.shape[1]
         if S > EMB_LEN:
             raise ValueError(f"{S} audio tokens exceed null_cond_embed's {EMB_LEN} rows (model/diffusion.py:136,378)")
@@ -271,13 +280,13 @@ class Denoiser(nn.Module):
             pred = y["keyframes"]
             new_mask = y["mask"][..., :: self.step].reshape(pred.shape[0], -1).to(pred.device)
             pred[~new_mask] = 0.0  # in place on the caller's tensor, like model/diffusion.py:318-320
-            ph = F.linear(pred.detach().clone().to(dev, torch.float32), sd["frame_cond_projection.weight"],
-                          sd["frame_cond_projection.bias"])
+            ph = per_sample(lambda k1: F.linear(k1, sd["frame_cond_projection.weight"], sd["frame_cond_projection.bias"]),
+                            pred.detach().clone().to(dev, torch.float32))
             pose_c = F.layer_norm(ph, (D,), sd["frame_norm_cond.weight"], sd["frame_norm_cond.bias"], 1e-5).contiguous()
             nk = pose_c.shape[1]
             pose_u = sd["null_pose_embed"][:, :nk].contiguous()
         sets = [
-            (0, batch_size, tok.contiguous(), hidden_of(tok).contiguous(), pose_c),
+            (0, batch_size, tok.contiguous(), per_sample(hidden_of, tok).contiguous(), pose_c),
             (1, 1, sd["null_cond_embed"][:, :S].contiguous(), sd["null_cond_hidden"].contiguous(), pose_u),
         ]
         st = torch.cuda.current_stream(dev).cuda_stream
