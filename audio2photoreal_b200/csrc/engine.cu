@@ -248,6 +248,7 @@ struct Ctx {
   cudaStream_t st;
   Prof* prof = nullptr;
   int cat = CAT_MISC;
+  bool skinny = false;   // route the next FFMA GEMMs to the warp-per-column kernel (per-step conditioning linears)
   std::string tag;
   void begin() {
     if (!prof) return;
@@ -270,7 +271,7 @@ int gemm(Ctx& c, const float* A, long long lda, int M, const float* W, long long
   c.h->launches++;
   if (c.prof) { char b_[96]; snprintf(b_, sizeof(b_), "ffma_gemm M=%d N=%d K=%d epi=%d", M, N, K, epi); c.tag = b_; }
   c.begin();
-  int rc = skinny_ok(p) ? launch_skinny_gemm(p, c.st) : launch_sgemm(p, c.st);
+  int rc = (c.skinny && skinny_ok(p)) ? launch_skinny_gemm(p, c.st) : launch_sgemm(p, c.st);
   c.end();
   return rc;
 }
@@ -366,6 +367,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
 
   // --- time conditioning (model/diffusion.py:384-389, model/utils.py:67-79)
   c.cat = CAT_COND;
+  c.skinny = true;
   time_embed_kernel<<<ceil_div(R * D / 2, 256), 256, 0, st>>>(ts, counter, B, R, D, h->time_freqs, e);
   h->launches++;
   A2P_TRY(gemm(c, e, D, R, h->time_w1, D, h->time_b1, 4 * D, D, th, 4 * D, EPI_MISH));
@@ -386,6 +388,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   A2P_TRY(gemm(c, mt, D, R, h->film_w, D, h->film_b, (int)film_ld, D, film, film_ld));
   // --- input projection (identical for both branches: computed once, duplicated)
   c.cat = CAT_IO_TCN;
+  c.skinny = false;
   if (cf.split_terms > 0) {
     __nv_bfloat16* xinP = reinterpret_cast<__nv_bfloat16*>(wsb + w.xinP);
     A2P_TRY(launch_split_planes(cf.split_terms, xin, C, xinP, (long long)B * T * C, (long long)B * T, C, 1.f, st));

@@ -170,11 +170,13 @@ namespace a2p {
 
 template <int MB>
 __global__ void __launch_bounds__(256) skinny_gemm_kernel(GemmParams p) {
-  extern __shared__ __align__(16) float sA[];   // [M][K]
+  extern __shared__ __align__(16) float sA[];   // [rows of this block][K]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < p.M * (p.K / 4); i += 256) {
+  const int row0 = blockIdx.y * MB;               // row block (the kernel choice never depends on M: batch-invariant results)
+  const int mrows = ::min(MB, p.M - row0);
+  for (int i = tid; i < mrows * (p.K / 4); i += 256) {
     const int r = i / (p.K / 4), c = i - r * (p.K / 4);
-    reinterpret_cast<float4*>(sA)[i] = *reinterpret_cast<const float4*>(p.A + (long long)r * p.lda + c * 4);
+    reinterpret_cast<float4*>(sA)[i] = *reinterpret_cast<const float4*>(p.A + (long long)(row0 + r) * p.lda + c * 4);
   }
   __syncthreads();
   const int n = blockIdx.x * 8 + warp;
@@ -187,7 +189,7 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(GemmParams p) {
     const float4 w = __ldg(reinterpret_cast<const float4*>(wr + k));
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
-      if (m < p.M) {
+      if (m < mrows) {
         const float4 a = *reinterpret_cast<const float4*>(sA + m * p.K + k);
         acc[m] = fmaf(a.x, w.x, acc[m]); acc[m] = fmaf(a.y, w.y, acc[m]);
         acc[m] = fmaf(a.z, w.z, acc[m]); acc[m] = fmaf(a.w, w.w, acc[m]);
@@ -203,12 +205,12 @@ __global__ void __launch_bounds__(256) skinny_gemm_kernel(GemmParams p) {
     const float b = p.bias ? p.bias[n] : 0.f;
 #pragma unroll
     for (int m = 0; m < MB; ++m) {
-      if (m >= p.M) break;
+      if (m >= mrows) break;
       float v = acc[m] + b;
       if (p.epi == EPI_GELU) v = gelu_erf(v);
       else if (p.epi == EPI_MISH) v = mishf(v);
-      else if (p.epi == EPI_ADDROW_MISH) v = mishf(v + p.rowvec.at(m)[n]);
-      p.C[(long long)m * p.ldc + n] = v;
+      else if (p.epi == EPI_ADDROW_MISH) v = mishf(v + p.rowvec.at(row0 + m)[n]);
+      p.C[(long long)(row0 + m) * p.ldc + n] = v;
     }
   }
 }
@@ -220,18 +222,16 @@ inline int init_skinny_gemm() {
   return 0;
 }
 
-// true if the skinny kernel can (and should) take this GEMM
+// true if the skinny kernel supports this GEMM (the CALL SITE decides whether to use it -- never the row count M,
+// so that a batch row gets bit-identical results however the batch is sharded)
 inline bool skinny_ok(const GemmParams& p) {
-  return p.M <= 64 && p.taps <= 1 && p.K % 4 == 0 && (size_t)p.M * p.K * 4 <= 200 * 1024 &&
+  return p.taps <= 1 && p.K % 4 == 0 && (size_t)16 * p.K * 4 <= 200 * 1024 &&
          (p.epi == EPI_BIAS || p.epi == EPI_GELU || p.epi == EPI_MISH || p.epi == EPI_ADDROW_MISH);
 }
 
 inline int launch_skinny_gemm(const GemmParams& p, cudaStream_t st) {
-  const size_t sm = (size_t)p.M * p.K * 4;
-  const int grid = ceil_div(p.N, 8);
-  if (p.M <= 16) skinny_gemm_kernel<16><<<grid, 256, sm, st>>>(p);
-  else if (p.M <= 32) skinny_gemm_kernel<32><<<grid, 256, sm, st>>>(p);
-  else skinny_gemm_kernel<64><<<grid, 256, sm, st>>>(p);
+  dim3 grid(ceil_div(p.N, 8), ceil_div(p.M, 16));
+  skinny_gemm_kernel<16><<<grid, 256, (size_t)16 * p.K * 4, st>>>(p);   // row blocks of 16: same per-row arithmetic for any M
   A2P_CUDA(cudaGetLastError());
   return 0;
 }
