@@ -10,6 +10,20 @@ from .denoiser import CFGDenoiser, Denoiser
 from .sampler import Sampler, create_gaussian_diffusion
 
 
+def default_split_terms(args) -> int:
+    """Arithmetic arm of the CUDA path.  `args.split_terms` (or A2P_SPLIT_TERMS) wins; otherwise the fastest arm that
+    meets rtol 1e-3 / atol 1e-4 against the reference on that model: two bf16 planes (16 mantissa bits, 3 tensor-core
+    products per MAC, fused row-chain kernels) for pose, three planes (6 products, ~fp32) for face, whose O(10) outputs
+    leave no margin at two planes (tests/test_gpu_tc_arm.py).  0 selects the exact-fp32 FFMA arm."""
+    import os
+    v = getattr(args, "split_terms", None)
+    if v is None and os.environ.get("A2P_SPLIT_TERMS"):
+        v = int(os.environ["A2P_SPLIT_TERMS"])
+    if v is None:
+        v = 2 if args.data_format == "pose" else 3
+    return int(v)
+
+
 def get_model_args(args, split_type: str) -> dict:
     """utils/model_util.py:49-76."""
     if args.data_format == "face":
@@ -25,7 +39,7 @@ def get_model_args(args, split_type: str) -> dict:
         "num_heads": args.heads, "dropout": 0.1, "cond_feature_dim": 512 * 2, "activation": F.gelu,
         "use_rotary": not args.not_rotary, "cond_mode": "uncond" if args.unconstrained else "audio",
         "split_type": split_type, "num_audio_layers": args.num_audio_layers, "device": args.device,
-        "split_terms": getattr(args, "split_terms", 0),
+        "split_terms": default_split_terms(args),
     }
 
 

@@ -20,6 +20,8 @@
 #include "sgemm.cuh"
 #include "umma_gemm.cuh"
 #include "umma_attention.cuh"
+#include "umma_chain.cuh"
+#include "umma_attention2.cuh"
 #include "umma_microbench.cuh"
 #include "../../include/a2p_b200_testing.h"
 
@@ -321,6 +323,21 @@ const float* find(const std::map<std::string, std::pair<const float*, int64_t>>&
   return it->second.first;
 }
 
+// A2P_NO_CHAIN=1 keeps the unfused GEMM / LayerNorm kernels (A/B measurements and the P = 3 / face arms use them anyway)
+// A2P_ATTN2: 0 = first-generation attention kernel, 1 = head-parallel kernel with P planes in shared memory,
+// 2 (default) = head-parallel kernel with P planes in tensor memory (umma_attention2.cuh; head dim 32, two planes)
+int attn2_variant() {
+  static int v = -1;
+  if (v < 0) v = getenv("A2P_ATTN2") ? atoi(getenv("A2P_ATTN2")) : 2;
+  return v;
+}
+
+bool chain_disabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("A2P_NO_CHAIN") ? 1 : 0;
+  return v == 1;
+}
+
 int check_cfg(const a2p_model_cfg* c) {
   if (!c) A2P_FAIL("null cfg");
   if (c->fmt != A2P_FMT_POSE && c->fmt != A2P_FMT_FACE) A2P_FAIL("cfg.fmt must be 0 (pose) or 1 (face)");
@@ -389,7 +406,9 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   // --- input projection (identical for both branches: computed once, duplicated)
   c.cat = CAT_IO_TCN;
   c.skinny = false;
-  if (cf.split_terms > 0) {
+  const bool chain_arm = cf.split_terms == 2 && D == 256 && (T % 8 == 0) && !chain_disabled();   // input projection fused below
+  if (chain_arm) {
+  } else if (cf.split_terms > 0) {
     __nv_bfloat16* xinP = reinterpret_cast<__nv_bfloat16*>(wsb + w.xinP);
     A2P_TRY(launch_split_planes(cf.split_terms, xin, C, xinP, (long long)B * T * C, (long long)B * T, C, 1.f, st));
     h->launches++;
@@ -399,7 +418,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   } else {
     A2P_TRY(gemm(c, xin, C, B * T, h->inp_w, C, h->inp_b, D, C, x, D));
   }
-  if (nb == 2) {
+  if (nb == 2 && !chain_arm) {
     A2P_CUDA(cudaMemcpyAsync(x + (size_t)B * T * D, x, sizeof(float) * (size_t)B * T * D, cudaMemcpyDeviceToDevice, st));
   }
   const float scale_log2e = (1.0f / sqrtf((float)dh)) * 1.4426950408889634f;
@@ -466,13 +485,96 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     }
     c.cat = kind == 0 ? CAT_ATT_SELF : (kind == 1 ? CAT_ATT_CROSS : CAT_ATT_CROSS2);
     c.begin();
-    int rc = launch_umma_attn(P, o, ap, st);
+    int rc = (P == 2 && dh == 32 && attn2_variant() > 0) ? launch_umma_attn2(attn2_variant(), o, ap, st) : launch_umma_attn(P, o, ap, st);
     c.end();
     c.cat = CAT_PROJ;
     h->launches++;
     return rc;
   };
-  for (int l = 0; P > 0 && l < L; ++l) {
+  // ===== fused row-chain arm (split_terms == 2, D == 256): per layer 4 chain launches + 3 attention launches =====
+  const bool chain = P == 2 && D == 256 && tc_attn && !chain_disabled();
+  if (chain) {
+    auto planes = [&](const float* key, long long row0, long long cols, const __nv_bfloat16** base, long long* pstride) -> int {
+      auto it = h->wplanes.find(key);
+      if (it == h->wplanes.end()) A2P_FAIL("chain: weight has no split planes");
+      *base = it->second + row0 * cols; *pstride = h->wnumel[key];
+      return 0;
+    };
+    // GEMM0 = A0 * W0^T (+ FiLM / residual), then LayerNorm (+RoPE), then GEMM1 (and optionally the V^T job of a self-attention)
+    struct Next { const float* lnw; const float* lnb; int rope; const float* w1; long long w1_row0; int N1; const float* b1;
+                  float oscale; int scale_ncols; int gelu; __nv_bfloat16* Cp; long long cp_ps, ldcp; int remap_rps, remap_pad;
+                  const float* w2; long long w2_row0; const float* b2; };
+    auto run_chain = [&](int cat, const char* tag, const __nv_bfloat16* A0, long long a0_rows, int K0, const float* w0, const float* b0,
+                         int film_off, const Next& nx) -> int {
+      ChainOperands o{};
+      ChainParams cp{};
+      o.A0 = A0; o.a0_rows = a0_rows; o.a0_ld = K0; o.a0_plane_stride = a0_rows * K0;
+      A2P_TRY(planes(w0, 0, K0, &o.W0, &o.w0_plane_stride));
+      A2P_TRY(planes(nx.w1, nx.w1_row0, D, &o.W1, &o.w1_plane_stride));
+      if (nx.w2) A2P_TRY(planes(nx.w2, nx.w2_row0, D, &o.W2, &o.w2_plane_stride));
+      cp.M = MT; cp.T = T; cp.K0 = K0; cp.bias0 = b0;
+      cp.film_mode = film_off >= 0 ? 1 : 0; cp.film = film; cp.film_ld = film_ld; cp.film_scale_off = film_off; cp.film_shift_off = film_off + D;
+      cp.x = x;
+      cp.ln_mode = nx.lnw ? 1 : 0; cp.ln_w = nx.lnw; cp.ln_b = nx.lnb; cp.rope = nx.rope; cp.rope_tab = h->rope_tab;
+      cp.N1 = nx.N1; cp.bias1 = nx.b1; cp.out_scale = nx.oscale; cp.scale_ncols = nx.scale_ncols; cp.gelu = nx.gelu;
+      cp.Cp = nx.Cp; cp.cp_plane_stride = nx.cp_ps; cp.ldcp = nx.ldcp; cp.remap_rps = nx.remap_rps; cp.remap_pad = nx.remap_pad;
+      cp.vjob = nx.w2 ? 1 : 0; cp.bias2 = nx.b2; cp.Vt = vtS; cp.vt_plane_stride = (long long)D * MT8; cp.ldvt = MT8;
+      c.cat = cat;
+      if (c.prof) c.tag = tag;
+      c.begin();
+      int rc = launch_umma_chain(o, cp, st);
+      c.end();
+      h->launches++;
+      return rc;
+    };
+    auto next_self = [&](int l) {   // LN1 + RoPE -> Q|K planes (Q pre-scaled), un-rotated LN1 -> V^T planes
+      const LayerW& lw = h->lw[l];
+      return Next{lw.n1w, lw.n1b, 1, lw.sa.in_w, 0, 2 * D, lw.sa.in_b, scale_log2e, D, 0, qkP, (long long)MT * 2 * D, 2 * D, 0, 0,
+                  lw.sa.in_w, 2 * D, lw.sa.in_b + 2 * D};
+    };
+    auto next_q = [&](const float* nw, const float* nb_, const AttnW& a) {   // LN + RoPE -> Q planes of a cross attention
+      return Next{nw, nb_, 1, a.in_w, 0, D, a.in_b, scale_log2e, 0, 0, qkP, (long long)MT * 2 * D, 2 * D, 0, 0, nullptr, 0, nullptr};
+    };
+    // input projection (both CFG branches see the same x_t: the planes are duplicated) -> layer 0 self-attention operands
+    __nv_bfloat16* xinP = reinterpret_cast<__nv_bfloat16*>(wsb + w.xinP);
+    c.cat = CAT_IO_TCN;
+    for (int b = 0; b < nb; ++b)
+      A2P_TRY(launch_split_planes(2, xin, C, xinP + (size_t)b * B * T * C, (long long)MT * C, (long long)B * T, C, 1.f, st));
+    h->launches += nb;
+    A2P_TRY(run_chain(CAT_IO_TCN, "chain in_proj->ln1->qkv", xinP, MT, C, h->inp_w, h->inp_b, -1, next_self(0)));
+    for (int l = 0; l < L; ++l) {
+      const LayerW& lw = h->lw[l];
+      const int fo = l * nf * 2 * D;
+      A2P_TRY(attn_tc(l, 0));
+      A2P_TRY(run_chain(CAT_PROJ, "chain sa_out->ln2->q", attP, MT, D, lw.sa.out_w, lw.sa.out_b, fo + 0 * 2 * D, next_q(lw.n2w, lw.n2b, lw.ca)));
+      A2P_TRY(attn_tc(l, 1));
+      const AttnW* last = &lw.ca;
+      int fidx = 1;
+      if (cf.fmt == A2P_FMT_POSE) {
+        A2P_TRY(run_chain(CAT_PROJ, "chain ca_out->ln2a->q", attP, MT, D, lw.ca.out_w, lw.ca.out_b, fo + 1 * 2 * D, next_q(lw.n2aw, lw.n2ab, lw.c2)));
+        A2P_TRY(attn_tc(l, 2));
+        last = &lw.c2; fidx = 2;
+      }
+      {
+        Next nx{lw.n3w, lw.n3b, 0, lw.l1w, 0, cf.FF, lw.l1b, 1.f, 0, 1, uP, (long long)MT * cf.FF, cf.FF, 0, 0, nullptr, 0, nullptr};
+        A2P_TRY(run_chain(CAT_FFN, "chain out->ln3->ffn1", attP, MT, D, last->out_w, last->out_b, fo + fidx * 2 * D, nx));
+      }
+      if (l + 1 < L) {
+        A2P_TRY(run_chain(CAT_FFN, "chain ffn2->ln1->qkv", uP, MT, cf.FF, lw.l2w, lw.l2b, fo + (nf - 1) * 2 * D, next_self(l + 1)));
+      } else if (cf.fmt == A2P_FMT_POSE) {
+        // last layer: FFN2 + FiLM + residual, then final_layer straight into the left-padded TCN input planes
+        const int Pl = T + TCN_PAD, Mp = R * Pl;
+        __nv_bfloat16* U = reinterpret_cast<__nv_bfloat16*>(wsb + w.tcnUP);
+        A2P_CUDA(cudaMemset2DAsync(U, (size_t)Pl * C * 2, 0, (size_t)TCN_PAD * C * 2, (size_t)P * R, st));
+        h->launches++;
+        Next nx{nullptr, nullptr, 0, h->fin_w, 0, C, h->fin_b, 1.f, 0, 0, U, (long long)Mp * C, C, T, TCN_PAD, nullptr, 0, nullptr};
+        A2P_TRY(run_chain(CAT_FFN, "chain ffn2->final_layer", uP, MT, cf.FF, lw.l2w, lw.l2b, fo + (nf - 1) * 2 * D, nx));
+      } else {
+        A2P_FAIL("chain arm: face models are not supported (D must be 256)");
+      }
+    }
+  }
+  for (int l = 0; P > 0 && !chain && l < L; ++l) {
     // ===== tensor-core arm: every [R*T, *] linear runs as a split-bf16 tcgen05 GEMM; LN / RoPE / softmax stay fp32 =====
     const LayerW& lw = h->lw[l];
     const int fo = l * nf * 2 * D;
@@ -649,10 +751,11 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     __nv_bfloat16* U = reinterpret_cast<__nv_bfloat16*>(wsb + w.tcnUP);
     __nv_bfloat16* V = reinterpret_cast<__nv_bfloat16*>(wsb + w.tcnVP);
     float *X = F(w.tcnA), *Y = F(w.tcnC);
-    A2P_TRY(launch_split_planes(P, x, D, hP, pstrideD, MT, D, 1.f, st));
-    A2P_CUDA(cudaMemset2DAsync(U, (size_t)Pl * C * 2, 0, (size_t)TCN_PAD * C * 2, (size_t)P * R, st));
-    h->launches += 2;
-    {
+    c.cat = CAT_IO_TCN;
+    if (!chain) {
+      A2P_TRY(launch_split_planes(P, x, D, hP, pstrideD, MT, D, 1.f, st));
+      A2P_CUDA(cudaMemset2DAsync(U, (size_t)Pl * C * 2, 0, (size_t)TCN_PAD * C * 2, (size_t)P * R, st));
+      h->launches += 2;
       TcGemmParams g{};
       g.Cp = U; g.cp_plane_stride = (long long)Mp * C; g.ldcp = C; g.remap_rps = T; g.remap_pad = TCN_PAD;
       A2P_TRY(tc_gemm(c, hP, MT, D, h->fin_w, 0, C, h->fin_b, TC_PLANES, g));
@@ -876,6 +979,8 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
     }
     A2P_TRY(init_umma_gemm());
     A2P_TRY(init_umma_attn());
+    A2P_TRY(init_umma_chain());
+    A2P_TRY(init_umma_attn2());
   }
   {
     int dev = 0;
@@ -1172,7 +1277,10 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   if (scratch_bytes < a2p_test_tc_attention_scratch_bytes(R, T, D, S, n_extra)) A2P_FAIL("test_tc_attention: scratch too small");
   if (n_extra > 8) A2P_FAIL("test_tc_attention: n_extra <= 8");
   cudaStream_t st = (cudaStream_t)stream;
+  int variant = 0;   // terms 20 / 21: second-generation kernel with P planes in shared / tensor memory (two planes)
+  if (terms >= 20) { variant = terms - 19; terms = 2; }
   A2P_TRY(init_umma_attn());
+  A2P_TRY(init_umma_attn2());
   const long long Sp = (long long)align_up((size_t)S, 8), Xp = 8;
   __nv_bfloat16* Qp = (__nv_bfloat16*)scratch;
   __nv_bfloat16* Kp = Qp + align_up((size_t)3 * R * T * D, 512);
@@ -1204,7 +1312,8 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   p.O = O; p.o_ld = D; p.Op = nullptr;
   p.skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : 0;
   p.trace = (iters < 0) ? reinterpret_cast<long long*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) : nullptr;   // iters < 0: trace mode
-  A2P_TRY(launch_umma_attn(terms, o, p, st));
+  auto launch = [&]() -> int { return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st); };
+  A2P_TRY(launch());
   if (iters < 0) {
     A2P_CUDA(cudaStreamSynchronize(st));
     A2P_CUDA(cudaMemcpy(O, p.trace, 64 * 16 * sizeof(long long), cudaMemcpyDeviceToDevice));   // trace returned in the O buffer
@@ -1213,12 +1322,64 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
-  for (int i = 0; i < iters; ++i) A2P_TRY(launch_umma_attn(terms, o, p, st));
+  for (int i = 0; i < iters; ++i) A2P_TRY(launch());
   cudaEventRecord(e1, st);
   A2P_CUDA(cudaStreamSynchronize(st));
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return 0;
+}
+
+size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T) {
+  return ((size_t)2 * align_up((size_t)M, 128) * K0 + (size_t)2 * 256 * K0 + (size_t)2 * N1 * 256 + (size_t)2 * 256 * 256) * 2 +
+         (size_t)T * 128 * 8 + 4096;
+}
+
+int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int rope, int gelu, int vjob, float out_scale,
+                   int scale_ncols, const float* A0, const float* W0, const float* bias0, const float* film, float* x,
+                   const float* ln_w, const float* ln_b, const float* rope_freqs, const float* W1, const float* bias1,
+                   const float* W2, const float* bias2, void* Cp_out, void* Vt_out, void* scratch, size_t scratch_bytes,
+                   int iters, float* ms_out, void* stream) {
+  if (scratch_bytes < a2p_test_chain_scratch_bytes(M, K0, N1, T)) A2P_FAIL("test_chain: scratch too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  A2P_TRY(init_umma_chain());
+  __nv_bfloat16* A0p = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* W0p = A0p + (size_t)2 * align_up((size_t)M, 128) * K0;
+  __nv_bfloat16* W1p = W0p + (size_t)2 * 256 * K0;
+  __nv_bfloat16* W2p = W1p + (size_t)2 * N1 * 256;
+  float2* tab = reinterpret_cast<float2*>(reinterpret_cast<char*>(W2p + (size_t)2 * 256 * 256) + 1024 -
+                                          (reinterpret_cast<uintptr_t>(W2p + (size_t)2 * 256 * 256) & 1023));
+  A2P_TRY(launch_split_planes(2, A0, K0, A0p, (long long)M * K0, M, K0, 1.f, st));
+  A2P_TRY(launch_split_planes(2, W0, K0, W0p, (long long)256 * K0, 256, K0, 1.f, st));
+  A2P_TRY(launch_split_planes(2, W1, 256, W1p, (long long)N1 * 256, N1, 256, 1.f, st));
+  if (vjob) A2P_TRY(launch_split_planes(2, W2, 256, W2p, (long long)256 * 256, 256, 256, 1.f, st));
+  rope_table_kernel<<<ceil_div(T * 128, 256), 256, 0, st>>>(rope_freqs, tab, T, 128);
+  A2P_CUDA(cudaGetLastError());
+  const long long M8 = (long long)align_up((size_t)M, 8);
+  ChainOperands o{};
+  o.A0 = A0p; o.a0_rows = M; o.a0_ld = K0; o.a0_plane_stride = (long long)M * K0;
+  o.W0 = W0p; o.w0_plane_stride = (long long)256 * K0;
+  o.W1 = W1p; o.w1_plane_stride = (long long)N1 * 256;
+  o.W2 = vjob ? W2p : nullptr; o.w2_plane_stride = (long long)256 * 256;
+  ChainParams cp{};
+  cp.M = M; cp.T = T; cp.K0 = K0; cp.bias0 = bias0; cp.film_mode = film_mode; cp.film = film; cp.film_ld = 512;
+  cp.film_scale_off = 0; cp.film_shift_off = 256; cp.x = x; cp.ln_mode = ln_mode; cp.ln_w = ln_w; cp.ln_b = ln_b;
+  cp.rope = rope; cp.rope_tab = tab; cp.N1 = N1; cp.bias1 = bias1; cp.out_scale = out_scale; cp.scale_ncols = scale_ncols;
+  cp.gelu = gelu; cp.Cp = (__nv_bfloat16*)Cp_out; cp.cp_plane_stride = (long long)M * N1; cp.ldcp = N1;
+  cp.vjob = vjob; cp.bias2 = bias2; cp.Vt = (__nv_bfloat16*)Vt_out; cp.vt_plane_stride = 256 * M8; cp.ldvt = M8;
+  A2P_TRY(launch_umma_chain(o, cp, st));
+  if (iters <= 0) { A2P_CUDA(cudaStreamSynchronize(st)); return 0; }
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, st);
+  for (int i = 0; i < iters; ++i) A2P_TRY(launch_umma_chain(o, cp, st));
+  cudaEventRecord(e1, st);
+  A2P_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  if (ms_out) *ms_out = ms / iters;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
 }

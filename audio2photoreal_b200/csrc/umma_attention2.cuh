@@ -1,0 +1,368 @@
+// K1 core, second generation (head dim 32, split-bf16 x2): softmax(Q K^T) V for one (sample-row, 64-column head
+// pair, 128-query tile) per CTA.  The two heads of the pair share the K / V^T tiles in shared memory and are
+// processed CONCURRENTLY by two softmax warpgroups (thread = query row, 64 keys per iteration), so the fixed
+// per-iteration latencies (mbarrier wake-up, tcgen05.ld, fences) are amortised over 64 scores per thread instead of
+// 32 and no cross-warpgroup merge is needed.
+//
+//   warp 0     TMA producer : Q tile once; per 64-key block the K tile [64 keys][64 cols] and the V^T tile
+//                             [64 cols][64 keys] of both planes (SWIZZLE_128B), 3-stage ring
+//   warp 1     MMA issuer   : per block and head  S = Q K^T (M128 x N64, K = 32, 3 plane products) into one of two
+//                             S/P TMEM buffers, one block AHEAD of  O_blk = P V (M128 x N32, K = 64 keys)
+//   warp 2     TMEM alloc   : 512 columns: per head 2 x 64 (S / P) + 2 x 32 (PV)
+//   warps 4-11 softmax      : warpgroup w = head w.  tcgen05.ld S -> running max / exp2 / sum -> P split into two
+//                             bf16 planes.  PT = 1: the planes are written back with tcgen05.st over the S buffer and
+//                             the PV product takes its A operand from TENSOR MEMORY (full-rate MMA, no shared-memory
+//                             store / proxy fence);  PT = 0: planes go to shared memory (UMMA K-major SWIZZLE_128B).
+//                             O accumulates in registers: O = O * alpha + PV.
+// Synchronisation is by data flow only: S(i+2) and PV(i+2) are issued after p_ready(i+1), which the softmax warps
+// signal after they have consumed S(i) / PV(i), so no "buffer free" barriers are needed for TMEM.
+// Q must be pre-scaled by log2(e)/sqrt(dh) (done by the Q-projection epilogue).  Operands/params as umma_attention.cuh.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+#include "umma_attention.cuh"
+
+namespace a2p {
+
+template <int PT>
+struct Attn2Cfg {
+  static constexpr int NST = 3;
+  static constexpr int Q_BYTES = 2 * 16384;            // [2 planes][128 rows][64 cols] bf16
+  static constexpr int KV_STAGE_BYTES = 2 * 2 * 8192;  // K planes then V^T planes, 8 KB each
+  static constexpr int P_BYTES = PT ? 0 : 2 * 2 * 16384;   // [head][plane][128 rows][64 keys] bf16
+  static constexpr int SMEM_BYTES = Q_BYTES + NST * KV_STAGE_BYTES + P_BYTES + 1024 + 512;
+  static constexpr int THREADS = 384;
+};
+
+__device__ __forceinline__ void tmem_ld32b(uint32_t taddr, float* v) { umma::tmem_ld32(taddr, v); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait2() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
+// probabilities p in [0, 2^k]: plane 0 = upper 16 bits (truncation, exact residual), plane 1 = residual rounded half-up
+// with an integer add (ALU pipe; the XU pipe is busy with MUFU.EX2).  |p - (p0 + p1)| <= 2^-17 p, unbiased.
+__device__ __forceinline__ void split_prob_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  const float ra = a - __uint_as_float(ua & 0xFFFF0000u), rb = b - __uint_as_float(ub & 0xFFFF0000u);
+  lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
+}
+
+template <int PT>
+__global__ void __launch_bounds__(384, 1)
+umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
+                  const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV0,
+                  const __grid_constant__ CUtensorMap tmV1, const __grid_constant__ CUtensorMap tmKx,
+                  const __grid_constant__ CUtensorMap tmVx, TcAttnParams p) {
+  using Cfg = Attn2Cfg<PT>;
+  constexpr int NST = Cfg::NST;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sKV = sQ + Cfg::Q_BYTES;
+  uint8_t* sP = sKV + NST * Cfg::KV_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
+  uint64_t* q_full = bars;             // [1]
+  uint64_t* kv_full = bars + 1;        // [3]
+  uint64_t* kv_empty = bars + 4;       // [3]
+  uint64_t* s_full = bars + 7;         // [head][2]
+  uint64_t* p_ready = bars + 11;       // [head][2]  128 arrivals
+  uint64_t* pv_full = bars + 15;       // [head][2]
+  uint64_t* p_free = bars + 19;        // [head]     (PT = 0: the shared-memory P buffer has been read by PV)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, g = blockIdx.y, r = blockIdx.z;
+  const int br = r >= p.rows_per_branch ? 1 : 0;
+  const int rr = r - br * p.rows_per_branch;
+  const int nb_main = ceil_div(p.n_keys, 64);
+  const int n_blocks = nb_main + (p.n_extra > 0 ? 1 : 0);
+
+  if (warp == 0 && lane == 0) {
+    umma::prefetch_tmap(&tmQ);
+    umma::prefetch_tmap(br ? &tmK1 : &tmK0);
+    umma::prefetch_tmap(br ? &tmV1 : &tmV0);
+  }
+  if (warp == 1 && lane == 0) {
+    umma::mbar_init(q_full, 1);
+    for (int i = 0; i < NST; ++i) { umma::mbar_init(&kv_full[i], 1); umma::mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 4; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&p_ready[i], 128); umma::mbar_init(&pv_full[i], 1); }
+    for (int i = 0; i < 2; ++i) umma::mbar_init(&p_free[i], 1);
+    umma::fence_barrier_init();
+  }
+  if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
+  pdl_trigger();
+  umma::fence_before();
+  __syncthreads();
+  umma::fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  // TMEM map: head w: S/P buffers at w*128 + b*64, PV buffers at 256 + w*64 + b*32
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (umma::elect_one()) {
+      umma::mbar_expect_tx(q_full, Cfg::Q_BYTES);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmQ, q_full, sQ + i * 16384, p.q_col0 + g * 64, r * p.T + q0, i);
+    }
+    __syncwarp();
+    const CUtensorMap* tK = br ? &tmK1 : &tmK0;
+    const CUtensorMap* tV = br ? &tmV1 : &tmV0;
+    const int k_row_base = (int)(rr * p.k_row_stride[br]);
+    const int v_col_base = (int)(rr * p.v_col_stride[br]);
+    int st = 0; uint32_t ph = 0;
+    for (int j = 0; j < n_blocks; ++j) {
+      umma::mbar_wait(&kv_empty[st], ph ^ 1);
+      if (umma::elect_one()) {
+        umma::mbar_expect_tx(&kv_full[st], Cfg::KV_STAGE_BYTES);
+        uint8_t* sk = sKV + st * Cfg::KV_STAGE_BYTES;
+        uint8_t* sv = sk + 2 * 8192;
+        if (j < nb_main) {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tK, &kv_full[st], sk + i * 8192, p.k_col0 + g * 64, k_row_base + j * 64, i);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tV, &kv_full[st], sv + i * 8192, v_col_base + j * 64, g * 64, i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmKx, &kv_full[st], sk + i * 8192, p.kx_col0 + g * 64, r * p.kx_row_stride, i);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmVx, &kv_full[st], sv + i * 8192, r * p.vx_col_stride, p.vx_row0 + g * 64, i);
+        }
+      }
+      __syncwarp();
+      if (++st == NST) { st = 0; ph ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);
+    constexpr uint32_t idPV = umma::idesc_bf16_f32(128, 32);
+    const uint32_t loQ = umma::desc_lo(umma::smem_u32(sQ));
+    const uint32_t loKV = umma::desc_lo(umma::smem_u32(sKV));
+    const uint32_t loP = umma::desc_lo(umma::smem_u32(sP));
+    umma::mbar_wait(q_full, 0);
+    int st = 0; uint32_t ph = 0;        // stage / phase of block i (S side)
+    int stj = 0;                        // stage of block i - 1 (PV side)
+    for (int i = 0; i <= n_blocks; ++i) {
+      if (i < n_blocks) {
+        umma::mbar_wait(&kv_full[st], ph);
+        umma::fence_after();
+        if (umma::elect_one()) {
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            const uint32_t lok = loKV + st * (Cfg::KV_STAGE_BYTES >> 4) + w * 4;   // head w: columns [32w, 32w+32) = +64 B
+            const uint32_t loq = loQ + w * 4;
+            const uint32_t d = tmem_base + w * 128 + (i & 1) * 64;
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+              for (int k = 0; k < 2; ++k)
+                umma::mma_bf16(d, umma::desc_make(loq + prod_a(pr) * (16384 >> 4) + 2 * k),
+                               umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
+            umma::mma_commit(&s_full[w * 2 + (i & 1)]);
+          }
+        }
+        __syncwarp();
+      }
+      if (i > 0) {
+        const int j = i - 1, b = j & 1;
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          umma::mbar_wait(&p_ready[w * 2 + b], (j >> 1) & 1);
+          umma::fence_after();
+          if (umma::elect_one()) {
+            const uint32_t lov = loKV + stj * (Cfg::KV_STAGE_BYTES >> 4) + 2 * (8192 >> 4) + w * (32 * 128 >> 4);   // V^T rows [32w, 32w+32)
+            const uint32_t d = tmem_base + 256 + w * 64 + b * 32;
+            const uint32_t tp = tmem_base + w * 128 + b * 64;                    // P planes: +0 (hi), +32 (lo); 8 columns per 16 keys
+            const uint32_t lop = loP + w * (2 * 16384 >> 4);
+#pragma unroll
+            for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const uint64_t bd = umma::desc_make(lov + prod_b(pr) * (8192 >> 4) + 2 * k);
+                if (PT) mma_bf16_ts(d, tp + prod_a(pr) * 32 + 8 * k, bd, idPV, (pr | k) != 0 ? 1u : 0u);
+                else umma::mma_bf16(d, umma::desc_make(lop + prod_a(pr) * (16384 >> 4) + 2 * k), bd, idPV, (pr | k) != 0 ? 1u : 0u);
+              }
+            umma::mma_commit(&pv_full[w * 2 + b]);
+            if (!PT) umma::mma_commit(&p_free[w]);
+            if (w == 1) umma::mma_commit(&kv_empty[stj]);
+          }
+          __syncwarp();
+        }
+        if (++stj == NST) stj = 0;
+      }
+      if (i < n_blocks) { if (++st == NST) { st = 0; ph ^= 1; } }
+    }
+  } else if (warp >= 4) {
+    // ================= softmax / output: warpgroup w owns head w =================
+    const int w = (warp - 4) >> 2;
+    const int wq = warp & 3;
+    const int trow = wq * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
+    const uint32_t tmS = tmem_base + lane_addr + w * 128;
+    const uint32_t tmO = tmem_base + lane_addr + 256 + w * 64;
+    const uint32_t sP_u32 = umma::smem_u32(sP) + w * (2 * 16384) + trow * 128;
+    float m = -INFINITY, l = 0.f, o[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) o[c] = 0.f;
+    float alpha_pend = 1.f;
+    auto consume_pv = [&](int j, float alpha) {
+      const int b = j & 1;
+      umma::mbar_wait(&pv_full[w * 2 + b], (j >> 1) & 1);
+      umma::fence_after();
+      float v[32];
+      umma::tmem_ld32(tmO + b * 32, v);
+      umma::tmem_ld_wait();
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[c] = o[c] * alpha + v[c];
+    };
+#pragma unroll 1
+    for (int i = 0; i < n_blocks; ++i) {
+      const int b = i & 1;
+      umma::mbar_wait(&s_full[w * 2 + b], (i >> 1) & 1);
+      umma::fence_after();
+      float s[64];
+      umma::tmem_ld32(tmS + b * 64, s);
+      umma::tmem_ld32(tmS + b * 64 + 32, s + 32);
+      umma::tmem_ld_wait();
+      const int nvalid = (i < nb_main) ? ::min(64, p.n_keys - i * 64) : p.n_extra;   // warp-uniform
+      if (nvalid < 64) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) s[c] = c < nvalid ? s[c] : -INFINITY;
+      }
+      float mx = fmax3(s[0], s[1], s[2]);
+#pragma unroll
+      for (int c = 3; c < 63; c += 2) mx = fmax3(mx, s[c], s[c + 1]);
+      mx = fmaxf(mx, s[63]);
+      const float mnew = fmaxf(m, mx);
+      const float alpha = umma::ex2_approx(m - mnew);
+      m = mnew;
+      if (!PT && i > 0) umma::mbar_wait(&p_free[w], (i - 1) & 1);   // PV(i-1) has finished reading the shared-memory planes
+      float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          const float a = umma::ex2_approx(s[hf * 32 + 2 * e] - mnew);
+          const float bb = umma::ex2_approx(s[hf * 32 + 2 * e + 1] - mnew);
+          rs0 += a; rs1 += bb;
+          split_prob_pair(a, bb, hi[e], lo[e]);
+        }
+        if (PT) {
+          tmem_st16(tmS + b * 64 + hf * 16, hi);
+          tmem_st16(tmS + b * 64 + 32 + hf * 16, lo);
+        } else {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            st_shared_v4(sP_u32 + (((hf * 4 + u) ^ (trow & 7)) << 4), hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+            st_shared_v4(sP_u32 + 16384 + (((hf * 4 + u) ^ (trow & 7)) << 4), lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+          }
+        }
+      }
+      if (PT) { tmem_st_wait2(); umma::fence_before(); }
+      else umma::fence_proxy_async();
+      umma::mbar_arrive(&p_ready[w * 2 + b]);
+      l = l * alpha + (rs0 + rs1);
+      if (i > 0) consume_pv(i - 1, alpha_pend);
+      alpha_pend = alpha;
+    }
+    consume_pv(n_blocks - 1, alpha_pend);
+    // ---- normalise, store head w of this row
+    const int row = q0 + trow;
+    if (row < p.T) {
+      const long long grow = (long long)r * p.T + row;
+      const float inv = 1.f / l;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) o[c] *= inv;
+      const int col = g * 64 + w * 32;
+      if (p.O) {
+        float* dst = p.O + grow * p.o_ld + col;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+      }
+      if (p.Op) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) {
+          uint32_t pk[2][4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t sp[2];
+            umma::split_bf16_pair<2>(o[c + 2 * e], o[c + 2 * e + 1], sp);
+            pk[0][e] = sp[0]; pk[1][e] = sp[1];
+          }
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+            *reinterpret_cast<uint4*>(p.Op + t * p.op_plane_stride + grow * p.o_ld + col + c) = make_uint4(pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    umma::fence_after();
+    umma::tmem_dealloc<512>(tmem_base);
+  }
+}
+
+template <int PT>
+int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
+  using Cfg = Attn2Cfg<PT>;
+  CUtensorMap tq, tk[2], tv[2], tkx, tvx;
+  const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  A2P_TRY(make_tmap_bf16_3d(&tq, o.Q, o.q_ld, o.q_rows, 2, o.q_ld, o.q_plane_stride, 64, 128, sw));
+  for (int b = 0; b < 2; ++b) {
+    const int s = o.K[b] ? b : 0;
+    A2P_TRY(make_tmap_bf16_3d(&tk[b], o.K[s], o.k_ld[s], o.k_rows[s], 2, o.k_ld[s], o.k_plane_stride[s], 64, 64, sw));
+    A2P_TRY(make_tmap_bf16_3d(&tv[b], o.Vt[s], o.vt_cols[s], o.vt_rows, 2, o.vt_ld[s], o.vt_plane_stride[s], 64, 64, sw));
+  }
+  if (o.Kx) {
+    A2P_TRY(make_tmap_bf16_3d(&tkx, o.Kx, o.kx_ld, o.kx_rows, 2, o.kx_ld, o.kx_plane_stride, 64, 64, sw));
+    A2P_TRY(make_tmap_bf16_3d(&tvx, o.Vx, o.vx_cols, o.vx_rows, 2, o.vx_ld, o.vx_plane_stride, 64, 64, sw));
+  } else {
+    tkx = tk[0]; tvx = tv[0];
+  }
+  dim3 grid(ceil_div(p.T, 128), p.D / 64, p.R);
+  A2P_CUDA(launch_pdl(umma_attn2_kernel<PT>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
+                      tkx, tvx, p));
+  return 0;
+}
+
+// variant: 2 = P planes in tensor memory, 1 = P planes in shared memory
+inline int launch_umma_attn2(int variant, const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
+  if (p.dh != 32) A2P_FAIL("umma_attn2: head dim must be 32");
+  return variant == 2 ? launch_umma_attn2_t<1>(o, p, st) : launch_umma_attn2_t<0>(o, p, st);
+}
+
+inline int init_umma_attn2() {
+  A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<0>::SMEM_BYTES));
+  A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<1>::SMEM_BYTES));
+  return 0;
+}
+
+}  // namespace a2p

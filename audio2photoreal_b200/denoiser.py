@@ -73,7 +73,7 @@ class Denoiser(nn.Module):
         device: str = "cuda",
         audio_model: Optional[nn.Module] = None,
         lip_model: Optional[nn.Module] = None,
-        split_terms: int = 0,
+        split_terms: Optional[int] = None,
         **kwargs,
     ) -> None:
         super().__init__()
@@ -93,7 +93,7 @@ class Denoiser(nn.Module):
         if (nfeats, latent_dim, ff_size) != (self.dims.C, self.dims.D, self.dims.FF):
             raise ValueError(f"geometry {(nfeats, latent_dim, ff_size)} is not the {self.data_format} model "
                              f"{(self.dims.C, self.dims.D, self.dims.FF)} (utils/model_util.py:49-76)")
-        self.split_terms = int(split_terms)
+        self.split_terms = int(split_terms) if split_terms is not None else (2 if self.data_format == "pose" else 3)
         if self.data_format == "pose":
             self.step = KEYFRAME_STEP
             self.use_cm = True

@@ -37,7 +37,7 @@ UNIT = "frames/s"
 WORKLOAD = dict(fmt="pose", layers=6, heads=8, T=600, S=1998, C=104, B=8, guidance=2.0, respacing="")
 
 
-SPLIT_TERMS = 3
+SPLIT_TERMS = 2
 
 
 def model_args(respacing):
@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--diffusion-steps", type=int, default=1000, help="debug only; anything but 1000 is not the benchmark")
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="debug only; per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--split-terms", type=int, default=3, help="0: exact-fp32 FFMA arm; 2|3: split-bf16 tcgen05 arm")
+    ap.add_argument("--split-terms", type=int, default=2, help="0: exact-fp32 FFMA arm; 2 (default, fused chain kernels) | 3: split-bf16 tcgen05 arms")
     a = ap.parse_args()
     global SPLIT_TERMS
     SPLIT_TERMS = a.split_terms

@@ -28,6 +28,17 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
 int a2p_test_simt_attention(int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K, const float* V,
                             const float* Kx, const float* Vx, float* O, int iters, float* ms_out, void* stream);
 
+/* the fused row-chain kernel (umma_chain.cuh; D = 256, split-bf16 x2): GEMM0 (A0[M,K0] * W0[256,K0]^T) -> FiLM/residual on
+ * x[M,256] (film[M/T][512] = scale | shift) -> LayerNorm -> optional RoPE -> GEMM1 (W1[N1,256]) -> bf16 planes Cp_out
+ * [2][M][N1]; optional V job (W2[256,256] on the un-rotated LayerNorm output) -> Vt_out [2][256][align8(M)].
+ * fp32 inputs are split by the hook.  iters <= 0: one launch (x is updated once); iters > 0: timing. */
+size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T);
+int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int rope, int gelu, int vjob, float out_scale,
+                   int scale_ncols, const float* A0, const float* W0, const float* bias0, const float* film, float* x,
+                   const float* ln_w, const float* ln_b, const float* rope_freqs, const float* W1, const float* bias1,
+                   const float* W2, const float* bias2, void* Cp_out, void* Vt_out, void* scratch, size_t scratch_bytes,
+                   int iters, float* ms_out, void* stream);
+
 /* micro-benchmark: total SM cycles for n_mma back-to-back tcgen05.mma (M=128, K=16, bf16) with the given N, A operand
  * from shared memory (0) or tensor memory (1); result written to the DEVICE pointer cycles_out_dev[0]. */
 int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_dev, void* stream);

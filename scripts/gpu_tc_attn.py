@@ -58,4 +58,15 @@ if __name__ == "__main__":
             run(terms, 16, 600, 256, 32, 20, 0)        # keyframe cross-attention
             run(terms, 4, 600, 512, 64, 1998, 2)       # face
         run(2, 16, 600, 256, 32, 1998, 2, qscale=4.0)  # peaky softmax
+    if which in ("all", "attn2"):
+        # second-generation kernel (umma_attention2.cuh): terms 20 = P planes in shared memory, 21 = in tensor memory
+        for terms in (20, 21):
+            run(terms, 1, 128, 64, 32, 64, 0, iters=1)
+            run(terms, 1, 128, 64, 32, 200, 0, iters=1)
+            run(terms, 2, 100, 256, 32, 77, 2, iters=1)
+            run(terms, 16, 600, 256, 32, 1998, 2)
+            run(terms, 16, 600, 256, 32, 600, 0)
+            run(terms, 16, 600, 256, 32, 20, 0)
+            run(terms, 16, 600, 256, 32, 1998, 2, qscale=4.0)
+        run(2, 16, 600, 256, 32, 1998, 2)
     print("DONE")

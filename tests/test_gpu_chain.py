@@ -1,0 +1,117 @@
+"""-m gpu: the fused row-chain kernel (csrc/umma_chain.cuh) against an fp64 torch restatement of the same chain
+(transformer_modules.py:190-217: out_proj + FiLM + residual -> LayerNorm -> RoPE -> in_proj; model/diffusion.py:364,397).
+Error budget: split-bf16 x2 operands keep 16 mantissa bits (2^-17 relative per operand), so every stage must agree with
+fp64 to a few 1e-5 of the output scale."""
+import ctypes as C
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    # name:        M     T    K0   N1   film ln rope gelu vjob scale_ncols
+    "sa_out_q":   (9600, 600, 256, 256, 1, 1, 1, 0, 0, 0),
+    "ffn2_qkv":   (9600, 600, 1024, 512, 1, 1, 1, 0, 1, 256),
+    "inproj_qkv": (9600, 600, 104, 512, 0, 1, 1, 0, 1, 256),
+    "out_ffn1":   (9600, 600, 256, 1024, 1, 1, 0, 1, 0, 0),
+    "ffn2_final": (9600, 600, 1024, 104, 1, 0, 0, 0, 0, 0),
+    "ragged":     (200, 40, 256, 256, 1, 1, 1, 0, 1, 0),
+}
+
+
+def _lib():
+    from audio2photoreal_b200 import _lib
+    lib = _lib.load()
+    vp, i32, sz, f32 = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+    lib.a2p_test_chain_scratch_bytes.argtypes = [i32] * 4
+    lib.a2p_test_chain_scratch_bytes.restype = sz
+    lib.a2p_test_chain.argtypes = [i32] * 9 + [f32, i32] + [vp] * 15 + [sz, i32, C.POINTER(f32), vp]
+    lib.a2p_test_chain.restype = i32
+    return _lib, lib
+
+
+def run_case(name, iters=0, seed=0):
+    """returns dict(stage -> (max abs err, max |ref|)) and the kernel time in ms (iters > 0)"""
+    M, T, K0, N1, film_mode, ln_mode, rope, gelu, vjob, scale_ncols = CASES[name]
+    L, lib = _lib()
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    dev = "cuda"
+    rn = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev) * sc).contiguous()
+    A0, W0, b0 = rn(M, K0), rn(256, K0, sc=K0 ** -0.5), rn(256, sc=0.1)
+    film = rn((M + T - 1) // T, 512, sc=0.3)
+    x0 = rn(M, 256, sc=2.0) + 0.5
+    lnw, lnb = 1.0 + rn(256, sc=0.1), rn(256, sc=0.1)
+    freqs = (10000.0 ** (-torch.arange(0, 256, 2, device=dev).float() / 256)).contiguous()
+    W1, b1 = rn(N1, 256, sc=1 / 16), rn(N1, sc=0.1)
+    W2, b2 = rn(256, 256, sc=1 / 16), rn(256, sc=0.1)
+    out_scale = 0.25504
+    M8 = (M + 7) // 8 * 8
+    Cp = torch.zeros(2, M, N1, device=dev, dtype=torch.bfloat16)
+    Vt = torch.zeros(2, 256, M8, device=dev, dtype=torch.bfloat16)
+    nb = lib.a2p_test_chain_scratch_bytes(M, K0, N1, T)
+    scratch = torch.zeros(nb, device=dev, dtype=torch.uint8)
+    x = x0.clone()
+    ms = C.c_float(0.0)
+    st = torch.cuda.current_stream().cuda_stream
+    call = lambda xx, it: L.check(lib.a2p_test_chain(
+        M, T, K0, N1, film_mode, ln_mode, rope, gelu, vjob, out_scale, scale_ncols, A0.data_ptr(), W0.data_ptr(), b0.data_ptr(),
+        film.data_ptr(), xx.data_ptr(), lnw.data_ptr(), lnb.data_ptr(), freqs.data_ptr(), W1.data_ptr(), b1.data_ptr(),
+        W2.data_ptr(), b2.data_ptr(), Cp.data_ptr(), Vt.data_ptr(), scratch.data_ptr(), nb, it, C.byref(ms), st))
+    call(x, 0)
+    torch.cuda.synchronize()
+    # ---- fp64 restatement
+    d = torch.float64
+    acc = A0.to(d) @ W0.to(d).T + b0.to(d)
+    if film_mode:
+        s_idx = torch.arange(M, device=dev) // T
+        sc, sh = film[s_idx, :256].to(d), film[s_idx, 256:].to(d)
+        xr = x0.to(d) + ((sc + 1) * acc + sh)
+    else:
+        xr = acc
+    if ln_mode:
+        mu = xr.mean(-1, keepdim=True)
+        var = ((xr - mu) ** 2).mean(-1, keepdim=True)
+        h = (xr - mu) / torch.sqrt(var + 1e-5) * lnw.to(d) + lnb.to(d)
+    else:
+        h = xr
+    hr = h
+    if rope:
+        pos = (torch.arange(M, device=dev) % T).float()
+        ang = (pos[:, None] * freqs[None, :]).to(d)          # fp32 product like the table kernel
+        cs, sn = torch.cos(ang), torch.sin(ang)
+        he, ho = h[:, 0::2], h[:, 1::2]
+        hr = torch.stack([he * cs - ho * sn, ho * cs + he * sn], -1).reshape(M, 256)
+    c1 = hr @ W1.to(d).T + b1.to(d)
+    if gelu:
+        c1 = torch.nn.functional.gelu(c1)
+    else:
+        ncol = scale_ncols if scale_ncols else N1
+        c1[:, :ncol] *= out_scale
+    res = {"x": ((x.to(d) - xr).abs().max().item(), xr.abs().max().item()),
+           "Cp": ((Cp.to(d).sum(0) - c1).abs().max().item(), c1.abs().max().item())}
+    if vjob:
+        vt = (h @ W2.to(d).T + b2.to(d)).T
+        res["Vt"] = ((Vt.to(d).sum(0)[:, :M] - vt).abs().max().item(), vt.abs().max().item())
+    t = None
+    if iters > 0:
+        call(x0.clone(), iters)
+        t = ms.value
+    return res, t
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_chain_vs_fp64(name):
+    res, _ = run_case(name)
+    for stage, (err, scale) in res.items():
+        tol = (2e-5 if stage == "x" else 4e-5) * max(1.0, scale)
+        assert err <= tol, f"{name}/{stage}: max|d|={err:.3e} (|ref|max={scale:.3f}, tol {tol:.1e})"
+
+
+if __name__ == "__main__":
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    for name in (sys.argv[1:] or list(CASES)):
+        res, t = run_case(name, iters=20)
+        print(name, {k: f"{e:.2e}/{s:.2f}" for k, (e, s) in res.items()}, f"{1e3 * t:.1f} us" if t else "", flush=True)
