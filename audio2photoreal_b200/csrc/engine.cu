@@ -159,6 +159,7 @@ struct WsLayout {
   size_t hP, hrP, attP, uP, xinP;   // split-bf16 activation planes (tensor-core arm)
   size_t tcnUP, tcnVP;              // TCN activation planes in the left-padded layout
   size_t qkP, vtS, kttP, vttT;      // tensor-core attention operands: Q|K planes, self V^T planes, time-token K / V^T planes
+  size_t ropeX;                     // chain arm: RoPE table extended to T + 128 rows (one TMA box per 128-row tile)
 };
 WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
   WsLayout w{};
@@ -185,6 +186,7 @@ WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
     w.uP = take(P * R * T * c.FF / 2 + 64); w.xinP = take(P * R * T * (D > c.C ? D : c.C) / 2 + 64);
     w.qkP = take(P * R * T * 2 * D / 2 + 64); w.vtS = take(P * D * align_up(R * T, 8) / 2 + 64);
     w.kttP = take(P * (2 * R + 64) * c.L * D / 2 + 64); w.vttT = take(P * c.L * D * (8 * R) / 2 + 64);
+    w.ropeX = take((size_t)(T + 128) * D);
     if (c.fmt == A2P_FMT_POSE) {
       const size_t cm = c.C > 256 ? c.C : 256;
       w.tcnUP = take(P * R * (T + TCN_PAD) * cm / 2 + 64); w.tcnVP = take(P * R * (T + TCN_PAD) * cm / 2 + 64);
@@ -406,7 +408,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   // --- input projection (identical for both branches: computed once, duplicated)
   c.cat = CAT_IO_TCN;
   c.skinny = false;
-  const bool chain_arm = cf.split_terms == 2 && D == 256 && (T % 8 == 0) && !chain_disabled();   // input projection fused below
+  const bool chain_arm = cf.split_terms == 2 && D == 256 && (T % 8 == 0) && T >= 128 && !chain_disabled();   // input projection fused below
   if (chain_arm) {
   } else if (cf.split_terms > 0) {
     __nv_bfloat16* xinP = reinterpret_cast<__nv_bfloat16*>(wsb + w.xinP);
@@ -492,8 +494,11 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     return rc;
   };
   // ===== fused row-chain arm (split_terms == 2, D == 256): per layer 4 chain launches + 3 attention launches =====
-  const bool chain = P == 2 && D == 256 && tc_attn && !chain_disabled();
+  const bool chain = P == 2 && D == 256 && tc_attn && T >= 128 && !chain_disabled();
   if (chain) {
+    float* ropeX = F(w.ropeX);
+    rope_ext_kernel<<<ceil_div((T + 128) * (D / 2), 256), 256, 0, st>>>(h->rope_tab, reinterpret_cast<float2*>(ropeX), T, D / 2);
+    h->launches++;
     auto planes = [&](const float* key, long long row0, long long cols, const __nv_bfloat16** base, long long* pstride) -> int {
       auto it = h->wplanes.find(key);
       if (it == h->wplanes.end()) A2P_FAIL("chain: weight has no split planes");
@@ -514,8 +519,8 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       if (nx.w2) A2P_TRY(planes(nx.w2, nx.w2_row0, D, &o.W2, &o.w2_plane_stride));
       cp.M = MT; cp.T = T; cp.K0 = K0; cp.bias0 = b0;
       cp.film_mode = film_off >= 0 ? 1 : 0; cp.film = film; cp.film_ld = film_ld; cp.film_scale_off = film_off; cp.film_shift_off = film_off + D;
-      cp.x = x;
-      cp.ln_mode = nx.lnw ? 1 : 0; cp.ln_w = nx.lnw; cp.ln_b = nx.lnb; cp.rope = nx.rope; cp.rope_tab = h->rope_tab;
+      o.x = x; o.rope_ext = ropeX; o.rope_ext_rows = T + 128;
+      cp.ln_mode = nx.lnw ? 1 : 0; cp.ln_w = nx.lnw; cp.ln_b = nx.lnb; cp.rope = nx.rope;
       cp.N1 = nx.N1; cp.bias1 = nx.b1; cp.out_scale = nx.oscale; cp.scale_ncols = nx.scale_ncols; cp.gelu = nx.gelu;
       cp.Cp = nx.Cp; cp.cp_plane_stride = nx.cp_ps; cp.ldcp = nx.ldcp; cp.remap_rps = nx.remap_rps; cp.remap_pad = nx.remap_pad;
       cp.vjob = nx.w2 ? 1 : 0; cp.bias2 = nx.b2; cp.Vt = vtS; cp.vt_plane_stride = (long long)D * MT8; cp.ldvt = MT8;
@@ -1334,7 +1339,7 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
 
 size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T) {
   return ((size_t)2 * align_up((size_t)M, 128) * K0 + (size_t)2 * 256 * K0 + (size_t)2 * N1 * 256 + (size_t)2 * 256 * 256) * 2 +
-         (size_t)T * 128 * 8 + 4096;
+         (size_t)T * 128 * 8 + (size_t)(T + 128) * 128 * 8 + 4096 + 1024;
 }
 
 int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int rope, int gelu, int vjob, float out_scale,
@@ -1355,7 +1360,9 @@ int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int
   A2P_TRY(launch_split_planes(2, W0, K0, W0p, (long long)256 * K0, 256, K0, 1.f, st));
   A2P_TRY(launch_split_planes(2, W1, 256, W1p, (long long)N1 * 256, N1, 256, 1.f, st));
   if (vjob) A2P_TRY(launch_split_planes(2, W2, 256, W2p, (long long)256 * 256, 256, 256, 1.f, st));
+  float2* ext = tab + (size_t)T * 128;
   rope_table_kernel<<<ceil_div(T * 128, 256), 256, 0, st>>>(rope_freqs, tab, T, 128);
+  rope_ext_kernel<<<ceil_div((T + 128) * 128, 256), 256, 0, st>>>(tab, ext, T, 128);
   A2P_CUDA(cudaGetLastError());
   const long long M8 = (long long)align_up((size_t)M, 8);
   ChainOperands o{};
@@ -1363,13 +1370,27 @@ int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int
   o.W0 = W0p; o.w0_plane_stride = (long long)256 * K0;
   o.W1 = W1p; o.w1_plane_stride = (long long)N1 * 256;
   o.W2 = vjob ? W2p : nullptr; o.w2_plane_stride = (long long)256 * 256;
+  o.x = x; o.rope_ext = reinterpret_cast<const float*>(ext); o.rope_ext_rows = T + 128;
   ChainParams cp{};
   cp.M = M; cp.T = T; cp.K0 = K0; cp.bias0 = bias0; cp.film_mode = film_mode; cp.film = film; cp.film_ld = 512;
-  cp.film_scale_off = 0; cp.film_shift_off = 256; cp.x = x; cp.ln_mode = ln_mode; cp.ln_w = ln_w; cp.ln_b = ln_b;
-  cp.rope = rope; cp.rope_tab = tab; cp.N1 = N1; cp.bias1 = bias1; cp.out_scale = out_scale; cp.scale_ncols = scale_ncols;
+  cp.film_scale_off = 0; cp.film_shift_off = 256; cp.ln_mode = ln_mode; cp.ln_w = ln_w; cp.ln_b = ln_b;
+  cp.rope = rope; cp.N1 = N1; cp.bias1 = bias1; cp.out_scale = out_scale; cp.scale_ncols = scale_ncols;
   cp.gelu = gelu; cp.Cp = (__nv_bfloat16*)Cp_out; cp.cp_plane_stride = (long long)M * N1; cp.ldcp = N1;
   cp.vjob = vjob; cp.bias2 = bias2; cp.Vt = (__nv_bfloat16*)Vt_out; cp.vt_plane_stride = 256 * M8; cp.ldvt = M8;
+  if (getenv("A2P_CHAIN_TRACE")) {   // clock64 timeline of CTA 0 (diagnostics): stored behind the RoPE tables in the scratch buffer
+    cp.trace = reinterpret_cast<long long*>(ext + (size_t)(T + 128) * 128);
+    A2P_CUDA(cudaMemsetAsync(cp.trace, 0, 64 * sizeof(long long), st));
+  }
   A2P_TRY(launch_umma_chain(o, cp, st));
+  if (cp.trace) {
+    long long tr[64];
+    A2P_CUDA(cudaStreamSynchronize(st));
+    A2P_CUDA(cudaMemcpy(tr, cp.trace, sizeof(tr), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "a2p chain trace (cycles since start):");
+    for (int i = 0; i < 64; ++i) if (tr[i]) fprintf(stderr, " [%d]=%lld", i, tr[i] - tr[0]);
+    fprintf(stderr, "\n");
+    cp.trace = nullptr;
+  }
   if (iters <= 0) { A2P_CUDA(cudaStreamSynchronize(st)); return 0; }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -21,6 +21,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "umma.cuh"
 #include "umma_attention.cuh"
@@ -74,7 +76,28 @@ __device__ __forceinline__ void split_prob_pair(float a, float b, uint32_t& hi, 
   lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
 }
 
-template <int PT>
+// packed fp32 pair add (FADD2 on sm_100): (x0, x1) = (a0, a1) + (b0, b1) -- one issue slot for two elements
+__device__ __forceinline__ void fadd2(float& x0, float& x1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\t"
+      "mov.b64 ra, {%2, %3};\n\t"
+      "mov.b64 rb, {%4, %5};\n\t"
+      "add.rn.f32x2 rc, ra, rb;\n\t"
+      "mov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(x0), "=f"(x1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
+// probabilities p >= 0: plane 0 = upper 16 bits (truncation); plane 1 = the exact residual p - plane0, rounded half-up with
+// an integer add.  The residual is one packed add against the NEGATED plane-0 values (sign bit OR-ed in: p >= 0).
+__device__ __forceinline__ void split_prob_pair2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  float ra, rb;
+  fadd2(ra, rb, a, b, __uint_as_float((ua & 0xFFFF0000u) | 0x80000000u), __uint_as_float((ub & 0xFFFF0000u) | 0x80000000u));
+  lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
+}
+
+// POLY of every 4 exponentials are evaluated with the FMA-pipe polynomial (umma::ex2_poly) instead of MUFU.EX2
+template <int PT, int POLY>
 __global__ void __launch_bounds__(384, 1)
 umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                   const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV0,
@@ -241,8 +264,10 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
       for (int c = 0; c < 32; ++c) o[c] = o[c] * alpha + v[c];
     };
-#pragma unroll 1
-    for (int i = 0; i < n_blocks; ++i) {
+    // one 64-key block; MASKED blocks (a ragged tail of the main keys, the extra keys) live in a second copy of the body so
+    // that the hot loop carries no per-score select
+    auto block = [&](int i, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       const int b = i & 1;
       umma::mbar_wait(&s_full[w * 2 + b], (i >> 1) & 1);
       umma::fence_after();
@@ -250,18 +275,19 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       umma::tmem_ld32(tmS + b * 64, s);
       umma::tmem_ld32(tmS + b * 64 + 32, s + 32);
       umma::tmem_ld_wait();
-      const int nvalid = (i < nb_main) ? ::min(64, p.n_keys - i * 64) : p.n_extra;   // warp-uniform
-      if (nvalid < 64) {
+      if (MASKED) {
+        const int nvalid = (i < nb_main) ? ::min(64, p.n_keys - i * 64) : p.n_extra;   // warp-uniform
 #pragma unroll
         for (int c = 0; c < 64; ++c) s[c] = c < nvalid ? s[c] : -INFINITY;
       }
-      float mx = fmax3(s[0], s[1], s[2]);
+      float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
 #pragma unroll
-      for (int c = 3; c < 63; c += 2) mx = fmax3(mx, s[c], s[c + 1]);
-      mx = fmaxf(mx, s[63]);
+      for (int c = 6; c < 62; c += 4) { mx0 = fmax3(mx0, s[c], s[c + 1]); mx1 = fmax3(mx1, s[c + 2], s[c + 3]); }
+      const float mx = fmax3(fmaxf(mx0, mx1), s[62], s[63]);
       const float mnew = fmaxf(m, mx);
       const float alpha = umma::ex2_approx(m - mnew);
       m = mnew;
+      const float nm = -mnew;
       if (!PT && i > 0) umma::mbar_wait(&p_free[w], (i - 1) & 1);   // PV(i-1) has finished reading the shared-memory planes
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
@@ -269,10 +295,12 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) {
-          const float a = umma::ex2_approx(s[hf * 32 + 2 * e] - mnew);
-          const float bb = umma::ex2_approx(s[hf * 32 + 2 * e + 1] - mnew);
-          rs0 += a; rs1 += bb;
-          split_prob_pair(a, bb, hi[e], lo[e]);
+          float x0, x1;
+          fadd2(x0, x1, s[hf * 32 + 2 * e], s[hf * 32 + 2 * e + 1], nm, nm);
+          const float a = ((2 * e) & 3) < POLY ? umma::ex2_poly(x0) : umma::ex2_approx(x0);
+          const float bb = ((2 * e + 1) & 3) < POLY ? umma::ex2_poly(x1) : umma::ex2_approx(x1);
+          fadd2(rs0, rs1, rs0, rs1, a, bb);
+          split_prob_pair2(a, bb, hi[e], lo[e]);
         }
         if (PT) {
           tmem_st16(tmS + b * 64 + hf * 16, hi);
@@ -291,7 +319,13 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       l = l * alpha + (rs0 + rs1);
       if (i > 0) consume_pv(i - 1, alpha_pend);
       alpha_pend = alpha;
-    }
+    };
+    const int n_full = ::min(p.n_keys / 64, n_blocks);    // leading blocks whose 64 keys are all valid
+    int i = 0;
+#pragma unroll 1
+    for (; i < n_full; ++i) block(i, std::false_type{});
+#pragma unroll 1
+    for (; i < n_blocks; ++i) block(i, std::true_type{});
     consume_pv(n_blocks - 1, alpha_pend);
     // ---- normalise, store head w of this row
     const int row = q0 + trow;
@@ -330,7 +364,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
-template <int PT>
+template <int PT, int POLY>
 int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
   using Cfg = Attn2Cfg<PT>;
   CUtensorMap tq, tk[2], tv[2], tkx, tvx;
@@ -348,20 +382,28 @@ int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStre
     tkx = tk[0]; tvx = tv[0];
   }
   dim3 grid(ceil_div(p.T, 128), p.D / 64, p.R);
-  A2P_CUDA(launch_pdl(umma_attn2_kernel<PT>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
+  A2P_CUDA(launch_pdl(umma_attn2_kernel<PT, POLY>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
                       tkx, tvx, p));
   return 0;
 }
 
-// variant: 2 = P planes in tensor memory, 1 = P planes in shared memory
+// variant: 1 = P planes in shared memory; 2 = P planes in tensor memory; 3 / 4 = as 2 with 1 / 2 of every 4 exponentials
+// on the FMA pipe
 inline int launch_umma_attn2(int variant, const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
   if (p.dh != 32) A2P_FAIL("umma_attn2: head dim must be 32");
-  return variant == 2 ? launch_umma_attn2_t<1>(o, p, st) : launch_umma_attn2_t<0>(o, p, st);
+  switch (variant) {
+    case 1: return launch_umma_attn2_t<0, 0>(o, p, st);
+    case 2: return launch_umma_attn2_t<1, 0>(o, p, st);
+    case 3: return launch_umma_attn2_t<1, 1>(o, p, st);
+    case 4: return launch_umma_attn2_t<1, 2>(o, p, st);
+  }
+  A2P_FAIL("umma_attn2: unknown variant %d", variant);
 }
 
 inline int init_umma_attn2() {
-  A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<0>::SMEM_BYTES));
-  A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<1>::SMEM_BYTES));
+#define A2P_SET(PT_, PL_) A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<PT_, PL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<PT_>::SMEM_BYTES));
+  A2P_SET(0, 0) A2P_SET(1, 0) A2P_SET(1, 1) A2P_SET(1, 2)
+#undef A2P_SET
   return 0;
 }
 

@@ -2,23 +2,29 @@
 // products per MAC, fp32 accumulation in TMEM).  One CTA owns 128 consecutive rows of the residual stream and runs,
 // without leaving the SM:
 //
-//   GEMM0    acc0[128,256]  = A0[128,K0] * W0[256,K0]^T          A0 planes streamed from global by TMA
-//   E_A      x = x + (film_scale + 1) * (acc0 + b0) + film_shift (or x = acc0 + b0), written back as fp32;
-//            h = LayerNorm(x) (two-pass, fp32), optional full-width RoPE, split into bf16 planes written straight
-//            into shared memory in the UMMA K-major SWIZZLE_128B layout (the A operand of GEMM1)
-//   GEMM1    acc1[128,N1]   = h[128,256] * W1[N1,256]^T          N1 in {104, 256, 512, 1024}, 128 columns at a time
-//   E_B      bias, optional scale / exact GELU, split into planes -> global (Q|K planes, FFN hidden planes, ...)
-//   V job    acc[256,128]   = W2[256,256] * h'[128,256]^T        (h' = un-rotated LayerNorm output): V^T planes for
-//            the PV product of the attention kernel come out already transposed
+//   GEMM0    acc0[128,256]  = A0[128,K0] * W0[256,K0]^T          A0 / W0 tiles streamed from global by TMA
+//   E_A      x = x + (film_scale + 1) * (acc0 + b0) + film_shift (or x = acc0 + b0); the old x tile arrives by TMA,
+//            the new one leaves by TMA store; h = LayerNorm(x) (two-pass, fp32), optional full-width RoPE (table rows
+//            arrive by TMA), split into two bf16 planes written IN PLACE over x in tensor memory
+//   GEMM1    acc1[128,N1]   = h[128,256] * W1[N1,256]^T          A operand from TENSOR MEMORY, 128 columns at a time
+//   E_B      bias, optional scale / erf-GELU, split into planes -> global (Q|K planes, FFN hidden planes, ...)
+//   V job    V[128,256]     = h'[128,256] * W2[256,256]^T        h' = un-rotated LayerNorm output (x tile re-read by
+//            TMA); the epilogue stores V TRANSPOSED (the V^T planes of the PV product of the attention kernel)
 //
 // This replaces, per decoder layer, 4 LayerNorm(+RoPE) launches and 9 GEMM launches of the unfused arm by 4 launches
-// (transformer_modules.py:190-217: out_proj+FiLM+residual -> norm -> rotate -> in_proj of the NEXT block), keeps the
-// 128x256 activation tile on chip between the two GEMMs and reads every weight once per 128 rows.
+// (transformer_modules.py:190-217: out_proj+FiLM+residual -> norm -> rotate -> in_proj of the NEXT block).
 //
-// Roles (384 threads):  warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4-11 two epilogue
-// warpgroups (thread = TMEM lane = row).  In E_A the warpgroups split the 256 columns (row statistics are exchanged
-// through shared memory); in E_B they alternate 128-column accumulator halves, so the epilogue of half i overlaps the
-// MMAs of half i+1.  TMEM: columns [0,256) acc0 / x, [256,384) and [384,512) the two GEMM1 accumulators.
+// Everything that comes from global memory arrives through ONE ring of eleven 16 KB shared-memory slots filled by the
+// TMA warp in a fixed, data-independent order (A0 / W0 tiles, x chunks, RoPE-table chunks, W1 tiles, x chunks again,
+// W2 tiles); consumers (the MMA warp or an epilogue warpgroup) find their slot by position in that order.  No
+// epilogue instruction waits on a global load: v0 of this kernel did (x, FiLM, LayerNorm weights, RoPE table with
+// plain loads and no L1 -- the whole 227 KB is shared memory) and spent 25 of its 44 us there (profiles/r01i).
+//
+// Roles (384 threads): warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4-11 two epilogue
+// warpgroups (thread = TMEM lane = row).  E_A: the warpgroups split the 256 columns (row statistics are exchanged
+// through shared memory).  E_B: they alternate 128-column accumulator halves, so the epilogue of half i overlaps
+// the MMAs of half i+1.  TMEM: columns [0,256) acc0 -> x -> planes (chunk c of 32 columns holds plane 0 in its first
+// 16 columns, plane 1 in the last 16: 8 columns per 16-element k-step), [256,384) / [384,512) the GEMM1 accumulators.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -30,30 +36,31 @@
 namespace a2p {
 
 struct ChainParams {
-  int M, T;                  // rows (samples * T); RoPE position = row % T, FiLM sample = row / T
+  int M, T;                  // rows (samples * T); RoPE position = row % T, FiLM sample = row / T.  T >= 128.
   int K0;                    // GEMM0 reduction length (any multiple of 8; TMA zero-fills the tail of the last 64-chunk)
   const float* bias0;        // [256]
   int film_mode;             // 1: x += (scale + 1) * (acc0 + b0) + shift    0: x = acc0 + b0
   const float* film; long long film_ld; int film_scale_off, film_shift_off;
-  float* x;                  // [M][256] fp32 residual stream
   int ln_mode;               // 1: h = LayerNorm(x) * ln_w + ln_b            0: h = x
   const float* ln_w; const float* ln_b;
   int rope;                  // rotate h before GEMM1 (the V job always uses the un-rotated h)
-  const float2* rope_tab;    // [max_pos][128] (cos, sin)
-  int N1;                    // GEMM1 output columns
+  int N1;                    // GEMM1 output columns (<= 1024)
   const float* bias1; float out_scale; int scale_ncols;   // out_scale applies to columns < scale_ncols (0 = all)
   int gelu;
   __nv_bfloat16* Cp; long long cp_plane_stride, ldcp; int remap_rps, remap_pad;
   int vjob; const float* bias2; __nv_bfloat16* Vt; long long vt_plane_stride, ldvt;
+  long long* trace;          // optional [64] clock64 timeline of CTA 0 (A2P_CHAIN_TRACE=1 in the test hook)
 };
 
 constexpr int CH_THREADS = 384;
-constexpr int CH_RING = 4;
-constexpr int CH_TILE = 16384;                    // one [128 rows][64 k] bf16 tile
-constexpr int CH_A_BYTES = 8 * CH_TILE;           // [2 planes][4 k-chunks]
-constexpr int CH_STG_BYTES = 8 * 4096;            // per epilogue warp: [32][32] fp32, 16-byte units XOR-swizzled by (row & 7)
-constexpr int CH_RED_BYTES = 1024;                // [2 warpgroups][128 rows] fp32
-constexpr int CH_SMEM_BYTES = CH_A_BYTES + CH_RING * CH_TILE + CH_STG_BYTES + CH_RED_BYTES + 256 + 1024;
+constexpr int CH_NS = 11;                          // ring slots
+constexpr int CH_TILE = 16384;                     // one slot: [128 rows][128 B], SWIZZLE_128B
+constexpr int CH_STG_BYTES = 8 * 4096;             // per epilogue warp: [32][32] fp32, 16-byte units XOR-swizzled by (row & 7)
+// parameter block (floats): bias0[256] | film[2 samples][scale 256 | shift 256] | ln_w[256] | ln_b[256] | bias1[1024] | bias2[256]
+constexpr int CH_PB_BIAS0 = 0, CH_PB_FILM = 256, CH_PB_LNW = 1280, CH_PB_LNB = 1536, CH_PB_BIAS1 = 1792, CH_PB_BIAS2 = 2816;
+constexpr int CH_PB_FLOATS = 3072;
+constexpr int CH_RED_BYTES = 1024;                 // [2 warpgroups][128 rows] fp32
+constexpr int CH_SMEM_BYTES = CH_NS * CH_TILE + CH_STG_BYTES + CH_PB_FLOATS * 4 + CH_RED_BYTES + 512 + 1024;
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
   const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
@@ -67,52 +74,123 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
         "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ void st_shared_v4u(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+// D[tmem] (+)= A[tmem] * B[smem]^T  (A: lane = row, 8 columns per 16 bf16 of K)
+__device__ __forceinline__ void mma_bf16_tmem_a(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
+
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, uint32_t dst_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// exact-erf GELU (torch's default, transformer_modules.py:265) with the Abramowitz-Stegun 7.1.26 erf: max abs error
+// 4.7e-7 over [-12, 12] (torch's own fp32 GELU is 1.2e-6 from fp64), 2 MUFU + ~13 FMA-pipe ops instead of erff().
+__device__ __forceinline__ float gelu_as(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float pl = 1.061405429f;
+  pl = fmaf(pl, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  pl *= t;
+  const float e = umma::ex2_approx(-(z * z) * 1.4426950408889634f);
+  const float er = copysignf(fmaf(-pl, e, 1.0f), x);
+  const float hx = 0.5f * x;
+  return fmaf(hx, er, hx);
+}
+
+// activations: plane 0 rounded to bf16, plane 1 = exact residual truncated (|x - p0 - p1| <= 2^-17 |x|, unbiased because the
+// residual has either sign): 8 ALU/FMA-pipe ops per pair
+__device__ __forceinline__ void split_act_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
+  hi = __byte_perm(ua, ub, 0x7632);
+  const float ra = a - __uint_as_float(ua & 0xFFFF0000u), rb = b - __uint_as_float(ub & 0xFFFF0000u);
+  lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
+}
+
+#define CH_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && (cond)) p.trace[slot] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
 umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
-                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, ChainParams p) {
+                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmTab, ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;                                   // [plane][k-chunk] tiles
-  uint8_t* sRing = sA + CH_A_BYTES;
-  float* sStg = reinterpret_cast<float*>(sRing + CH_RING * CH_TILE);
-  float* sRed = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStg) + CH_STG_BYTES);
+  uint8_t* sSlots = smem;
+  float* sStg = reinterpret_cast<float*>(sSlots + CH_NS * CH_TILE);
+  float* sPB = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sStg) + CH_STG_BYTES);
+  float* sRed = sPB + CH_PB_FLOATS;
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sRed) + CH_RED_BYTES);
-  uint64_t* r_full = bars;             // [4]
-  uint64_t* r_empty = bars + 4;        // [4]
-  uint64_t* a0_full = bars + 8;        // [4]
-  uint64_t* a0_empty = bars + 12;      // [4]
-  uint64_t* acc0_full = bars + 16;
-  uint64_t* a_ready = bars + 17;       // 256 arrivals
-  uint64_t* acc1_full = bars + 18;     // [2]
-  uint64_t* acc1_empty = bars + 20;    // [2] 128 arrivals
-  uint64_t* a_reads_done = bars + 22;
-  uint64_t* a2_ready = bars + 23;      // 256 arrivals
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  uint64_t* s_full = bars;             // [11]
+  uint64_t* s_empty = bars + 11;       // [11]
+  uint64_t* acc0_full = bars + 22;
+  uint64_t* a_ready = bars + 23;       // 256 arrivals
+  uint64_t* acc1_full = bars + 24;     // [2]
+  uint64_t* acc1_empty = bars + 26;    // [2] 128 arrivals
+  uint64_t* a_reads_done = bars + 28;
+  uint64_t* a2_ready = bars + 29;      // 256 arrivals
+  uint64_t* x_stored = bars + 30;      // 2 arrivals (one per warpgroup): the x tile written by E_A is globally visible
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
   const int kc0 = ceil_div(p.K0, 64);
   const int NH1 = ceil_div(p.N1, 128);
   const int n_acc = NH1 + (p.vjob ? 2 : 0);
+  // ring positions of the slot sequence (identical arithmetic in every role)
+  const int seqEA = 6 * kc0;                      // 8 x chunks (loaded, or only reserved as store buffers if !film_mode)
+  const int seqTab = seqEA + 8;                   // 8 RoPE-table chunks (if rope)
+  const int seqG1 = seqTab + (p.rope ? 8 : 0);    // NH1 * 8 W1 tiles
+  const int seqVx = seqG1 + 8 * NH1;              // 8 x chunks again (V job)
+  const int seqV = seqVx + 8;                     // 16 W2 tiles
 
   if (warp == 0 && lane == 0) {
-    umma::prefetch_tmap(&tmA0); umma::prefetch_tmap(&tmW0); umma::prefetch_tmap(&tmW1);
+    umma::prefetch_tmap(&tmA0); umma::prefetch_tmap(&tmW0); umma::prefetch_tmap(&tmW1); umma::prefetch_tmap(&tmX);
+    if (p.rope) umma::prefetch_tmap(&tmTab);
     if (p.vjob) umma::prefetch_tmap(&tmW2);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 4; ++i) {
-      umma::mbar_init(&r_full[i], 1); umma::mbar_init(&r_empty[i], 1);
-      umma::mbar_init(&a0_full[i], 1); umma::mbar_init(&a0_empty[i], 1);
-    }
+    for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 1); }
     umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 256);
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 128); }
-    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 256);
+    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 256); umma::mbar_init(x_stored, 2);
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
@@ -121,186 +199,233 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   __syncthreads();
   umma::fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t slots_u32 = umma::smem_u32(sSlots);
   pdl_wait();
+  CH_TRACE(0, threadIdx.x == 128);
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    int rs = 0; uint32_t rph = 0;
-    auto ring_load = [&](const CUtensorMap* tm, int k0, int row0, int plane) {
-      umma::mbar_wait(&r_empty[rs], rph ^ 1);
+    // ================= TMA producer: one pass over the slot sequence =================
+    int q = 0;
+    auto acquire = [&]() -> int {       // returns the slot of sequence position q (waits until its previous user released it)
+      const int s = q % CH_NS;
+      umma::mbar_wait(&s_empty[s], ((q / CH_NS) & 1) ^ 1);
+      ++q;
+      return s;
+    };
+    auto load3 = [&](const CUtensorMap* tm, int c0, int c1, int c2) {
+      const int s = acquire();
       if (umma::elect_one()) {
-        umma::mbar_expect_tx(&r_full[rs], CH_TILE);
-        umma::tma_load_3d(tm, &r_full[rs], sRing + rs * CH_TILE, k0, row0, plane);
+        umma::mbar_expect_tx(&s_full[s], CH_TILE);
+        umma::tma_load_3d(tm, &s_full[s], sSlots + s * CH_TILE, c0, c1, c2);
       }
       __syncwarp();
-      if (++rs == CH_RING) { rs = 0; rph ^= 1; }
+    };
+    auto load2 = [&](const CUtensorMap* tm, int c0, int c1) {
+      const int s = acquire();
+      if (umma::elect_one()) {
+        umma::mbar_expect_tx(&s_full[s], CH_TILE);
+        tma_load_2d(tm, &s_full[s], slots_u32 + s * CH_TILE, c0, c1);
+      }
+      __syncwarp();
+    };
+    auto reserve = [&]() {              // hand an empty slot to its consumer (store staging buffer)
+      const int s = acquire();
+      if (umma::elect_one()) umma::mbar_arrive(&s_full[s]);
+      __syncwarp();
     };
     for (int kc = 0; kc < kc0; ++kc) {
-      const int slot = kc & 3;
-      umma::mbar_wait(&a0_empty[slot], ((kc >> 2) & 1) ^ 1);
-      if (umma::elect_one()) {
-        umma::mbar_expect_tx(&a0_full[slot], 2 * CH_TILE);
-        umma::tma_load_3d(&tmA0, &a0_full[slot], sA + slot * CH_TILE, kc * 64, m0, 0);
-        umma::tma_load_3d(&tmA0, &a0_full[slot], sA + (4 + slot) * CH_TILE, kc * 64, m0, 1);
-      }
-      __syncwarp();
+      load3(&tmA0, kc * 64, m0, 0);
+      load3(&tmA0, kc * 64, m0, 1);
       for (int pw = 0; pw < 2; ++pw)
-        for (int nh = 0; nh < 2; ++nh) ring_load(&tmW0, kc * 64, nh * 128, pw);
+        for (int nh = 0; nh < 2; ++nh) load3(&tmW0, kc * 64, nh * 128, pw);
     }
+    CH_TRACE(24, lane == 0);
+    for (int cc = 0; cc < 4; ++cc)
+      for (int w = 0; w < 2; ++w) {
+        if (p.film_mode) load2(&tmX, (w * 4 + cc) * 32, m0);
+        else reserve();
+      }
+    if (p.rope)
+      for (int cc = 0; cc < 4; ++cc)
+        for (int w = 0; w < 2; ++w) load2(&tmTab, (w * 4 + cc) * 32, m0 % p.T);
+    CH_TRACE(25, lane == 0);
     for (int h = 0; h < NH1; ++h)
       for (int kc = 0; kc < 4; ++kc)
-        for (int pw = 0; pw < 2; ++pw) ring_load(&tmW1, kc * 64, h * 128, pw);
-    if (p.vjob)
-      for (int mh = 0; mh < 2; ++mh)
+        for (int pw = 0; pw < 2; ++pw) load3(&tmW1, kc * 64, h * 128, pw);
+    CH_TRACE(26, lane == 0);
+    if (p.vjob) {
+      umma::mbar_wait(x_stored, 0);
+      for (int cc = 0; cc < 4; ++cc)
+        for (int w = 0; w < 2; ++w) load2(&tmX, (w * 4 + cc) * 32, m0);
+      for (int nh = 0; nh < 2; ++nh)
         for (int kc = 0; kc < 4; ++kc)
-          for (int pw = 0; pw < 2; ++pw) ring_load(&tmW2, kc * 64, mh * 128, pw);
+          for (int pw = 0; pw < 2; ++pw) load3(&tmW2, kc * 64, nh * 128, pw);
+    }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma::idesc_bf16_f32(128, 128);
-    constexpr uint32_t TU = CH_TILE >> 4;   // descriptor units per tile
-    const uint32_t loA = umma::desc_lo(umma::smem_u32(sA));
-    const uint32_t loR = umma::desc_lo(umma::smem_u32(sRing));
-    int rs = 0; uint32_t rph = 0;
-    // ---- GEMM0: both 128-column halves of acc0 advance together (A0 chunk loaded once)
+    constexpr uint32_t TU = CH_TILE >> 4;
+    const uint32_t lo0 = umma::desc_lo(slots_u32);
+    // ---- GEMM0 (A0 and W0 both from ring slots): both 128-column halves of acc0 advance together
+    int q = 0;
+    CH_TRACE(16, lane == 0);
     for (int kc = 0; kc < kc0; ++kc) {
-      const int slot = kc & 3;
-      umma::mbar_wait(&a0_full[slot], (kc >> 2) & 1);
+      const int sa0 = q % CH_NS, sa1 = (q + 1) % CH_NS;
+      umma::mbar_wait(&s_full[sa0], (q / CH_NS) & 1);
+      umma::mbar_wait(&s_full[sa1], ((q + 1) / CH_NS) & 1);
+      q += 2;
       for (int pw = 0; pw < 2; ++pw)
         for (int nh = 0; nh < 2; ++nh) {
-          umma::mbar_wait(&r_full[rs], rph);
+          const int s = q % CH_NS;
+          umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
+          ++q;
           umma::fence_after();
           if (umma::elect_one()) {
-            const uint32_t lob = loR + rs * TU;
+            const uint32_t lob = lo0 + s * TU;
             const uint32_t d = tmem_base + nh * 128;
             if (pw == 0) {
 #pragma unroll
-              for (int i = 0; i < 2; ++i)
+              for (int k = 0; k < 4; ++k)
+                umma::mma_bf16(d, umma::desc_make(lo0 + sa0 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma::mma_bf16(d, umma::desc_make(loA + (i * 4 + slot) * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc,
-                                 (kc | i | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k)
+                umma::mma_bf16(d, umma::desc_make(lo0 + sa1 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, 1u);
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma::mma_bf16(d, umma::desc_make(loA + slot * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, 1u);
+                umma::mma_bf16(d, umma::desc_make(lo0 + sa0 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, 1u);
             }
-            umma::mma_commit(&r_empty[rs]);
+            umma::mma_commit(&s_empty[s]);
             if (pw == 1 && nh == 1) {
-              umma::mma_commit(&a0_empty[slot]);
+              umma::mma_commit(&s_empty[sa0]);
+              umma::mma_commit(&s_empty[sa1]);
               if (kc == kc0 - 1) umma::mma_commit(acc0_full);
             }
           }
           __syncwarp();
-          if (++rs == CH_RING) { rs = 0; rph ^= 1; }
         }
     }
-    // ---- GEMM1 (A = planes written by E_A) and the V job (A = W2 tile from the ring, B = un-rotated planes)
+    // ---- GEMM1 and the V job: A = planes in tensor memory, B = weight tile from the ring
+    CH_TRACE(17, lane == 0);
     for (int h = 0; h < n_acc; ++h) {
-      const bool vj = h >= NH1;
-      if (h == 0) { umma::mbar_wait(a_ready, 0); umma::fence_after(); }
-      if (h == NH1 && vj) { umma::mbar_wait(a2_ready, 0); umma::fence_after(); }
+      if (h == 0) { umma::mbar_wait(a_ready, 0); umma::fence_after(); q = seqG1; CH_TRACE(18, lane == 0); }
+      if (h == NH1) { umma::mbar_wait(a2_ready, 0); umma::fence_after(); q = seqV; }
       const int buf = h & 1;
       if (h >= 2) { umma::mbar_wait(&acc1_empty[buf], ((h >> 1) - 1) & 1); umma::fence_after(); }
       const uint32_t d = tmem_base + 256 + buf * 128;
       for (int kc = 0; kc < 4; ++kc)
         for (int pw = 0; pw < 2; ++pw) {
-          umma::mbar_wait(&r_full[rs], rph);
+          const int s = q % CH_NS;
+          umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
+          ++q;
           umma::fence_after();
           if (umma::elect_one()) {
-            const uint32_t low = loR + rs * TU;
+            const uint32_t low = lo0 + s * TU;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
-              if (pw == 1 && i == 1) break;          // plane pairs (0,0) (1,0) | (0,1)
+              if (pw == 1 && i == 1) break;          // plane pairs (act 0, w 0) (act 1, w 0) | (act 0, w 1)
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                const uint64_t dact = umma::desc_make(loA + (i * 4 + kc) * TU + 2 * k);   // activation plane i
-                const uint64_t dw = umma::desc_make(low + 2 * k);                         // weight plane pw
-                const uint32_t accf = (kc | pw | i | k) != 0 ? 1u : 0u;
-                if (vj) umma::mma_bf16(d, dw, dact, idesc, accf);
-                else umma::mma_bf16(d, dact, dw, idesc, accf);
+                const int ks = kc * 4 + k;             // 16-element k-step: chunk ks >> 1, half ks & 1
+                mma_bf16_tmem_a(d, tmem_base + (ks >> 1) * 32 + i * 16 + (ks & 1) * 8, umma::desc_make(low + 2 * k), idesc,
+                                (kc | pw | i | k) != 0 ? 1u : 0u);
               }
             }
-            umma::mma_commit(&r_empty[rs]);
+            umma::mma_commit(&s_empty[s]);
             if (kc == 3 && pw == 1) {
               umma::mma_commit(&acc1_full[buf]);
               if (h == NH1 - 1) umma::mma_commit(a_reads_done);
             }
           }
           __syncwarp();
-          if (++rs == CH_RING) { rs = 0; rph ^= 1; }
         }
+      CH_TRACE(32 + h, lane == 0 && h < 12);
     }
   } else if (warp >= 4) {
     // ================= epilogue warpgroups =================
     const int wg = (warp - 4) >> 2;
     const int wq = warp & 3;
     const int trow = wq * 32 + lane;                       // row inside the tile == TMEM lane
+    const int et = threadIdx.x - 128;                      // 0..255
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    float* stg = sStg + (warp - 4) * 1024;                 // [32][32] fp32, unit (q) of row r stored at unit q ^ (r & 7)
-    const int rsub = lane >> 3, uq = lane & 7;             // transposed phase: lane -> (row sub-index, 16-byte unit)
-    const uint32_t sA_u32 = umma::smem_u32(sA);
+    float* stg = sStg + (warp - 4) * 1024;
+    const int rsub = lane >> 3, uq = lane & 7;
+    const uint32_t row_off = trow * 128;                   // byte offset of this thread's row inside a slot
+    const int rx = trow & 7;
+    const uint32_t pb_u32 = umma::smem_u32(sPB);
+    const int grow_own = m0 + trow;
+    const int s_first = m0 / p.T;
+    const int sl = grow_own / p.T - s_first;               // 0 or 1 (T >= 128)
+    auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory"); };
 
-    // ---------------- E_A pass 1: x = x + film(acc0 + b0); keep x in TMEM; row sums
+    // ---------------- parameter block -> shared memory (hidden behind GEMM0)
+    {
+      for (int i = et; i < 256; i += 256) {
+        sPB[CH_PB_BIAS0 + i] = p.bias0 ? __ldg(p.bias0 + i) : 0.f;
+        sPB[CH_PB_LNW + i] = p.ln_mode ? __ldg(p.ln_w + i) : 1.f;
+        sPB[CH_PB_LNB + i] = p.ln_mode ? __ldg(p.ln_b + i) : 0.f;
+        sPB[CH_PB_BIAS2 + i] = (p.vjob && p.bias2) ? __ldg(p.bias2 + i) : 0.f;
+      }
+      for (int i = et; i < 1024; i += 256) sPB[CH_PB_BIAS1 + i] = (p.bias1 && i < p.N1) ? __ldg(p.bias1 + i) : 0.f;
+      if (p.film_mode) {
+        const int n_samp = (p.M + p.T - 1) / p.T;
+        for (int i = et; i < 1024; i += 256) {
+          const int s = i >> 9, j = i & 511;                // sample-local index, [scale 256 | shift 256]
+          const int smp = ::min(s_first + s, n_samp - 1);
+          const float* fs = p.film + (long long)smp * p.film_ld;
+          sPB[CH_PB_FILM + i] = __ldg(fs + (j < 256 ? p.film_scale_off + j : p.film_shift_off + (j - 256)));
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+    CH_TRACE(1, et == 0);
+
+    // ---------------- E_A pass 1: x = x + film(acc0 + b0); x tile out by TMA store; x kept in TMEM; row sums
     umma::mbar_wait(acc0_full, 0);
     umma::fence_after();
+    CH_TRACE(2, et == 0);
     float sum = 0.f;
+    int pend_slot = -1;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
       const int c = wg * 4 + cc;
+      const int qx = seqEA + cc * 2 + wg;
+      const int sx = qx % CH_NS;
       float v[32];
       umma::tmem_ld32(tmem_base + lane_addr + c * 32, v);
+      umma::mbar_wait(&s_full[sx], (qx / CH_NS) & 1);
       umma::tmem_ld_wait();
+      const uint32_t srow = slots_u32 + sx * CH_TILE + row_off;
+      const uint32_t pbc = pb_u32 + (CH_PB_BIAS0 + c * 32) * 4;
+      const uint32_t pfs = pb_u32 + (CH_PB_FILM + sl * 512 + c * 32) * 4;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-      __syncwarp();
-      const int col = c * 32 + uq * 4;
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias0 + col));
-#pragma unroll
-      for (int grp = 0; grp < 2; ++grp) {
-        float4 av[4], xv[4], scv[4], shv[4];
-        bool ok[4];
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = (grp * 4 + it) * 4 + rsub;
-          const int grow = m0 + wq * 32 + r;
-          ok[it] = grow < p.M;
-          av[it] = *reinterpret_cast<const float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2));
-          xv[it] = scv[it] = shv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ok[it] && p.film_mode) {
-            const float* fs = p.film + (long long)(grow / p.T) * p.film_ld;
-            scv[it] = __ldg(reinterpret_cast<const float4*>(fs + p.film_scale_off + col));
-            shv[it] = __ldg(reinterpret_cast<const float4*>(fs + p.film_shift_off + col));
-            xv[it] = *reinterpret_cast<const float4*>(p.x + (long long)grow * 256 + col);
-          }
+      for (int u = 0; u < 8; ++u) {
+        const float4 bb = lds128(pbc + u * 16);
+        float4 o = make_float4(v[4 * u] + bb.x, v[4 * u + 1] + bb.y, v[4 * u + 2] + bb.z, v[4 * u + 3] + bb.w);
+        if (p.film_mode) {
+          const float4 xo = lds128(srow + ((u ^ rx) << 4));
+          const float4 sc = lds128(pfs + u * 16), sh = lds128(pfs + 1024 + u * 16);
+          o = make_float4(xo.x + ((sc.x + 1.f) * o.x + sh.x), xo.y + ((sc.y + 1.f) * o.y + sh.y),
+                          xo.z + ((sc.z + 1.f) * o.z + sh.z), xo.w + ((sc.w + 1.f) * o.w + sh.w));
         }
-#pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int r = (grp * 4 + it) * 4 + rsub;
-          const int grow = m0 + wq * 32 + r;
-          const float4 a = av[it];
-          float4 o = make_float4(a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w);
-          if (p.film_mode) {
-            const float4 sc = scv[it], sh = shv[it], x = xv[it];
-            o = make_float4(x.x + ((sc.x + 1.f) * o.x + sh.x), x.y + ((sc.y + 1.f) * o.y + sh.y),
-                            x.z + ((sc.z + 1.f) * o.z + sh.z), x.w + ((sc.w + 1.f) * o.w + sh.w));
-          }
-          if (ok[it]) *reinterpret_cast<float4*>(p.x + (long long)grow * 256 + col) = o;
-          *reinterpret_cast<float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2)) = o;
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 t = *reinterpret_cast<const float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2));
-        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        sts128(srow + ((u ^ rx) << 4), o);
+        v[4 * u] = o.x; v[4 * u + 1] = o.y; v[4 * u + 2] = o.z; v[4 * u + 3] = o.w;
       }
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum += v[j];
       tmem_st32(tmem_base + lane_addr + c * 32, v);
-      __syncwarp();
+      umma::fence_proxy_async();        // this thread's slot writes -> visible to the TMA store (async proxy)
+      wg_sync();
+      if (trow == 0) {
+        tma_store_2d(&tmX, slots_u32 + sx * CH_TILE, c * 32, m0);
+        bulk_commit();
+        if (pend_slot >= 0) { bulk_wait_read<1>(); umma::mbar_arrive(&s_empty[pend_slot]); }   // previous chunk's store has read its slot
+        pend_slot = sx;
+      }
     }
+    if (trow == 0) { bulk_wait_read<0>(); umma::mbar_arrive(&s_empty[pend_slot]); }
     tmem_st_wait();
+    CH_TRACE(3, et == 0);
     // ---------------- row statistics (two-pass LayerNorm; the two warpgroups own 128 columns each)
     float mean = 0.f, rstd = 1.f;
     if (p.ln_mode) {
@@ -321,64 +446,75 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       asm volatile("bar.sync 1, 256;" ::: "memory");
       rstd = rsqrtf((sRed[trow] + sRed[128 + trow]) / 256.f + 1e-5f);
     }
-    // ---------------- planes of (rotated) LayerNorm(x) -> shared memory in the UMMA A-operand layout
-    auto emit_planes = [&](bool rot) {
+    CH_TRACE(4, et == 0);
+    // ---------------- planes of (rotated) LayerNorm(x), written in place over x in tensor memory
+    // src_slot >= 0: x chunk comes from that ring position (V job: re-read by TMA); otherwise from tensor memory
+    auto emit_planes = [&](bool rot, int seq_x, int seq_tab) {
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
         const int c = wg * 4 + cc;
         float v[32];
-        umma::tmem_ld32(tmem_base + lane_addr + c * 32, v);
-        if (rot) {   // stage this warp's 32 table rows (16 (cos, sin) pairs = 128 B each) with coalesced loads
+        int sx = -1, st = -1;
+        if (seq_x >= 0) {
+          const int qx = seq_x + cc * 2 + wg;
+          sx = qx % CH_NS;
+          umma::mbar_wait(&s_full[sx], (qx / CH_NS) & 1);
+          const uint32_t srow = slots_u32 + sx * CH_TILE + row_off;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + rsub;
-            const int pos = (m0 + wq * 32 + r) % p.T;
-            const float4 t = __ldg(reinterpret_cast<const float4*>(p.rope_tab + (long long)pos * 128) + c * 8 + uq);
-            *reinterpret_cast<float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2)) = t;
+          for (int u = 0; u < 8; ++u) {
+            const float4 t = lds128(srow + ((u ^ rx) << 4));
+            v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
           }
-          __syncwarp();
+        } else {
+          umma::tmem_ld32(tmem_base + lane_addr + c * 32, v);
+          umma::tmem_ld_wait();
         }
-        umma::tmem_ld_wait();
         if (p.ln_mode) {
+          const uint32_t pw_ = pb_u32 + (CH_PB_LNW + c * 32) * 4, pb_ = pb_u32 + (CH_PB_LNB + c * 32) * 4;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 ww = __ldg(reinterpret_cast<const float4*>(p.ln_w + c * 32 + 4 * q));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln_b + c * 32 + 4 * q));
-            v[4 * q + 0] = (v[4 * q + 0] - mean) * rstd * ww.x + bb.x;
-            v[4 * q + 1] = (v[4 * q + 1] - mean) * rstd * ww.y + bb.y;
-            v[4 * q + 2] = (v[4 * q + 2] - mean) * rstd * ww.z + bb.z;
-            v[4 * q + 3] = (v[4 * q + 3] - mean) * rstd * ww.w + bb.w;
+          for (int u = 0; u < 8; ++u) {
+            const float4 ww = lds128(pw_ + u * 16), bb = lds128(pb_ + u * 16);
+            v[4 * u + 0] = (v[4 * u + 0] - mean) * rstd * ww.x + bb.x;
+            v[4 * u + 1] = (v[4 * u + 1] - mean) * rstd * ww.y + bb.y;
+            v[4 * u + 2] = (v[4 * u + 2] - mean) * rstd * ww.z + bb.z;
+            v[4 * u + 3] = (v[4 * u + 3] - mean) * rstd * ww.w + bb.w;
           }
         }
         if (rot) {
+          const int qt = seq_tab + cc * 2 + wg;
+          st = qt % CH_NS;
+          umma::mbar_wait(&s_full[st], (qt / CH_NS) & 1);
+          const uint32_t trw = slots_u32 + st * CH_TILE + row_off;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 cs = *reinterpret_cast<const float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2));   // (cos0, sin0, cos1, sin1)
-            const float h0 = v[4 * q], h1 = v[4 * q + 1], h2 = v[4 * q + 2], h3 = v[4 * q + 3];
-            v[4 * q + 0] = h0 * cs.x - h1 * cs.y; v[4 * q + 1] = h1 * cs.x + h0 * cs.y;
-            v[4 * q + 2] = h2 * cs.z - h3 * cs.w; v[4 * q + 3] = h3 * cs.z + h2 * cs.w;
+          for (int u = 0; u < 8; ++u) {
+            const float4 cs = lds128(trw + ((u ^ rx) << 4));   // (cos0, sin0, cos1, sin1)
+            const float h0 = v[4 * u], h1 = v[4 * u + 1], h2 = v[4 * u + 2], h3 = v[4 * u + 3];
+            v[4 * u + 0] = h0 * cs.x - h1 * cs.y; v[4 * u + 1] = h1 * cs.x + h0 * cs.y;
+            v[4 * u + 2] = h2 * cs.z - h3 * cs.w; v[4 * u + 3] = h3 * cs.z + h2 * cs.w;
           }
-          __syncwarp();   // staging tile is reused by the next chunk
         }
-        const int kc = c >> 1, ub = (c & 1) * 4;
+        uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          uint32_t pk[2][4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            uint32_t sp[2];
-            umma::split_bf16_pair<2>(v[8 * u + 2 * e], v[8 * u + 2 * e + 1], sp);
-            pk[0][e] = sp[0]; pk[1][e] = sp[1];
+        for (int e = 0; e < 16; ++e) split_act_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+        tmem_st16u(tmem_base + lane_addr + c * 32, hi);
+        tmem_st16u(tmem_base + lane_addr + c * 32 + 16, lo);
+        if (sx >= 0 || st >= 0) {       // release the slots this warpgroup has finished reading
+          wg_sync();
+          if (trow == 0) {
+            if (sx >= 0) umma::mbar_arrive(&s_empty[sx]);
+            if (st >= 0) umma::mbar_arrive(&s_empty[st]);
           }
-#pragma unroll
-          for (int t = 0; t < 2; ++t)
-            st_shared_v4u(sA_u32 + (t * 4 + kc) * CH_TILE + trow * 128 + (((ub + u) ^ (trow & 7)) << 4), pk[t][0], pk[t][1], pk[t][2], pk[t][3]);
         }
       }
-      umma::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tmem_st_wait();
+      umma::fence_before();
     };
-    emit_planes(p.rope != 0);
+    emit_planes(p.rope != 0, -1, seqTab);
     umma::mbar_arrive(a_ready);
+    CH_TRACE(5, et == 0);
+    // this warpgroup's x stores were issued several microseconds ago: confirm completion (global visibility) so that the
+    // TMA warp may re-read the tile for the V job as soon as ring slots free up
+    if (p.vjob && trow == 0) { bulk_wait_all(); umma::mbar_arrive(x_stored); }
 
     // ---------------- E_B: this warpgroup drains accumulator halves h = wg, wg + 2, ...
     bool vprep_done = false;
@@ -386,15 +522,16 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int h = wg; h < n_acc; h += 2) {
       const bool vj = h >= NH1;
       if (vj && !vprep_done) {
-        // every GEMM1 MMA has read the rotated planes: overwrite them with the un-rotated ones for the V job
-        umma::mbar_wait(a_reads_done, 0);
-        emit_planes(false);
+        umma::mbar_wait(a_reads_done, 0);    // every GEMM1 MMA has read the rotated planes
+        umma::fence_after();
+        emit_planes(false, seqVx, 0);
         umma::mbar_arrive(a2_ready);
         vprep_done = true;
       }
       const int buf = h & 1;
       umma::mbar_wait(&acc1_full[buf], (h >> 1) & 1);
       umma::fence_after();
+      CH_TRACE(6 + h, et == 0 && h < 10);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         {
@@ -407,55 +544,60 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
         __syncwarp();
-        // normal: rows = tokens, columns = output features.  V job: rows = output channels, columns = tokens.
-        const int col = (vj ? m0 : h * 128) + c * 32 + uq * 4;
-        const bool col_ok = vj ? (col < p.M) : (col < p.N1);
-        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!vj && col_ok && p.bias1) bb = __ldg(reinterpret_cast<const float4*>(p.bias1 + col));
-        const float osc = (vj || (p.scale_ncols != 0 && col >= p.scale_ncols)) ? 1.f : p.out_scale;
+        if (!vj) {
+          // rows = tokens, columns = output features: 4 rows x 128 B per warp instruction
+          const int col = h * 128 + c * 32 + uq * 4;
+          const bool col_ok = col < p.N1;
+          const float4 bb = lds128(pb_u32 + (CH_PB_BIAS1 + (col_ok ? col : 0)) * 4);
+          const float osc = (p.scale_ncols != 0 && col >= p.scale_ncols) ? 1.f : p.out_scale;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int r = it * 4 + rsub;
-          const float4 a = *reinterpret_cast<const float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2));
-          float o[4] = {a.x, a.y, a.z, a.w};
-          long long orow;
-          bool ok = col_ok;
-          if (vj) {
-            const int ch = (h - NH1) * 128 + wq * 32 + r;
-            const float b2 = p.bias2 ? __ldg(p.bias2 + ch) : 0.f;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] += b2;
-            orow = ch;
-          } else {
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + rsub;
+            const float4 a = *reinterpret_cast<const float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2));
+            float o[4] = {a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w};
             const int grow = m0 + wq * 32 + r;
-            ok = ok && grow < p.M;
-            o[0] += bb.x; o[1] += bb.y; o[2] += bb.z; o[3] += bb.w;
             if (p.gelu) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = gelu_erf(o[j]);
+              for (int j = 0; j < 4; ++j) o[j] = gelu_as(o[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 4; ++j) o[j] *= osc;
             }
-            orow = grow;
+            if (!(col_ok && grow < p.M)) continue;
+            long long orow = grow;
             if (p.remap_rps > 0) orow += (long long)(grow / p.remap_rps + 1) * p.remap_pad;
+            uint32_t h0, l0, h1, l1;
+            split_act_pair(o[0], o[1], h0, l0);
+            split_act_pair(o[2], o[3], h1, l1);
+            __nv_bfloat16* dst = p.Cp + orow * p.ldcp + col;
+            *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(dst + p.cp_plane_stride) = make_uint2(l0, l1);
           }
-          if (!ok) continue;
-          uint32_t pk[2][2];
+        } else {
+          // V job: the accumulator is V[tokens, channels]; store V^T: lane = channel, 32 consecutive tokens = 64 B per plane
+          const int ch = (h - NH1) * 128 + c * 32 + lane;
+          const float b2 = sPB[CH_PB_BIAS2 + ch];
+          float t[32];
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            uint32_t sp[2];
-            umma::split_bf16_pair<2>(o[2 * e], o[2 * e + 1], sp);
-            pk[0][e] = sp[0]; pk[1][e] = sp[1];
+          for (int r = 0; r < 32; ++r) t[r] = stg[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)] + b2;
+          const int tok0 = m0 + wq * 32;
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) split_act_pair(t[2 * e], t[2 * e + 1], hi[e], lo[e]);
+          __nv_bfloat16* dst = p.Vt + (long long)ch * p.ldvt + tok0;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (tok0 + 8 * u < p.M) {   // M % 8 == 0 (checked by the launcher)
+              *reinterpret_cast<uint4*>(dst + 8 * u) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+              *reinterpret_cast<uint4*>(dst + p.vt_plane_stride + 8 * u) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+            }
           }
-          __nv_bfloat16* dst = vj ? p.Vt + orow * p.ldvt + col : p.Cp + orow * p.ldcp + col;
-          const long long ps = vj ? p.vt_plane_stride : p.cp_plane_stride;
-#pragma unroll
-          for (int t = 0; t < 2; ++t) *reinterpret_cast<uint2*>(dst + t * ps) = make_uint2(pk[t][0], pk[t][1]);
         }
         __syncwarp();
       }
     }
+    CH_TRACE(30, et == 0);
+    if (!p.vjob && trow == 0) bulk_wait_all();   // the x stores must have completed before the CTA exits
   }
   __syncthreads();
   if (warp == 2) {
@@ -465,31 +607,62 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 }
 
 // ------------------------------------------------------------------ host side
+inline int make_tmap_f32_2d(CUtensorMap* tm, const void* base, long long cols, long long rows, long long ld, int box_cols, int box_rows) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (!fn) A2P_FAIL("cuTensorMapEncodeTiled entry point not available");
+  if ((ld * 4) % 16 || (reinterpret_cast<uintptr_t>(base) % 16)) A2P_FAIL("TMA fp32 operand not 16-byte aligned (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) A2P_FAIL("cuTensorMapEncodeTiled(fp32) failed (%d) cols=%lld rows=%lld ld=%lld", (int)r, cols, rows, ld);
+  return 0;
+}
+
 struct ChainOperands {
   const __nv_bfloat16* A0; long long a0_rows, a0_ld, a0_plane_stride;   // [2][a0_rows][a0_ld], K0 valid columns
   const __nv_bfloat16* W0; long long w0_plane_stride;                   // [2][256][K0]
   const __nv_bfloat16* W1; long long w1_plane_stride;                   // [2][N1][256]
   const __nv_bfloat16* W2; long long w2_plane_stride;                   // [2][256][256] (null without a V job)
+  float* x;                                                             // [M][256] fp32 residual stream (read if film_mode, always written)
+  const float* rope_ext; long long rope_ext_rows;                       // [T + 128][256] fp32: (cos, sin) pairs of position (row % T)
 };
 
 inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaStream_t st) {
   if (p.K0 % 8 || p.N1 % 8 || p.N1 <= 0 || p.N1 > 1024) A2P_FAIL("chain: bad K0=%d / N1=%d", p.K0, p.N1);
+  if (p.T < 128 || p.M % 8) A2P_FAIL("chain: needs T >= 128 and M %% 8 == 0 (T=%d M=%d)", p.T, p.M);
   if (p.vjob && (!o.W2 || !p.Vt)) A2P_FAIL("chain: V job needs W2 and Vt");
-  CUtensorMap tA0, tW0, tW1, tW2;
+  if (p.rope && (!o.rope_ext || o.rope_ext_rows < p.T + 128)) A2P_FAIL("chain: RoPE needs the extended table (T + 128 rows)");
+  CUtensorMap tA0, tW0, tW1, tW2, tX, tTab;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   A2P_TRY(make_tmap_bf16_3d(&tA0, o.A0, p.K0, o.a0_rows, 2, o.a0_ld, o.a0_plane_stride, 64, 128, sw));
   A2P_TRY(make_tmap_bf16_3d(&tW0, o.W0, p.K0, 256, 2, p.K0, o.w0_plane_stride, 64, 128, sw));
   A2P_TRY(make_tmap_bf16_3d(&tW1, o.W1, 256, p.N1, 2, 256, o.w1_plane_stride, 64, 128, sw));
   if (p.vjob) A2P_TRY(make_tmap_bf16_3d(&tW2, o.W2, 256, 256, 2, 256, o.w2_plane_stride, 64, 128, sw));
   else tW2 = tW1;
+  A2P_TRY(make_tmap_f32_2d(&tX, o.x, 256, p.M, 256, 32, 128));
+  if (p.rope) A2P_TRY(make_tmap_f32_2d(&tTab, o.rope_ext, 256, o.rope_ext_rows, 256, 32, 128));
+  else tTab = tX;
   const int grid = ceil_div(p.M, 128);
-  A2P_CUDA(launch_pdl(umma_chain_kernel, dim3(grid), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, st, tA0, tW0, tW1, tW2, p));
+  A2P_CUDA(launch_pdl(umma_chain_kernel, dim3(grid), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, st, tA0, tW0, tW1, tW2, tX, tTab, p));
   return 0;
 }
 
 inline int init_umma_chain() {
   A2P_CUDA(cudaFuncSetAttribute(umma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
   return 0;
+}
+
+// ext[r][2i], ext[r][2i+1] = tab[r % T][i]  (cos, sin), r < T + 128: any 128 consecutive rows of the residual stream
+// (position = row % T) map to 128 consecutive rows of the extended table, so one TMA box covers a tile
+__global__ void rope_ext_kernel(const float2* __restrict__ tab, float2* __restrict__ ext, int T, int half) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (T + 128) * half) return;
+  const int r = idx / half, i = idx - r * half;
+  ext[idx] = tab[(long long)(r % T) * half + i];
 }
 
 }  // namespace a2p

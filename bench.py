@@ -109,6 +109,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
+CPU_SAMPLE_STEPS = 10  # diffusion steps the in-line CPU arm times (about 10 s on 32 threads)
 CPU_SAMPLE_ROWS = 2   # rows of the B=8 batch the CPU arm actually evaluates (per-row cost is independent of the batch)
 
 
@@ -142,7 +143,7 @@ def run_reference_arm(a):
     if rank != 0:
         return
     threads = min(os.cpu_count() or 1, 32)   # torch CPU GEMMs of this size stop scaling (and regress) beyond ~32 threads
-    K_diff = 1
+    K_diff = 5
     vals = []
     for _ in range(max(1, a.steps)):
         v, dt = cpu_port_frames_per_s(K_diff, threads)
@@ -211,15 +212,16 @@ def main():
     def loop_resident():
         yy = dict(y_dev)
         model._cond_sig = None          # drop the conditioning cache: the one-time precompute is part of every loop
-        return sampler.ddim_sample_loop(cfg, shape, noise=noise_dev, clip_denoised=False, model_kwargs={"y": yy},
-                                        advance_rng=False)
+        res = sampler.ddim_sample_loop(cfg, shape, noise=noise_dev, clip_denoised=False, model_kwargs={"y": yy},
+                                       advance_rng=False)
+        return all_gather_rows(res, B * world)     # the one collective of the path (no-op at world size 1)
 
     def loop_e2e():
         yy = {k: v.to(dev, non_blocking=True) for k, v in y_host.items()}
         nz = noise_host.to(dev, non_blocking=True)
         model._cond_sig = None
         res = sampler.ddim_sample_loop(cfg, shape, noise=nz, clip_denoised=False, model_kwargs={"y": yy}, advance_rng=False)
-        return res.cpu()
+        return all_gather_rows(res, B * world).cpu()
 
     def barrier():
         if world > 1:
@@ -254,9 +256,7 @@ def main():
     launches = (model.launch_count() - launches0)
     loop_e2e()
     ms_e2e, out_h = timed(loop_e2e, a.steps)
-    # the one collective of the path: all-gather of the final motion codes (timed separately, once)
-    gathered = all_gather_rows(out, B * world) if world > 1 else out
-    assert gathered.shape[0] == B * world and torch.isfinite(gathered).all()
+    assert out.shape[0] == B * world and torch.isfinite(out).all()
 
     frames = world * B * T
     value = frames / (ms_step / 1e3)
@@ -287,8 +287,13 @@ def main():
         dom = int(np.argmax(acc))
         R = 2 * B
         D, L = 256, w["layers"]
+        # per-launch algorithmic FLOPs of each category (attention cores exactly; linears = category total / launches)
+        lin_proj = (6 * T * D * D + 2 * T * D * D + 4 * T * D * D + 4 * T * D * D) * R * L
+        lin_ffn = 4 * T * D * 1024 * R * L
+        if SPLIT_TERMS == 2:   # fused chain arm: PROJ = {sa_out+q, ca_out+q} per layer, FFN = {out+ffn1, ffn2+next qkv} per layer
+            lin_proj, lin_ffn = 8 * T * D * D * R * L, (2 * T * D * D + 4 * T * D * 1024 + 6 * T * D * D) * R * L
         alg = {3: 4 * T * T * D * R, 4: 4 * T * (S + 2) * D * R, 5: 4 * T * 20 * D * R,
-               2: (6 * T * D * D + 2 * T * D * D + 4 * T * D * D + 4 * T * D * D) * R / 8.0, 6: 4 * T * D * 1024 * R / 2.0}
+               2: lin_proj / max(1, n_cat[2]), 6: lin_ffn / max(1, n_cat[6])}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -308,10 +313,10 @@ def main():
                              "products per MAC for fp32-level parity" % {0: 0, 1: 1, 2: 3, 3: 6}[SPLIT_TERMS])}
         if not a.no_cpu_baseline:
             threads = min(os.cpu_count() or 1, 32)
-            v, dt = cpu_port_frames_per_s(1, threads)
+            v, dt = cpu_port_frames_per_s(CPU_SAMPLE_STEPS, threads)
             cpu_base = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"1 of 1000 diffusion steps of {CPU_SAMPLE_ROWS} of the 8 batch rows (CFG, T=600, S=1998) in {dt:.1f}s, "
-                                  f"scaled x1000 x 8/{CPU_SAMPLE_ROWS}"}
+                        "sample": f"{CPU_SAMPLE_STEPS} of 1000 diffusion steps of {CPU_SAMPLE_ROWS} of the 8 batch rows (CFG, T=600, S=1998) "
+                                  f"in {dt:.1f}s, scaled x1000/{CPU_SAMPLE_STEPS} x 8/{CPU_SAMPLE_ROWS}"}
         f_fwd = flops_per_sample_forward()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,

@@ -58,6 +58,12 @@ if __name__ == "__main__":
             run(terms, 16, 600, 256, 32, 20, 0)        # keyframe cross-attention
             run(terms, 4, 600, 512, 64, 1998, 2)       # face
         run(2, 16, 600, 256, 32, 1998, 2, qscale=4.0)  # peaky softmax
+    if which == "attn2poly":
+        for terms in (21, 22, 23):     # 22 / 23: 1 / 2 of every 4 exponentials on the FMA pipe
+            run(terms, 16, 600, 256, 32, 1998, 2)
+            run(terms, 16, 600, 256, 32, 600, 0)
+    if which == "prof":
+        run(int(sys.argv[2]), 16, 600, 256, 32, 1998, 2, iters=1)
     if which in ("all", "attn2"):
         # second-generation kernel (umma_attention2.cuh): terms 20 = P planes in shared memory, 21 = in tensor memory
         for terms in (20, 21):
