@@ -22,6 +22,7 @@
 #include "umma_attention.cuh"
 #include "umma_chain.cuh"
 #include "umma_attention2.cuh"
+#include "umma_attention3.cuh"
 #include "umma_microbench.cuh"
 #include "../../include/a2p_b200_testing.h"
 
@@ -327,7 +328,8 @@ const float* find(const std::map<std::string, std::pair<const float*, int64_t>>&
 
 // A2P_NO_CHAIN=1 keeps the unfused GEMM / LayerNorm kernels (A/B measurements and the P = 3 / face arms use them anyway)
 // A2P_ATTN2: 0 = first-generation attention kernel, 1 = head-parallel kernel with P planes in shared memory,
-// 2 (default) = head-parallel kernel with P planes in tensor memory (umma_attention2.cuh; head dim 32, two planes)
+// 2 (default) = head-parallel kernel with P planes in tensor memory (umma_attention2.cuh; head dim 32, two planes),
+// 3 / 4 = as 2 with 1 / 2 of every 4 exponentials on the FMA pipe, 5 / 6 = sixteen-softmax-warp kernel (umma_attention3.cuh)
 int attn2_variant() {
   static int v = -1;
   if (v < 0) v = getenv("A2P_ATTN2") ? atoi(getenv("A2P_ATTN2")) : 2;
@@ -487,7 +489,9 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     }
     c.cat = kind == 0 ? CAT_ATT_SELF : (kind == 1 ? CAT_ATT_CROSS : CAT_ATT_CROSS2);
     c.begin();
-    int rc = (P == 2 && dh == 32 && attn2_variant() > 0) ? launch_umma_attn2(attn2_variant(), o, ap, st) : launch_umma_attn(P, o, ap, st);
+    const int av = attn2_variant();
+    int rc = (P == 2 && dh == 32 && av > 0) ? (av >= 5 ? launch_umma_attn3(av, o, ap, st) : launch_umma_attn2(av, o, ap, st))
+                                            : launch_umma_attn(P, o, ap, st);
     c.end();
     c.cat = CAT_PROJ;
     h->launches++;
@@ -986,6 +990,7 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
     A2P_TRY(init_umma_attn());
     A2P_TRY(init_umma_chain());
     A2P_TRY(init_umma_attn2());
+    A2P_TRY(init_umma_attn3());
   }
   {
     int dev = 0;
@@ -1286,6 +1291,7 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   if (terms >= 20) { variant = terms - 19; terms = 2; }
   A2P_TRY(init_umma_attn());
   A2P_TRY(init_umma_attn2());
+  A2P_TRY(init_umma_attn3());
   const long long Sp = (long long)align_up((size_t)S, 8), Xp = 8;
   __nv_bfloat16* Qp = (__nv_bfloat16*)scratch;
   __nv_bfloat16* Kp = Qp + align_up((size_t)3 * R * T * D, 512);
@@ -1317,7 +1323,10 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   p.O = O; p.o_ld = D; p.Op = nullptr;
   p.skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : 0;
   p.trace = (iters < 0) ? reinterpret_cast<long long*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) : nullptr;   // iters < 0: trace mode
-  auto launch = [&]() -> int { return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st); };
+  auto launch = [&]() -> int {
+    if (variant >= 5) return launch_umma_attn3(variant, o, p, st);
+    return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st);
+  };
   A2P_TRY(launch());
   if (iters < 0) {
     A2P_CUDA(cudaStreamSynchronize(st));

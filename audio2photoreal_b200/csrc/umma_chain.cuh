@@ -145,6 +145,80 @@ __device__ __forceinline__ void split_act_pair(float a, float b, uint32_t& hi, u
   lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
 }
 
+// Epilogue-thread context of chain_emit_planes (kept out of line: it runs twice in kernels with a V job, and the chain
+// kernel is instruction-fetch sensitive -- every launch starts with a cold instruction cache).
+struct ChainEpiCtx {
+  uint32_t tmem_row;       // tmem_base + lane quarter
+  uint32_t slots_u32, row_off, pb_u32;
+  uint64_t* s_full; uint64_t* s_empty;
+  int wg, trow, ln_mode;
+  float mean, rstd;
+};
+
+// planes of (rotated) LayerNorm(x), written in place over x in tensor memory.  seq_x >= 0: the x chunks come from that
+// ring position (V job: tile re-read by TMA); otherwise from tensor memory.  rot: RoPE with table chunks at seq_tab.
+__device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, int seq_x, int seq_tab) {
+  const int rx = c.trow & 7;
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    const int ch = c.wg * 4 + cc;
+    float v[32];
+    int sx = -1, st = -1;
+    if (seq_x >= 0) {
+      const int qx = seq_x + cc * 2 + c.wg;
+      sx = qx % CH_NS;
+      umma::mbar_wait(&c.s_full[sx], (qx / CH_NS) & 1);
+      const uint32_t srow = c.slots_u32 + sx * CH_TILE + c.row_off;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 t = lds128(srow + ((u ^ rx) << 4));
+        v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
+      }
+    } else {
+      umma::tmem_ld32(c.tmem_row + ch * 32, v);
+      umma::tmem_ld_wait();
+    }
+    if (c.ln_mode) {
+      const uint32_t pw_ = c.pb_u32 + (CH_PB_LNW + ch * 32) * 4, pb_ = c.pb_u32 + (CH_PB_LNB + ch * 32) * 4;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 ww = lds128(pw_ + u * 16), bb = lds128(pb_ + u * 16);
+        v[4 * u + 0] = (v[4 * u + 0] - c.mean) * c.rstd * ww.x + bb.x;
+        v[4 * u + 1] = (v[4 * u + 1] - c.mean) * c.rstd * ww.y + bb.y;
+        v[4 * u + 2] = (v[4 * u + 2] - c.mean) * c.rstd * ww.z + bb.z;
+        v[4 * u + 3] = (v[4 * u + 3] - c.mean) * c.rstd * ww.w + bb.w;
+      }
+    }
+    if (rot) {
+      const int qt = seq_tab + cc * 2 + c.wg;
+      st = qt % CH_NS;
+      umma::mbar_wait(&c.s_full[st], (qt / CH_NS) & 1);
+      const uint32_t trw = c.slots_u32 + st * CH_TILE + c.row_off;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 cs = lds128(trw + ((u ^ rx) << 4));   // (cos0, sin0, cos1, sin1)
+        const float h0 = v[4 * u], h1 = v[4 * u + 1], h2 = v[4 * u + 2], h3 = v[4 * u + 3];
+        v[4 * u + 0] = h0 * cs.x - h1 * cs.y; v[4 * u + 1] = h1 * cs.x + h0 * cs.y;
+        v[4 * u + 2] = h2 * cs.z - h3 * cs.w; v[4 * u + 3] = h3 * cs.z + h2 * cs.w;
+      }
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) split_act_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+    tmem_st16u(c.tmem_row + ch * 32, hi);
+    tmem_st16u(c.tmem_row + ch * 32 + 16, lo);
+    if (sx >= 0 || st >= 0) {       // release the slots this warpgroup has finished reading
+      asm volatile("bar.sync %0, 128;" ::"r"(2 + c.wg) : "memory");
+      if (c.trow == 0) {
+        if (sx >= 0) umma::mbar_arrive(&c.s_empty[sx]);
+        if (st >= 0) umma::mbar_arrive(&c.s_empty[st]);
+      }
+    }
+  }
+  tmem_st_wait();
+  umma::fence_before();
+}
+
 #define CH_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && (cond)) p.trace[slot] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
@@ -205,61 +279,49 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   if (warp == 0) {
     // ================= TMA producer: one pass over the slot sequence =================
-    int q = 0;
-    auto acquire = [&]() -> int {       // returns the slot of sequence position q (waits until its previous user released it)
-      const int s = q % CH_NS;
-      umma::mbar_wait(&s_empty[s], ((q / CH_NS) & 1) ^ 1);
-      ++q;
-      return s;
-    };
-    auto load3 = [&](const CUtensorMap* tm, int c0, int c1, int c2) {
-      const int s = acquire();
+    // Rolled nested loops (the fully unrolled form of this role alone was 25 KB of cold code), but no per-load decode
+    // arithmetic: the load -> consume -> release -> reload round trip of a slot is the critical path of the GEMMs.
+    int sl_ = 0; uint32_t ph_ = 0;
+    auto issue = [&](const CUtensorMap* tm, int kind, int c0, int c1, int c2) {   // kind 0: 3-D bf16 tile, 1: 2-D fp32 tile, 2: reserve
+      umma::mbar_wait(&s_empty[sl_], ph_ ^ 1);
       if (umma::elect_one()) {
-        umma::mbar_expect_tx(&s_full[s], CH_TILE);
-        umma::tma_load_3d(tm, &s_full[s], sSlots + s * CH_TILE, c0, c1, c2);
+        if (kind == 2) {
+          umma::mbar_arrive(&s_full[sl_]);
+        } else {
+          umma::mbar_expect_tx(&s_full[sl_], CH_TILE);
+          if (kind == 0) umma::tma_load_3d(tm, &s_full[sl_], sSlots + sl_ * CH_TILE, c0, c1, c2);
+          else tma_load_2d(tm, &s_full[sl_], slots_u32 + sl_ * CH_TILE, c0, c1);
+        }
       }
       __syncwarp();
+      if (++sl_ == CH_NS) { sl_ = 0; ph_ ^= 1; }
     };
-    auto load2 = [&](const CUtensorMap* tm, int c0, int c1) {
-      const int s = acquire();
-      if (umma::elect_one()) {
-        umma::mbar_expect_tx(&s_full[s], CH_TILE);
-        tma_load_2d(tm, &s_full[s], slots_u32 + s * CH_TILE, c0, c1);
-      }
-      __syncwarp();
-    };
-    auto reserve = [&]() {              // hand an empty slot to its consumer (store staging buffer)
-      const int s = acquire();
-      if (umma::elect_one()) umma::mbar_arrive(&s_full[s]);
-      __syncwarp();
-    };
+#pragma unroll 1
     for (int kc = 0; kc < kc0; ++kc) {
-      load3(&tmA0, kc * 64, m0, 0);
-      load3(&tmA0, kc * 64, m0, 1);
-      for (int pw = 0; pw < 2; ++pw)
-        for (int nh = 0; nh < 2; ++nh) load3(&tmW0, kc * 64, nh * 128, pw);
+#pragma unroll 1
+      for (int j = 0; j < 6; ++j) {
+        if (j < 2) issue(&tmA0, 0, kc * 64, m0, j);
+        else issue(&tmW0, 0, kc * 64, ((j - 2) & 1) * 128, (j - 2) >> 1);
+      }
     }
     CH_TRACE(24, lane == 0);
-    for (int cc = 0; cc < 4; ++cc)
-      for (int w = 0; w < 2; ++w) {
-        if (p.film_mode) load2(&tmX, (w * 4 + cc) * 32, m0);
-        else reserve();
-      }
-    if (p.rope)
-      for (int cc = 0; cc < 4; ++cc)
-        for (int w = 0; w < 2; ++w) load2(&tmTab, (w * 4 + cc) * 32, m0 % p.T);
+#pragma unroll 1
+    for (int j = 0; j < 8; ++j) issue(&tmX, p.film_mode ? 1 : 2, ((j & 1) * 4 + (j >> 1)) * 32, m0, 0);
+    if (p.rope) {
+      const int tab_row = m0 % p.T;
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) issue(&tmTab, 1, ((j & 1) * 4 + (j >> 1)) * 32, tab_row, 0);
+    }
     CH_TRACE(25, lane == 0);
-    for (int h = 0; h < NH1; ++h)
-      for (int kc = 0; kc < 4; ++kc)
-        for (int pw = 0; pw < 2; ++pw) load3(&tmW1, kc * 64, h * 128, pw);
+#pragma unroll 1
+    for (int j = 0; j < 8 * NH1; ++j) issue(&tmW1, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
     CH_TRACE(26, lane == 0);
     if (p.vjob) {
-      umma::mbar_wait(x_stored, 0);
-      for (int cc = 0; cc < 4; ++cc)
-        for (int w = 0; w < 2; ++w) load2(&tmX, (w * 4 + cc) * 32, m0);
-      for (int nh = 0; nh < 2; ++nh)
-        for (int kc = 0; kc < 4; ++kc)
-          for (int pw = 0; pw < 2; ++pw) load3(&tmW2, kc * 64, nh * 128, pw);
+      umma::mbar_wait(x_stored, 0);   // the x tile written by E_A is globally visible
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) issue(&tmX, 1, ((j & 1) * 4 + (j >> 1)) * 32, m0, 0);
+#pragma unroll 1
+      for (int j = 0; j < 16; ++j) issue(&tmW2, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -269,13 +331,16 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ---- GEMM0 (A0 and W0 both from ring slots): both 128-column halves of acc0 advance together
     int q = 0;
     CH_TRACE(16, lane == 0);
+#pragma unroll 1
     for (int kc = 0; kc < kc0; ++kc) {
       const int sa0 = q % CH_NS, sa1 = (q + 1) % CH_NS;
       umma::mbar_wait(&s_full[sa0], (q / CH_NS) & 1);
       umma::mbar_wait(&s_full[sa1], ((q + 1) / CH_NS) & 1);
       q += 2;
-      for (int pw = 0; pw < 2; ++pw)
-        for (int nh = 0; nh < 2; ++nh) {
+#pragma unroll 1
+      for (int st4 = 0; st4 < 4; ++st4) {
+        const int pw = st4 >> 1, nh = st4 & 1;
+        {
           const int s = q % CH_NS;
           umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
           ++q;
@@ -304,17 +369,21 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           __syncwarp();
         }
+      }
     }
     // ---- GEMM1 and the V job: A = planes in tensor memory, B = weight tile from the ring
     CH_TRACE(17, lane == 0);
+#pragma unroll 1
     for (int h = 0; h < n_acc; ++h) {
       if (h == 0) { umma::mbar_wait(a_ready, 0); umma::fence_after(); q = seqG1; CH_TRACE(18, lane == 0); }
       if (h == NH1) { umma::mbar_wait(a2_ready, 0); umma::fence_after(); q = seqV; }
       const int buf = h & 1;
       if (h >= 2) { umma::mbar_wait(&acc1_empty[buf], ((h >> 1) - 1) & 1); umma::fence_after(); }
       const uint32_t d = tmem_base + 256 + buf * 128;
-      for (int kc = 0; kc < 4; ++kc)
-        for (int pw = 0; pw < 2; ++pw) {
+#pragma unroll 1
+      for (int st8 = 0; st8 < 8; ++st8) {
+        const int kc = st8 >> 1, pw = st8 & 1;
+        {
           const int s = q % CH_NS;
           umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
           ++q;
@@ -339,6 +408,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           }
           __syncwarp();
         }
+      }
       CH_TRACE(32 + h, lane == 0 && h < 12);
     }
   } else if (warp >= 4) {
@@ -385,7 +455,6 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     umma::fence_after();
     CH_TRACE(2, et == 0);
     float sum = 0.f;
-    int pend_slot = -1;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
       const int c = wg * 4 + cc;
@@ -419,11 +488,13 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (trow == 0) {
         tma_store_2d(&tmX, slots_u32 + sx * CH_TILE, c * 32, m0);
         bulk_commit();
-        if (pend_slot >= 0) { bulk_wait_read<1>(); umma::mbar_arrive(&s_empty[pend_slot]); }   // previous chunk's store has read its slot
-        pend_slot = sx;
       }
     }
-    if (trow == 0) { bulk_wait_read<0>(); umma::mbar_arrive(&s_empty[pend_slot]); }
+    if (trow == 0) {   // release the four store-staging slots once the stores have read them (never blocks the chunk loop)
+      bulk_wait_read<0>();
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) umma::mbar_arrive(&s_empty[(seqEA + cc * 2 + wg) % CH_NS]);
+    }
     tmem_st_wait();
     CH_TRACE(3, et == 0);
     // ---------------- row statistics (two-pass LayerNorm; the two warpgroups own 128 columns each)
@@ -447,69 +518,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       rstd = rsqrtf((sRed[trow] + sRed[128 + trow]) / 256.f + 1e-5f);
     }
     CH_TRACE(4, et == 0);
-    // ---------------- planes of (rotated) LayerNorm(x), written in place over x in tensor memory
-    // src_slot >= 0: x chunk comes from that ring position (V job: re-read by TMA); otherwise from tensor memory
-    auto emit_planes = [&](bool rot, int seq_x, int seq_tab) {
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        const int c = wg * 4 + cc;
-        float v[32];
-        int sx = -1, st = -1;
-        if (seq_x >= 0) {
-          const int qx = seq_x + cc * 2 + wg;
-          sx = qx % CH_NS;
-          umma::mbar_wait(&s_full[sx], (qx / CH_NS) & 1);
-          const uint32_t srow = slots_u32 + sx * CH_TILE + row_off;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 t = lds128(srow + ((u ^ rx) << 4));
-            v[4 * u] = t.x; v[4 * u + 1] = t.y; v[4 * u + 2] = t.z; v[4 * u + 3] = t.w;
-          }
-        } else {
-          umma::tmem_ld32(tmem_base + lane_addr + c * 32, v);
-          umma::tmem_ld_wait();
-        }
-        if (p.ln_mode) {
-          const uint32_t pw_ = pb_u32 + (CH_PB_LNW + c * 32) * 4, pb_ = pb_u32 + (CH_PB_LNB + c * 32) * 4;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 ww = lds128(pw_ + u * 16), bb = lds128(pb_ + u * 16);
-            v[4 * u + 0] = (v[4 * u + 0] - mean) * rstd * ww.x + bb.x;
-            v[4 * u + 1] = (v[4 * u + 1] - mean) * rstd * ww.y + bb.y;
-            v[4 * u + 2] = (v[4 * u + 2] - mean) * rstd * ww.z + bb.z;
-            v[4 * u + 3] = (v[4 * u + 3] - mean) * rstd * ww.w + bb.w;
-          }
-        }
-        if (rot) {
-          const int qt = seq_tab + cc * 2 + wg;
-          st = qt % CH_NS;
-          umma::mbar_wait(&s_full[st], (qt / CH_NS) & 1);
-          const uint32_t trw = slots_u32 + st * CH_TILE + row_off;
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4 cs = lds128(trw + ((u ^ rx) << 4));   // (cos0, sin0, cos1, sin1)
-            const float h0 = v[4 * u], h1 = v[4 * u + 1], h2 = v[4 * u + 2], h3 = v[4 * u + 3];
-            v[4 * u + 0] = h0 * cs.x - h1 * cs.y; v[4 * u + 1] = h1 * cs.x + h0 * cs.y;
-            v[4 * u + 2] = h2 * cs.z - h3 * cs.w; v[4 * u + 3] = h3 * cs.z + h2 * cs.w;
-          }
-        }
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) split_act_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-        tmem_st16u(tmem_base + lane_addr + c * 32, hi);
-        tmem_st16u(tmem_base + lane_addr + c * 32 + 16, lo);
-        if (sx >= 0 || st >= 0) {       // release the slots this warpgroup has finished reading
-          wg_sync();
-          if (trow == 0) {
-            if (sx >= 0) umma::mbar_arrive(&s_empty[sx]);
-            if (st >= 0) umma::mbar_arrive(&s_empty[st]);
-          }
-        }
-      }
-      tmem_st_wait();
-      umma::fence_before();
-    };
-    emit_planes(p.rope != 0, -1, seqTab);
+    ChainEpiCtx ectx{tmem_base + lane_addr, slots_u32, row_off, pb_u32, s_full, s_empty, wg, trow, p.ln_mode, mean, rstd};
+    chain_emit_planes(ectx, p.rope, -1, seqTab);
     umma::mbar_arrive(a_ready);
     CH_TRACE(5, et == 0);
     // this warpgroup's x stores were issued several microseconds ago: confirm completion (global visibility) so that the
@@ -524,7 +534,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (vj && !vprep_done) {
         umma::mbar_wait(a_reads_done, 0);    // every GEMM1 MMA has read the rotated planes
         umma::fence_after();
-        emit_planes(false, seqVx, 0);
+        chain_emit_planes(ectx, 0, seqVx, 0);
         umma::mbar_arrive(a2_ready);
         vprep_done = true;
       }
@@ -550,7 +560,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const bool col_ok = col < p.N1;
           const float4 bb = lds128(pb_u32 + (CH_PB_BIAS1 + (col_ok ? col : 0)) * 4);
           const float osc = (p.scale_ncols != 0 && col >= p.scale_ncols) ? 1.f : p.out_scale;
-#pragma unroll
+#pragma unroll 2
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
             const float4 a = *reinterpret_cast<const float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2));
