@@ -22,7 +22,6 @@
 #include "umma_attention.cuh"
 #include "umma_chain.cuh"
 #include "umma_attention2.cuh"
-#include "umma_attention3.cuh"
 #include "umma_microbench.cuh"
 #include "../../include/a2p_b200_testing.h"
 
@@ -84,6 +83,8 @@ struct a2p_denoiser {
   int64_t graph_nodes = 0;
   cudaGraphExec_t gexec = nullptr;
   cudaStream_t cap_stream = nullptr;  // private stream used only to CAPTURE a step (the legacy default stream cannot capture)
+  cudaStream_t cond_stream = nullptr; // side stream: the per-step conditioning chain runs beside the first chain / self-attention launches
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   GraphKey gkey{};
   bool gvalid = false;
 };
@@ -329,7 +330,7 @@ const float* find(const std::map<std::string, std::pair<const float*, int64_t>>&
 // A2P_NO_CHAIN=1 keeps the unfused GEMM / LayerNorm kernels (A/B measurements and the P = 3 / face arms use them anyway)
 // A2P_ATTN2: 0 = first-generation attention kernel, 1 = head-parallel kernel with P planes in shared memory,
 // 2 (default) = head-parallel kernel with P planes in tensor memory (umma_attention2.cuh; head dim 32, two planes),
-// 3 / 4 = as 2 with 1 / 2 of every 4 exponentials on the FMA pipe, 5 / 6 = sixteen-softmax-warp kernel (umma_attention3.cuh)
+// 3 / 4 = as 2 with 1 / 2 of every 4 exponentials on the FMA pipe
 int attn2_variant() {
   static int v = -1;
   if (v < 0) v = getenv("A2P_ATTN2") ? atoi(getenv("A2P_ATTN2")) : 2;
@@ -387,6 +388,20 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   cudaStream_t st = c.st;
 
   // --- time conditioning (model/diffusion.py:384-389, model/utils.py:67-79)
+  // It depends on the timestep only, not on x_t: on the fused arm it runs on a side stream beside the input-projection chain
+  // launch and the first self-attention (fork / join by events; inside a graph capture these become parallel branches) and
+  // is joined before the first kernel that reads the FiLM table.
+  const bool chain_arm = cf.split_terms == 2 && D == 256 && (T % 8 == 0) && T >= 128 && !chain_disabled();
+  const bool side = chain_arm && !c.prof && !getenv("A2P_NO_SIDE_STREAM");
+  cudaStream_t st_main = st;
+  if (side) {
+    if (!h->cond_stream) A2P_CUDA(cudaStreamCreateWithFlags(&h->cond_stream, cudaStreamNonBlocking));
+    if (!h->ev_fork) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    if (!h->ev_join) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+    A2P_CUDA(cudaEventRecord(h->ev_fork, st_main));
+    A2P_CUDA(cudaStreamWaitEvent(h->cond_stream, h->ev_fork, 0));
+    st = h->cond_stream; c.st = st;
+  }
   c.cat = CAT_COND;
   c.skinny = true;
   time_embed_kernel<<<ceil_div(R * D / 2, 256), 256, 0, st>>>(ts, counter, B, R, D, h->time_freqs, e);
@@ -410,8 +425,8 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   // --- input projection (identical for both branches: computed once, duplicated)
   c.cat = CAT_IO_TCN;
   c.skinny = false;
-  const bool chain_arm = cf.split_terms == 2 && D == 256 && (T % 8 == 0) && T >= 128 && !chain_disabled();   // input projection fused below
-  if (chain_arm) {
+  st = st_main; c.st = st_main;
+  if (chain_arm) {   // input projection fused into the first chain launch below
   } else if (cf.split_terms > 0) {
     __nv_bfloat16* xinP = reinterpret_cast<__nv_bfloat16*>(wsb + w.xinP);
     A2P_TRY(launch_split_planes(cf.split_terms, xin, C, xinP, (long long)B * T * C, (long long)B * T, C, 1.f, st));
@@ -443,6 +458,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   const long long MT8 = (long long)align_up((size_t)MT, 8);
   const long long XP = 8LL * R;   // time-token V^T: 8 columns per sample (TMA needs 16-byte aligned box starts), 2 used
   if (tc_attn) {
+    if (side) { st = h->cond_stream; c.st = st; }
     c.cat = CAT_COND;
     c.begin();
     A2P_TRY(launch_split_planes(P, ktt, (long long)L * D, kttP, (long long)2 * R * L * D, 2 * R, L * D, 1.f, st));
@@ -450,6 +466,10 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     A2P_TRY(launch_transpose_split(P, vtt, (long long)L * D, vttT, (long long)L * D * XP, XP, 2 * R, L * D, 2, 8, 1.f, st));
     c.end();
     h->launches += 3;
+    if (side) {
+      A2P_CUDA(cudaEventRecord(h->ev_join, h->cond_stream));
+      st = st_main; c.st = st_main;
+    }
   }
   auto attn_tc = [&](int l, int kind) -> int {   // kind 0 self, 1 audio cross (+2 time tokens), 2 keyframe cross
     TcAttnOperands o{};
@@ -490,8 +510,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     c.cat = kind == 0 ? CAT_ATT_SELF : (kind == 1 ? CAT_ATT_CROSS : CAT_ATT_CROSS2);
     c.begin();
     const int av = attn2_variant();
-    int rc = (P == 2 && dh == 32 && av > 0) ? (av >= 5 ? launch_umma_attn3(av, o, ap, st) : launch_umma_attn2(av, o, ap, st))
-                                            : launch_umma_attn(P, o, ap, st);
+    int rc = (P == 2 && dh == 32 && av > 0) ? launch_umma_attn2(av, o, ap, st) : launch_umma_attn(P, o, ap, st);
     c.end();
     c.cat = CAT_PROJ;
     h->launches++;
@@ -555,6 +574,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       const LayerW& lw = h->lw[l];
       const int fo = l * nf * 2 * D;
       A2P_TRY(attn_tc(l, 0));
+      if (l == 0 && side) A2P_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));   // FiLM table + time-token K/V rows are ready
       A2P_TRY(run_chain(CAT_PROJ, "chain sa_out->ln2->q", attP, MT, D, lw.sa.out_w, lw.sa.out_b, fo + 0 * 2 * D, next_q(lw.n2w, lw.n2b, lw.ca)));
       A2P_TRY(attn_tc(l, 1));
       const AttnW* last = &lw.ca;
@@ -877,6 +897,9 @@ void a2p_denoiser_destroy(a2p_denoiser_t* h) {
   if (!h) return;
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
+  if (h->cond_stream) cudaStreamDestroy(h->cond_stream);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   delete h;
 }
 
@@ -990,7 +1013,6 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
     A2P_TRY(init_umma_attn());
     A2P_TRY(init_umma_chain());
     A2P_TRY(init_umma_attn2());
-    A2P_TRY(init_umma_attn3());
   }
   {
     int dev = 0;
@@ -1291,7 +1313,6 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   if (terms >= 20) { variant = terms - 19; terms = 2; }
   A2P_TRY(init_umma_attn());
   A2P_TRY(init_umma_attn2());
-  A2P_TRY(init_umma_attn3());
   const long long Sp = (long long)align_up((size_t)S, 8), Xp = 8;
   __nv_bfloat16* Qp = (__nv_bfloat16*)scratch;
   __nv_bfloat16* Kp = Qp + align_up((size_t)3 * R * T * D, 512);
@@ -1323,10 +1344,7 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   p.O = O; p.o_ld = D; p.Op = nullptr;
   p.skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : 0;
   p.trace = (iters < 0) ? reinterpret_cast<long long*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) : nullptr;   // iters < 0: trace mode
-  auto launch = [&]() -> int {
-    if (variant >= 5) return launch_umma_attn3(variant, o, p, st);
-    return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st);
-  };
+  auto launch = [&]() -> int { return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st); };
   A2P_TRY(launch());
   if (iters < 0) {
     A2P_CUDA(cudaStreamSynchronize(st));

@@ -293,14 +293,28 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
         uint32_t hi[16], lo[16];
+        // software pipeline: the exponentials of pair e + DEPTH are issued before the split of pair e, so that the MUFU pipe
+        // (one warp instruction per 8 cycles) is fed every ~6 issue slots instead of in one burst of 64
+        constexpr int DEPTH = 3;
+        float pa[16], pb[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) {
+        for (int e = 0; e < DEPTH; ++e) {
           float x0, x1;
           fadd2(x0, x1, s[hf * 32 + 2 * e], s[hf * 32 + 2 * e + 1], nm, nm);
-          const float a = ((2 * e) & 3) < POLY ? umma::ex2_poly(x0) : umma::ex2_approx(x0);
-          const float bb = ((2 * e + 1) & 3) < POLY ? umma::ex2_poly(x1) : umma::ex2_approx(x1);
-          fadd2(rs0, rs1, rs0, rs1, a, bb);
-          split_prob_pair2(a, bb, hi[e], lo[e]);
+          pa[e] = ((2 * e) & 3) < POLY ? umma::ex2_poly(x0) : umma::ex2_approx(x0);
+          pb[e] = ((2 * e + 1) & 3) < POLY ? umma::ex2_poly(x1) : umma::ex2_approx(x1);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) {
+          if (e + DEPTH < 16) {
+            const int f = e + DEPTH;
+            float x0, x1;
+            fadd2(x0, x1, s[hf * 32 + 2 * f], s[hf * 32 + 2 * f + 1], nm, nm);
+            pa[f] = ((2 * f) & 3) < POLY ? umma::ex2_poly(x0) : umma::ex2_approx(x0);
+            pb[f] = ((2 * f + 1) & 3) < POLY ? umma::ex2_poly(x1) : umma::ex2_approx(x1);
+          }
+          fadd2(rs0, rs1, rs0, rs1, pa[e], pb[e]);
+          split_prob_pair2(pa[e], pb[e], hi[e], lo[e]);
         }
         if (PT) {
           tmem_st16(tmS + b * 64 + hf * 16, hi);

@@ -207,11 +207,14 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
     for (int e = 0; e < 16; ++e) split_act_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
     tmem_st16u(c.tmem_row + ch * 32, hi);
     tmem_st16u(c.tmem_row + ch * 32 + 16, lo);
-    if (sx >= 0 || st >= 0) {       // release the slots this warpgroup has finished reading
-      asm volatile("bar.sync %0, 128;" ::"r"(2 + c.wg) : "memory");
-      if (c.trow == 0) {
-        if (sx >= 0) umma::mbar_arrive(&c.s_empty[sx]);
-        if (st >= 0) umma::mbar_arrive(&c.s_empty[st]);
+  }
+  if (seq_x >= 0 || rot) {          // release the slots this warpgroup has finished reading (one barrier for all four chunks)
+    asm volatile("bar.sync %0, 128;" ::"r"(2 + c.wg) : "memory");
+    if (c.trow == 0) {
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        if (seq_x >= 0) umma::mbar_arrive(&c.s_empty[(seq_x + cc * 2 + c.wg) % CH_NS]);
+        if (rot) umma::mbar_arrive(&c.s_empty[(seq_tab + cc * 2 + c.wg) % CH_NS]);
       }
     }
   }
@@ -483,18 +486,23 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
       for (int j = 0; j < 32; ++j) sum += v[j];
       tmem_st32(tmem_base + lane_addr + c * 32, v);
-      umma::fence_proxy_async();        // this thread's slot writes -> visible to the TMA store (async proxy)
-      wg_sync();
-      if (trow == 0) {
-        tma_store_2d(&tmX, slots_u32 + sx * CH_TILE, c * 32, m0);
-        bulk_commit();
-      }
     }
-    if (trow == 0) {   // release the four store-staging slots once the stores have read them (never blocks the chunk loop)
-      bulk_wait_read<0>();
+    // one proxy fence + one warpgroup barrier for the four chunks, then the x tile leaves by TMA store and the four
+    // staging slots are released once the stores have read them
+    umma::fence_proxy_async();
+    wg_sync();
+    if (trow == 0) {
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) umma::mbar_arrive(&s_empty[(seqEA + cc * 2 + wg) % CH_NS]);
+      for (int cc = 0; cc < 4; ++cc) tma_store_2d(&tmX, slots_u32 + ((seqEA + cc * 2 + wg) % CH_NS) * CH_TILE, (wg * 4 + cc) * 32, m0);
+      bulk_commit();
     }
+    auto release_x_slots = [&]() {   // later, off the critical path: the stores have read the staging slots -> hand them back
+      if (trow == 0) {
+        bulk_wait_read<0>();
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) umma::mbar_arrive(&s_empty[(seqEA + cc * 2 + wg) % CH_NS]);
+      }
+    };
     tmem_st_wait();
     CH_TRACE(3, et == 0);
     // ---------------- row statistics (two-pass LayerNorm; the two warpgroups own 128 columns each)
@@ -503,6 +511,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       sRed[wg * 128 + trow] = sum;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mean = (sRed[trow] + sRed[128 + trow]) / 256.f;
+      release_x_slots();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       float qs = 0.f;
 #pragma unroll 1
@@ -516,6 +525,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       sRed[wg * 128 + trow] = qs;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       rstd = rsqrtf((sRed[trow] + sRed[128 + trow]) / 256.f + 1e-5f);
+    } else {
+      release_x_slots();
     }
     CH_TRACE(4, et == 0);
     ChainEpiCtx ectx{tmem_base + lane_addr, slots_u32, row_off, pb_u32, s_full, s_empty, wg, trow, p.ln_mode, mean, rstd};

@@ -62,17 +62,6 @@ if __name__ == "__main__":
         for terms in (21, 22, 23):     # 22 / 23: 1 / 2 of every 4 exponentials on the FMA pipe
             run(terms, 16, 600, 256, 32, 1998, 2)
             run(terms, 16, 600, 256, 32, 600, 0)
-    if which == "attn3":
-        for terms in (24, 25):       # umma_attention3.cuh: 16 softmax warps; 25: 1 of 4 exponentials on the FMA pipe
-            run(terms, 1, 128, 64, 32, 64, 0, iters=1)
-            run(terms, 1, 128, 64, 32, 200, 0, iters=1)
-            run(terms, 2, 100, 256, 32, 77, 2, iters=1)
-            run(terms, 3, 600, 256, 32, 20, 0, iters=1)
-            run(terms, 16, 600, 256, 32, 1998, 2)
-            run(terms, 16, 600, 256, 32, 600, 0)
-            run(terms, 16, 600, 256, 32, 20, 0)
-            run(terms, 16, 600, 256, 32, 1998, 2, qscale=4.0)
-        run(21, 16, 600, 256, 32, 1998, 2)
     if which == "prof":
         run(int(sys.argv[2]), 16, 600, 256, 32, 1998, 2, iters=1)
     if which in ("all", "attn2"):
