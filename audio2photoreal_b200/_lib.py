@@ -13,7 +13,7 @@ SYMBOLS = [
     "a2p_abi_version", "a2p_last_error", "a2p_has_tcgen05", "a2p_denoiser_create", "a2p_denoiser_destroy",
     "a2p_packed_weight_bytes", "a2p_denoiser_bind_weights", "a2p_kv_cache_bytes", "a2p_denoiser_set_conditioning",
     "a2p_conditioning_workspace_bytes", "a2p_workspace_bytes", "a2p_denoiser_forward", "a2p_sampler_step",
-    "a2p_sample_loop", "a2p_profile_forward", "a2p_launch_count",
+    "a2p_sample_loop", "a2p_sample_loop_rng", "a2p_sampler_step_rng", "a2p_profile_forward", "a2p_launch_count",
 ]
 
 
@@ -65,12 +65,14 @@ def load() -> C.CDLL:
     lib.a2p_denoiser_forward.argtypes = [vp, i32, i32, vp, i32, vp, i32, vp, vp, vp, sz, vp]
     lib.a2p_sampler_step.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp]
     lib.a2p_sample_loop.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, i32, i32, i32, vp, sz, vp]
+    lib.a2p_sample_loop_rng.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, C.c_uint64, i64, i32, i32, i32, vp, sz, vp]
+    lib.a2p_sampler_step_rng.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, C.c_uint64, i64, i64, i32, vp, vp, vp]
     lib.a2p_profile_forward.argtypes = [vp, i32, i32, vp, vp, i32, vp, sz, vp, vp, vp, i32]
     lib.a2p_profile_forward.restype = i32
     lib.a2p_launch_count.argtypes = [vp]
     lib.a2p_launch_count.restype = i64
     for name in ("a2p_denoiser_create", "a2p_denoiser_bind_weights", "a2p_denoiser_set_conditioning",
-                 "a2p_denoiser_forward", "a2p_sampler_step", "a2p_sample_loop"):
+                 "a2p_denoiser_forward", "a2p_sampler_step", "a2p_sample_loop", "a2p_sample_loop_rng", "a2p_sampler_step_rng"):
         getattr(lib, name).restype = i32
     if lib.a2p_abi_version() != 1:
         raise A2PError("liba2p_b200.so ABI version mismatch")

@@ -232,7 +232,30 @@ struct K3Params {
   int B, C, T, kind, clip;
   long long x0_sample_stride;  // floats between consecutive samples of x0c / x0u (rows are C apart)
   int* step_counter_dec;      // if set, thread 0 of block 0 decrements after use (graph loop)
+  int rng;                    // 1: noise = counter-based N(0,1) (Philox4x32-10 + Box-Muller) instead of a tape
+  unsigned long long seed;    // Philox key
+  long long rng_row0;         // global index of batch row 0 (sharded runs draw the rows they own from the same stream)
 };
+
+// Philox4x32-10 (Salmon et al., SC'11; the generator behind curand / torch CUDA).  counter = (element lo, element hi,
+// loop iteration, 0), key = seed.  Statistically -- not bitwise -- equivalent to the reference's th.randn_like.
+__host__ __device__ inline void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0, p1 = (unsigned long long)0xCD9E8D57u * c2;
+    const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1, n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long elem, unsigned iter) {
+  unsigned r[4];
+  philox4x32_10((unsigned)elem, (unsigned)(elem >> 32), iter, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+  const float u1 = ((float)r[0] + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+  const float u2 = (float)r[1] * 2.3283064365386963e-10f;            // [0, 1)
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
 
 __global__ void __launch_bounds__(256) k3_sampler_kernel(K3Params p) {
   __shared__ float tile[32][33];
@@ -268,11 +291,15 @@ __global__ void __launch_bounds__(256) k3_sampler_kernel(K3Params p) {
       float x0 = tile[threadIdx.x][i];
       float xt = p.x_t[o];
       float nz = noise ? noise[o] : 0.f;
+      if (p.rng) {
+        const long long it = p.step_counter ? (long long)(p.n_steps - 1 - step) : p.noise_step_stride;   // single step: iteration passed in noise_step_stride
+        nz = philox_normal(p.seed, (unsigned long long)(((p.rng_row0 + b) * p.C + c) * (long long)p.T + t), (unsigned)it);
+      }
       float out;
       if (p.kind == 0) {  // DDIM
         float eps = __fdiv_rn(__fsub_rn(__fmul_rn(co[0], xt), x0), co[1]);
         float mean = __fadd_rn(__fmul_rn(x0, co[2]), __fmul_rn(co[3], eps));
-        out = noise ? __fadd_rn(mean, __fmul_rn(co[4], nz)) : mean;
+        out = (noise || p.rng) ? __fadd_rn(mean, __fmul_rn(co[4], nz)) : mean;
       } else {  // ancestral
         float mean = __fadd_rn(__fmul_rn(co[5], x0), __fmul_rn(co[6], xt));
         out = __fadd_rn(mean, __fmul_rn(co[7], nz));

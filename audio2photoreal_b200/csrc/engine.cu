@@ -51,10 +51,11 @@ struct GraphKey {
   int B, T, kind, n_steps, clip, mask;
   const void *coeffs, *ts, *scale, *x, *pred, *noise, *ws;
   const void *kv0, *kv1;
+  unsigned long long seed; long long row0; int rng;
   bool operator==(const GraphKey& o) const {
     return B == o.B && T == o.T && kind == o.kind && n_steps == o.n_steps && clip == o.clip && mask == o.mask &&
            coeffs == o.coeffs && ts == o.ts && scale == o.scale && x == o.x && pred == o.pred && noise == o.noise &&
-           ws == o.ws && kv0 == o.kv0 && kv1 == o.kv1;
+           ws == o.ws && kv0 == o.kv0 && kv1 == o.kv1 && seed == o.seed && row0 == o.row0 && rng == o.rng;
   }
 };
 
@@ -1160,15 +1161,16 @@ int a2p_sampler_step(int kind, int B, int C, int T, const float* x_t, const floa
   return launch_k3(c, p);
 }
 
-int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, const float* coeffs, const int64_t* timesteps,
-                    const float* scale, float* x, float* pred_xstart, const float* noise_tape, int clip_denoised,
-                    int branch_mask, int use_graph, void* ws, size_t ws_bytes, void* stream) {
+static int sample_loop_impl(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, const float* coeffs, const int64_t* timesteps,
+                            const float* scale, float* x, float* pred_xstart, const float* noise_tape, int rng,
+                            unsigned long long seed, long long row0, int clip_denoised, int branch_mask, int use_graph, void* ws,
+                            size_t ws_bytes, void* stream) {
   if (!h || !h->bound) A2P_FAIL("sample_loop: weights not bound");
   if (kind != A2P_SAMPLER_DDIM && kind != A2P_SAMPLER_ANCESTRAL) A2P_FAIL("sample_loop: unknown kind %d", kind);
   if (B <= 0 || T <= 0 || n_steps <= 0 || !coeffs || !timesteps || !x || !pred_xstart || !ws) A2P_FAIL("sample_loop: bad argument");
   if (branch_mask != A2P_MASK_BOTH && branch_mask != A2P_MASK_COND) A2P_FAIL("sample_loop: branch_mask must be BOTH or COND");
   if (branch_mask == A2P_MASK_BOTH && !scale) A2P_FAIL("sample_loop: CFG needs scale");
-  if (kind == A2P_SAMPLER_ANCESTRAL && !noise_tape) A2P_FAIL("sample_loop: ancestral sampling needs a noise tape");
+  if (kind == A2P_SAMPLER_ANCESTRAL && !noise_tape && !rng) A2P_FAIL("sample_loop: ancestral sampling needs a noise tape (or a2p_sample_loop_rng)");
   const a2p_model_cfg& cf = h->cfg;
   const WsLayout w = ws_layout(cf, B, T);
   if (ws_bytes < w.total) A2P_FAIL("sample_loop: workspace too small (%zu < %zu)", ws_bytes, w.total);
@@ -1187,6 +1189,7 @@ int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, cons
     p.noise = noise_tape; p.noise_step_stride = (long long)B * cf.C * T; p.n_steps = n_steps;
     p.x_prev = x; p.pred = pred_xstart; p.B = B; p.C = cf.C; p.T = T; p.kind = kind; p.clip = clip_denoised;
     p.x0_sample_stride = sstride;
+    p.rng = rng; p.seed = seed; p.rng_row0 = row0;
     A2P_TRY(launch_k3(c, p));
     step_dec_kernel<<<1, 1, 0, c.st>>>(counter);
     h->launches++;
@@ -1201,7 +1204,7 @@ int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, cons
     return 0;
   }
   GraphKey key{B, T, kind, n_steps, clip_denoised, branch_mask, coeffs, timesteps, scale, x, pred_xstart, noise_tape, ws,
-               h->cond[0].base, h->cond[1].base};
+               h->cond[0].base, h->cond[1].base, seed, row0, rng};
   if (!h->gvalid || !(h->gkey == key)) {
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     h->gvalid = false;
@@ -1230,6 +1233,35 @@ int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, cons
   for (int i = 0; i < n_steps; ++i) A2P_CUDA(cudaGraphLaunch(h->gexec, c.st));
   h->launches += h->graph_nodes * n_steps;
   return 0;
+}
+
+int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, const float* coeffs, const int64_t* timesteps,
+                    const float* scale, float* x, float* pred_xstart, const float* noise_tape, int clip_denoised,
+                    int branch_mask, int use_graph, void* ws, size_t ws_bytes, void* stream) {
+  return sample_loop_impl(h, kind, B, T, n_steps, coeffs, timesteps, scale, x, pred_xstart, noise_tape, 0, 0ull, 0, clip_denoised,
+                          branch_mask, use_graph, ws, ws_bytes, stream);
+}
+
+int a2p_sample_loop_rng(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, const float* coeffs, const int64_t* timesteps,
+                        const float* scale, float* x, float* pred_xstart, uint64_t seed, int64_t row0, int clip_denoised,
+                        int branch_mask, int use_graph, void* ws, size_t ws_bytes, void* stream) {
+  return sample_loop_impl(h, kind, B, T, n_steps, coeffs, timesteps, scale, x, pred_xstart, nullptr, 1, (unsigned long long)seed,
+                          (long long)row0, clip_denoised, branch_mask, use_graph, ws, ws_bytes, stream);
+}
+
+int a2p_sampler_step_rng(int kind, int B, int C, int T, const float* x_t, const float* x0_cond, const float* x0_uncond,
+                         const float* scale, const float* coeffs, uint64_t seed, int64_t iteration, int64_t row0,
+                         int clip_denoised, float* x_prev, float* pred_xstart, void* stream) {
+  if (kind != A2P_SAMPLER_DDIM && kind != A2P_SAMPLER_ANCESTRAL) A2P_FAIL("sampler_step_rng: unknown kind %d", kind);
+  if (B <= 0 || C <= 0 || T <= 0 || !x_t || !x0_cond || !coeffs || !x_prev || !pred_xstart) A2P_FAIL("sampler_step_rng: bad argument");
+  if (x0_uncond && !scale) A2P_FAIL("sampler_step_rng: guidance needs scale");
+  Ctx c{nullptr, (cudaStream_t)stream};
+  K3Params p{};
+  p.x_t = x_t; p.x0c = x0_cond; p.x0u = x0_uncond; p.scale = scale; p.coeffs = coeffs; p.step_counter = nullptr;
+  p.noise = nullptr; p.noise_step_stride = (long long)iteration; p.n_steps = 1; p.x_prev = x_prev; p.pred = pred_xstart;
+  p.B = B; p.C = C; p.T = T; p.kind = kind; p.clip = clip_denoised; p.x0_sample_stride = (long long)T * C;
+  p.rng = 1; p.seed = (unsigned long long)seed; p.rng_row0 = (long long)row0;
+  return launch_k3(c, p);
 }
 
 int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, const int64_t* timesteps, int branch_mask,
@@ -1291,6 +1323,12 @@ int a2p_test_tc_gemm(int terms, int M, int N, int K, int taps, int dil, const fl
   if (ms_out) *ms_out = iters > 0 ? ms / iters : 0.f;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
+}
+
+void a2p_test_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4) {
+  unsigned o[4];
+  philox4x32_10(c0, c1, c2, c3, k0, k1, o);   // the same inline function the K3 kernel calls (host compilation)
+  for (int i = 0; i < 4; ++i) out4[i] = o[i];
 }
 
 int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_dev, void* stream) {

@@ -96,6 +96,15 @@ __device__ __forceinline__ void split_prob_pair2(float a, float b, uint32_t& hi,
   lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
 }
 
+#ifndef A2P_ATTN2_TRACE
+#define A2P_ATTN2_TRACE 0   // 1: clock64 timeline of CTA (0,0,0) into TcAttnParams::trace (scripts/gpu_attn_trace.py 21)
+#endif
+#if A2P_ATTN2_TRACE
+#define A2_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (cond) && i < 64) p.trace[i * 16 + (slot)] = clock64(); } while (0)
+#else
+#define A2_TRACE(slot, cond) do { } while (0)
+#endif
+
 // POLY of every 4 exponentials are evaluated with the FMA-pipe polynomial (umma::ex2_poly) instead of MUFU.EX2
 template <int PT, int POLY>
 __global__ void __launch_bounds__(384, 1)
@@ -192,9 +201,11 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     int st = 0; uint32_t ph = 0;        // stage / phase of block i (S side)
     int stj = 0;                        // stage of block i - 1 (PV side)
     for (int i = 0; i <= n_blocks; ++i) {
+      A2_TRACE(8, lane == 0);
       if (i < n_blocks) {
         umma::mbar_wait(&kv_full[st], ph);
         umma::fence_after();
+        A2_TRACE(9, lane == 0);
         if (umma::elect_one()) {
 #pragma unroll
           for (int w = 0; w < 2; ++w) {
@@ -216,8 +227,10 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int j = i - 1, b = j & 1;
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
+          A2_TRACE(10 + 2 * w, lane == 0);
           umma::mbar_wait(&p_ready[w * 2 + b], (j >> 1) & 1);
           umma::fence_after();
+          A2_TRACE(11 + 2 * w, lane == 0);
           if (umma::elect_one()) {
             const uint32_t lov = loKV + stj * (Cfg::KV_STAGE_BYTES >> 4) + 2 * (8192 >> 4) + w * (32 * 128 >> 4);   // V^T rows [32w, 32w+32)
             const uint32_t d = tmem_base + 256 + w * 64 + b * 32;
@@ -254,6 +267,10 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
     for (int c = 0; c < 32; ++c) o[c] = 0.f;
     float alpha_pend = 1.f;
+    // The two warpgroups would run in lockstep (both S tiles arrive together) and hit the MUFU-bound exponential phase at
+    // the same time; starting head 1 half an iteration late lets one warpgroup's exponentials overlap the other's
+    // load / max / barrier phase on every scheduler.
+    if (w == 1 && p.skew_ns > 0) __nanosleep(p.skew_ns);
     auto consume_pv = [&](int j, float alpha) {
       const int b = j & 1;
       umma::mbar_wait(&pv_full[w * 2 + b], (j >> 1) & 1);
@@ -269,12 +286,18 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     auto block = [&](int i, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int b = i & 1;
+      A2_TRACE(0, threadIdx.x == 128);
       umma::mbar_wait(&s_full[w * 2 + b], (i >> 1) & 1);
       umma::fence_after();
+      A2_TRACE(1, threadIdx.x == 128);
       float s[64];
       umma::tmem_ld32(tmS + b * 64, s);
       umma::tmem_ld32(tmS + b * 64 + 32, s + 32);
-      umma::tmem_ld_wait();
+      // PV(i-1) landed long ago: fold it into O now, so that its tcgen05.ld shares the wait with the S loads and its 32
+      // FMAs fill the issue slots between the exponentials below instead of trailing the iteration
+      if (i > 0) consume_pv(i - 1, alpha_pend);
+      else umma::tmem_ld_wait();
+      A2_TRACE(2, threadIdx.x == 128);
       if (MASKED) {
         const int nvalid = (i < nb_main) ? ::min(64, p.n_keys - i * 64) : p.n_extra;   // warp-uniform
 #pragma unroll
@@ -288,6 +311,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float alpha = umma::ex2_approx(m - mnew);
       m = mnew;
       const float nm = -mnew;
+      A2_TRACE(3, threadIdx.x == 128);
       if (!PT && i > 0) umma::mbar_wait(&p_free[w], (i - 1) & 1);   // PV(i-1) has finished reading the shared-memory planes
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
@@ -327,11 +351,13 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
       }
+      A2_TRACE(4, threadIdx.x == 128);
       if (PT) { tmem_st_wait2(); umma::fence_before(); }
       else umma::fence_proxy_async();
       umma::mbar_arrive(&p_ready[w * 2 + b]);
+      A2_TRACE(5, threadIdx.x == 128);
       l = l * alpha + (rs0 + rs1);
-      if (i > 0) consume_pv(i - 1, alpha_pend);
+      A2_TRACE(6, threadIdx.x == 128);
       alpha_pend = alpha;
     };
     const int n_full = ::min(p.n_keys / 64, n_blocks);    // leading blocks whose 64 keys are all valid

@@ -178,15 +178,18 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
       umma::tmem_ld32(c.tmem_row + ch * 32, v);
       umma::tmem_ld_wait();
     }
+    // all shared-memory loads of a stage are issued before its first dependent instruction (volatile asm keeps program order)
     if (c.ln_mode) {
       const uint32_t pw_ = c.pb_u32 + (CH_PB_LNW + ch * 32) * 4, pb_ = c.pb_u32 + (CH_PB_LNB + ch * 32) * 4;
+      float4 ww[8], bb[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { ww[u] = lds128(pw_ + u * 16); bb[u] = lds128(pb_ + u * 16); }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 ww = lds128(pw_ + u * 16), bb = lds128(pb_ + u * 16);
-        v[4 * u + 0] = (v[4 * u + 0] - c.mean) * c.rstd * ww.x + bb.x;
-        v[4 * u + 1] = (v[4 * u + 1] - c.mean) * c.rstd * ww.y + bb.y;
-        v[4 * u + 2] = (v[4 * u + 2] - c.mean) * c.rstd * ww.z + bb.z;
-        v[4 * u + 3] = (v[4 * u + 3] - c.mean) * c.rstd * ww.w + bb.w;
+        v[4 * u + 0] = (v[4 * u + 0] - c.mean) * c.rstd * ww[u].x + bb[u].x;
+        v[4 * u + 1] = (v[4 * u + 1] - c.mean) * c.rstd * ww[u].y + bb[u].y;
+        v[4 * u + 2] = (v[4 * u + 2] - c.mean) * c.rstd * ww[u].z + bb[u].z;
+        v[4 * u + 3] = (v[4 * u + 3] - c.mean) * c.rstd * ww[u].w + bb[u].w;
       }
     }
     if (rot) {
@@ -194,12 +197,14 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
       st = qt % CH_NS;
       umma::mbar_wait(&c.s_full[st], (qt / CH_NS) & 1);
       const uint32_t trw = c.slots_u32 + st * CH_TILE + c.row_off;
+      float4 cs[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cs[u] = lds128(trw + ((u ^ rx) << 4));   // (cos0, sin0, cos1, sin1)
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        const float4 cs = lds128(trw + ((u ^ rx) << 4));   // (cos0, sin0, cos1, sin1)
         const float h0 = v[4 * u], h1 = v[4 * u + 1], h2 = v[4 * u + 2], h3 = v[4 * u + 3];
-        v[4 * u + 0] = h0 * cs.x - h1 * cs.y; v[4 * u + 1] = h1 * cs.x + h0 * cs.y;
-        v[4 * u + 2] = h2 * cs.z - h3 * cs.w; v[4 * u + 3] = h3 * cs.z + h2 * cs.w;
+        v[4 * u + 0] = h0 * cs[u].x - h1 * cs[u].y; v[4 * u + 1] = h1 * cs[u].x + h0 * cs[u].y;
+        v[4 * u + 2] = h2 * cs[u].z - h3 * cs[u].w; v[4 * u + 3] = h3 * cs[u].z + h2 * cs[u].w;
       }
     }
     uint32_t hi[16], lo[16];
@@ -243,8 +248,9 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* acc1_empty = bars + 26;    // [2] 128 arrivals
   uint64_t* a_reads_done = bars + 28;
   uint64_t* a2_ready = bars + 29;      // 256 arrivals
-  uint64_t* x_stored = bars + 30;      // 2 arrivals (one per warpgroup): the x tile written by E_A is globally visible
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
+  uint64_t* x_stored = bars + 30;      // the x tile written by E_A is globally visible (store warp)
+  uint64_t* x_written = bars + 31;     // [2] 128 arrivals each: warpgroup w has written its four x chunks into the staging slots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -267,7 +273,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 1); }
     umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 256);
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 128); }
-    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 256); umma::mbar_init(x_stored, 2);
+    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 256); umma::mbar_init(x_stored, 1);
+    umma::mbar_init(&x_written[0], 128); umma::mbar_init(&x_written[1], 128);
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
@@ -414,6 +421,30 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
       CH_TRACE(32 + h, lane == 0 && h < 12);
     }
+  } else if (warp == 3) {
+    // ================= store warp: x tile -> global by TMA, then hand the staging slots back =================
+    if (lane == 0) {
+      umma::mbar_wait(&x_written[0], 0);
+      umma::mbar_wait(&x_written[1], 0);
+      // one bulk group per chunk, in ring order, so that each staging slot goes back to the producer as soon as ITS store
+      // has read it (the RoPE-table chunks of pass 3 are waiting for these slots)
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) {
+        tma_store_2d(&tmX, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, ((j & 1) * 4 + (j >> 1)) * 32, m0);
+        bulk_commit();
+      }
+      bulk_wait_read<7>(); umma::mbar_arrive(&s_empty[(seqEA + 0) % CH_NS]);
+      bulk_wait_read<6>(); umma::mbar_arrive(&s_empty[(seqEA + 1) % CH_NS]);
+      bulk_wait_read<5>(); umma::mbar_arrive(&s_empty[(seqEA + 2) % CH_NS]);
+      bulk_wait_read<4>(); umma::mbar_arrive(&s_empty[(seqEA + 3) % CH_NS]);
+      bulk_wait_read<3>(); umma::mbar_arrive(&s_empty[(seqEA + 4) % CH_NS]);
+      bulk_wait_read<2>(); umma::mbar_arrive(&s_empty[(seqEA + 5) % CH_NS]);
+      bulk_wait_read<1>(); umma::mbar_arrive(&s_empty[(seqEA + 6) % CH_NS]);
+      bulk_wait_read<0>(); umma::mbar_arrive(&s_empty[(seqEA + 7) % CH_NS]);
+      bulk_wait_all();           // globally visible (the V job re-reads the tile; nothing may be in flight at exit)
+      if (p.vjob) umma::mbar_arrive(x_stored);
+    }
+    __syncwarp();
   } else if (warp >= 4) {
     // ================= epilogue warpgroups =================
     const int wg = (warp - 4) >> 2;
@@ -470,39 +501,47 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const uint32_t srow = slots_u32 + sx * CH_TILE + row_off;
       const uint32_t pbc = pb_u32 + (CH_PB_BIAS0 + c * 32) * 4;
       const uint32_t pfs = pb_u32 + (CH_PB_FILM + sl * 512 + c * 32) * 4;
+      // 16 columns at a time: ALL shared-memory loads of the group are issued before the first dependent instruction
+      // (the loads / stores are volatile asm and keep program order: interleaving them per 4 columns serialised eight
+      // load-latency bubbles per chunk)
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 bb = lds128(pbc + u * 16);
-        float4 o = make_float4(v[4 * u] + bb.x, v[4 * u + 1] + bb.y, v[4 * u + 2] + bb.z, v[4 * u + 3] + bb.w);
+      for (int hf = 0; hf < 2; ++hf) {
+        float4 bb[4], xo[4], sc[4], sh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bb[k] = lds128(pbc + (hf * 4 + k) * 16);
         if (p.film_mode) {
-          const float4 xo = lds128(srow + ((u ^ rx) << 4));
-          const float4 sc = lds128(pfs + u * 16), sh = lds128(pfs + 1024 + u * 16);
-          o = make_float4(xo.x + ((sc.x + 1.f) * o.x + sh.x), xo.y + ((sc.y + 1.f) * o.y + sh.y),
-                          xo.z + ((sc.z + 1.f) * o.z + sh.z), xo.w + ((sc.w + 1.f) * o.w + sh.w));
-        }
-        sts128(srow + ((u ^ rx) << 4), o);
-        v[4 * u] = o.x; v[4 * u + 1] = o.y; v[4 * u + 2] = o.z; v[4 * u + 3] = o.w;
-      }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) sum += v[j];
+          for (int k = 0; k < 4; ++k) {
+            xo[k] = lds128(srow + (((hf * 4 + k) ^ rx) << 4));
+            sc[k] = lds128(pfs + (hf * 4 + k) * 16);
+            sh[k] = lds128(pfs + 1024 + (hf * 4 + k) * 16);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int u = hf * 4 + k;
+          float4 o = make_float4(v[4 * u] + bb[k].x, v[4 * u + 1] + bb[k].y, v[4 * u + 2] + bb[k].z, v[4 * u + 3] + bb[k].w);
+          if (p.film_mode)
+            o = make_float4(xo[k].x + ((sc[k].x + 1.f) * o.x + sh[k].x), xo[k].y + ((sc[k].y + 1.f) * o.y + sh[k].y),
+                            xo[k].z + ((sc[k].z + 1.f) * o.z + sh[k].z), xo[k].w + ((sc[k].w + 1.f) * o.w + sh[k].w));
+          v[4 * u] = o.x; v[4 * u + 1] = o.y; v[4 * u + 2] = o.z; v[4 * u + 3] = o.w;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int u = hf * 4 + k;
+          sts128(srow + ((u ^ rx) << 4), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+        }
+      }
+      float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int j = 0; j < 32; ++j) s4[j & 3] += v[j];
+      sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       tmem_st32(tmem_base + lane_addr + c * 32, v);
     }
-    // one proxy fence + one warpgroup barrier for the four chunks, then the x tile leaves by TMA store and the four
-    // staging slots are released once the stores have read them
+    // the x tile leaves by TMA store from the STORE WARP (warp 3): this thread only makes its writes visible to the async
+    // proxy and signals; waiting for the stores to drain the staging slots is nobody's critical path
     umma::fence_proxy_async();
-    wg_sync();
-    if (trow == 0) {
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) tma_store_2d(&tmX, slots_u32 + ((seqEA + cc * 2 + wg) % CH_NS) * CH_TILE, (wg * 4 + cc) * 32, m0);
-      bulk_commit();
-    }
-    auto release_x_slots = [&]() {   // later, off the critical path: the stores have read the staging slots -> hand them back
-      if (trow == 0) {
-        bulk_wait_read<0>();
-#pragma unroll 1
-        for (int cc = 0; cc < 4; ++cc) umma::mbar_arrive(&s_empty[(seqEA + cc * 2 + wg) % CH_NS]);
-      }
-    };
+    umma::mbar_arrive(&x_written[wg]);
     tmem_st_wait();
     CH_TRACE(3, et == 0);
     // ---------------- row statistics (two-pass LayerNorm; the two warpgroups own 128 columns each)
@@ -511,7 +550,6 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       sRed[wg * 128 + trow] = sum;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       mean = (sRed[trow] + sRed[128 + trow]) / 256.f;
-      release_x_slots();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       float qs = 0.f;
 #pragma unroll 1
@@ -525,17 +563,12 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       sRed[wg * 128 + trow] = qs;
       asm volatile("bar.sync 1, 256;" ::: "memory");
       rstd = rsqrtf((sRed[trow] + sRed[128 + trow]) / 256.f + 1e-5f);
-    } else {
-      release_x_slots();
     }
     CH_TRACE(4, et == 0);
     ChainEpiCtx ectx{tmem_base + lane_addr, slots_u32, row_off, pb_u32, s_full, s_empty, wg, trow, p.ln_mode, mean, rstd};
     chain_emit_planes(ectx, p.rope, -1, seqTab);
     umma::mbar_arrive(a_ready);
     CH_TRACE(5, et == 0);
-    // this warpgroup's x stores were issued several microseconds ago: confirm completion (global visibility) so that the
-    // TMA warp may re-read the tile for the V job as soon as ring slots free up
-    if (p.vjob && trow == 0) { bulk_wait_all(); umma::mbar_arrive(x_stored); }
 
     // ---------------- E_B: this warpgroup drains accumulator halves h = wg, wg + 2, ...
     bool vprep_done = false;
@@ -618,7 +651,6 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       }
     }
     CH_TRACE(30, et == 0);
-    if (!p.vjob && trow == 0) bulk_wait_all();   // the x stores must have completed before the CTA exits
   }
   __syncthreads();
   if (warp == 2) {

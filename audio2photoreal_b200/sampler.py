@@ -108,7 +108,7 @@ class Sampler(DiffusionTables):
 
     # ------------------------------------------------------------------ the loop
     def _loop(self, kind, model, shape, noise, clip_denoised, model_kwargs, device, progress, eta, skip_timesteps,
-              init_image, const_noise, noise_tape, advance_rng, use_graph):
+              init_image, const_noise, noise_tape, advance_rng, use_graph, noise_rng="torch", seed=None, row0=0):
         assert isinstance(shape, (tuple, list))
         dev = self._device_of(model, device)
         if dev.type != "cuda":
@@ -122,7 +122,15 @@ class Sampler(DiffusionTables):
             coeffs, tsmap = self._tables_on(dev, eta)
             need_noise = kind == ANCESTRAL or eta != 0.0
             tape = None
-            if need_noise:
+            philox = need_noise and noise_rng == "philox"
+            if noise_rng not in ("torch", "philox"):
+                raise ValueError("noise_rng must be 'torch' (bit-parity tape) or 'philox' (in-kernel, statistically equivalent)")
+            if philox:
+                if const_noise or noise_tape is not None:
+                    raise ValueError("noise_rng='philox' draws inside the kernel: const_noise / noise_tape need noise_rng='torch'")
+                if seed is None:
+                    seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            if need_noise and not philox:
                 if noise_tape is not None:
                     tape = noise_tape.to(dev, torch.float32).contiguous()
                     assert tape.shape == (n, B, Cc, one, T), "noise_tape must be [n_steps, B, C, 1, T]"
@@ -147,11 +155,17 @@ class Sampler(DiffusionTables):
                 scale = y["scale"].to(dev, torch.float32).contiguous() if cfg else None
                 ws = inner._workspace(lib.a2p_workspace_bytes(C.byref(inner._cfg), B, T), dev)
                 # sub-tables for skip_timesteps: loop runs indices n-1 .. 0
-                _lib.check(lib.a2p_sample_loop(
-                    inner._handle, kind, B, T, n, coeffs.data_ptr(), tsmap.data_ptr(),
-                    scale.data_ptr() if scale is not None else None, x.data_ptr(), pred.data_ptr(),
-                    tape.data_ptr() if tape is not None else None, int(bool(clip_denoised)), 3 if cfg else 1,
-                    int(bool(use_graph)), ws.data_ptr(), ws.numel(), st))
+                if philox:
+                    _lib.check(lib.a2p_sample_loop_rng(
+                        inner._handle, kind, B, T, n, coeffs.data_ptr(), tsmap.data_ptr(),
+                        scale.data_ptr() if scale is not None else None, x.data_ptr(), pred.data_ptr(), int(seed), int(row0),
+                        int(bool(clip_denoised)), 3 if cfg else 1, int(bool(use_graph)), ws.data_ptr(), ws.numel(), st))
+                else:
+                    _lib.check(lib.a2p_sample_loop(
+                        inner._handle, kind, B, T, n, coeffs.data_ptr(), tsmap.data_ptr(),
+                        scale.data_ptr() if scale is not None else None, x.data_ptr(), pred.data_ptr(),
+                        tape.data_ptr() if tape is not None else None, int(bool(clip_denoised)), 3 if cfg else 1,
+                        int(bool(use_graph)), ws.data_ptr(), ws.numel(), st))
                 self._last_keep = (x, pred, tape, scale)
                 return x, pred
             # generic model: caller's PyTorch forward + fused K3 epilogue
@@ -163,36 +177,44 @@ class Sampler(DiffusionTables):
                 ts = torch.full((B,), self.timestep_map[i], device=dev, dtype=torch.int64)
                 with torch.no_grad():
                     out = model(x, ts, **model_kwargs).float().contiguous()
-                _lib.check(lib.a2p_sampler_step(
-                    kind, B, Cc, T, x.data_ptr(), out.data_ptr(), None, None, coeffs[i].data_ptr(),
-                    tape[k].data_ptr() if tape is not None else None, int(bool(clip_denoised)), x.data_ptr(),
-                    pred.data_ptr(), st))
+                if philox:
+                    _lib.check(lib.a2p_sampler_step_rng(
+                        kind, B, Cc, T, x.data_ptr(), out.data_ptr(), None, None, coeffs[i].data_ptr(), int(seed), k, int(row0),
+                        int(bool(clip_denoised)), x.data_ptr(), pred.data_ptr(), st))
+                else:
+                    _lib.check(lib.a2p_sampler_step(
+                        kind, B, Cc, T, x.data_ptr(), out.data_ptr(), None, None, coeffs[i].data_ptr(),
+                        tape[k].data_ptr() if tape is not None else None, int(bool(clip_denoised)), x.data_ptr(),
+                        pred.data_ptr(), st))
             return x, pred
 
     def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                          model_kwargs=None, device=None, progress=False, eta=0.0, skip_timesteps=0, init_image=None,
                          randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,
-                         noise_tape=None, advance_rng=True, use_graph=True):
-        """Returns the last pred_xstart [B,C,1,T] (gaussian_diffusion.py:862)."""
+                         noise_tape=None, advance_rng=True, use_graph=True, noise_rng="torch", seed=None, row0=0):
+        """Returns the last pred_xstart [B,C,1,T] (gaussian_diffusion.py:862).  noise_rng='philox' (eta > 0 only): the
+        per-step noise is drawn inside the kernel (statistically equivalent to th.randn_like, no tape)."""
         if dump_steps is not None:
             raise NotImplementedError()
         if const_noise == True:  # noqa: E712  (same check as the reference, :841)
             raise NotImplementedError()
         self._unsupported(denoised_fn, cond_fn, randomize_class, cond_fn_with_grad)
         _, pred = self._loop(DDIM, model, shape, noise, clip_denoised, model_kwargs, device, progress, eta,
-                             skip_timesteps, init_image, False, noise_tape, advance_rng, use_graph)
+                             skip_timesteps, init_image, False, noise_tape, advance_rng, use_graph, noise_rng, seed, row0)
         return pred
 
     def p_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
                       model_kwargs=None, device=None, progress=False, skip_timesteps=0, init_image=None,
                       randomize_class=False, cond_fn_with_grad=False, dump_steps=None, const_noise=False,
-                      noise_tape=None, use_graph=True):
-        """Ancestral sampling; returns the final sample [B,C,1,T] (gaussian_diffusion.py:590)."""
+                      noise_tape=None, use_graph=True, noise_rng="torch", seed=None, row0=0):
+        """Ancestral sampling; returns the final sample [B,C,1,T] (gaussian_diffusion.py:590).  noise_rng='torch' (default)
+        reproduces the reference's randn_like draws bit for bit through a tape; 'philox' draws the noise inside the
+        sampler kernel (Philox4x32-10 keyed by `seed`; `row0` = global index of the first batch row when sharded)."""
         if dump_steps is not None:
             raise NotImplementedError("dump_steps needs per-step host copies; not on the reference callers' path")
         self._unsupported(denoised_fn, cond_fn, randomize_class, cond_fn_with_grad)
         x, _ = self._loop(ANCESTRAL, model, shape, noise, clip_denoised, model_kwargs, device, progress, 0.0,
-                          skip_timesteps, init_image, const_noise, noise_tape, False, use_graph)
+                          skip_timesteps, init_image, const_noise, noise_tape, False, use_graph, noise_rng, seed, row0)
         return x
 
 

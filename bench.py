@@ -304,8 +304,15 @@ def main():
         per_launch_ms = acc[dom] / max(1, n_cat[dom])
         flops_launch = alg.get(dom, 0)
         achieved = flops_launch / (per_launch_ms * 1e-3) / 1e12 if per_launch_ms > 0 else 0.0
+        traffic = None     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
+            if tr.get("kernel") == names[dom] and B == WORKLOAD["B"]:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": names[dom], "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None, "peak_source": f"bf16_tflops burst, of {peak_src}",
+                    "frac": achieved / peak_tf, "traffic": traffic, "peak_source": f"bf16_tflops burst, of {peak_src}",
                     "ms_per_launch": per_launch_ms, "launches_per_forward": int(n_cat[dom]),
                     "forward_ms_by_kernel": {n: round(float(v), 4) for n, v in zip(names, acc)},
                     "split_terms": SPLIT_TERMS,

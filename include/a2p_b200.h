@@ -154,6 +154,19 @@ int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, cons
                     const float* noise_tape, int clip_denoised, int branch_mask, int use_graph, void* ws,
                     size_t ws_bytes, void* stream);
 
+/* Same loop / step with IN-KERNEL noise instead of a tape: every (batch row, channel, frame, loop
+ * iteration) draws N(0,1) from Philox4x32-10 keyed by `seed` + Box-Muller inside K3.  This replaces the per-step
+ * th.randn_like(x) of p_sample (gaussian_diffusion.py:471-476, upstream form) and of ddim_sample at eta > 0 (:708-713)
+ * STATISTICALLY, not bitwise (parity runs use the tape).  row0 = global index of this call's batch row 0, so a batch
+ * sharded over ranks draws exactly the numbers the unsharded batch would.  No [n_steps,B,C,1,T] tape (2 GB at B = 8). */
+int a2p_sample_loop_rng(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, const float* coeffs,
+                        const int64_t* timesteps, const float* scale, float* x, float* pred_xstart, uint64_t seed,
+                        int64_t row0, int clip_denoised, int branch_mask, int use_graph, void* ws, size_t ws_bytes,
+                        void* stream);
+int a2p_sampler_step_rng(int kind, int B, int C, int T, const float* x_t, const float* x0_cond, const float* x0_uncond,
+                         const float* scale, const float* coeffs, uint64_t seed, int64_t iteration, int64_t row0,
+                         int clip_denoised, float* x_prev, float* pred_xstart, void* stream);
+
 /* Measurement aid (bench.py roofline): one un-captured denoiser evaluation with a CUDA-event pair around
  * every kernel; ms_by_cat / launches_by_cat are HOST arrays of ncat >= 9 entries, categories:
  * 0 time-conditioning GEMMs, 1 LayerNorm+RoPE, 2 attention projections, 3 self-attention core,

@@ -39,6 +39,9 @@ int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int
                    const float* W2, const float* bias2, void* Cp_out, void* Vt_out, void* scratch, size_t scratch_bytes,
                    int iters, float* ms_out, void* stream);
 
+/* Philox4x32-10 block function used by the in-kernel noise of K3 (host build of the same inline code; known-answer tests) */
+void a2p_test_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out4);
+
 /* micro-benchmark: total SM cycles for n_mma back-to-back tcgen05.mma (M=128, K=16, bf16) with the given N, A operand
  * from shared memory (0) or tensor memory (1); result written to the DEVICE pointer cycles_out_dev[0]. */
 int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_dev, void* stream);

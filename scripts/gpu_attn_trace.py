@@ -21,10 +21,12 @@ _lib.check(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.
 torch.cuda.synchronize()
 tr = O.view(-1)[: 64 * 16 * 2].view(torch.int64).view(64, 16).cpu()
 t0 = tr[8, 0].item()
-names = ["sm:top", "sm:s_full", "sm:ldtm", "sm:max/alpha", "sm:p_empty", "sm:exp+sts", "sm:fence+arr", "sm:consume",
+names = ["sm:top", "sm:s_full", "sm:ldtm", "sm:max/alpha", "sm:exp+st", "sm:wait+arr", "sm:consume", "-",
+         "mma:top", "mma:kv_full", "mma:w_p0", "mma:p0", "mma:w_p1", "mma:p1"] if terms >= 20 else \
+        ["sm:top", "sm:s_full", "sm:ldtm", "sm:max/alpha", "sm:p_empty", "sm:exp+sts", "sm:fence+arr", "sm:consume",
          "mma:top", "mma:kv_full", "mma:S_issued", "mma:PV_issued"]
 print("iter " + " ".join(f"{n:>13}" for n in names))
 for i in range(8, 28):
-    print(f"{i:4d} " + " ".join(f"{tr[i, k].item() - t0:13d}" for k in range(12)))
+    print(f"{i:4d} " + " ".join(f"{tr[i, k].item() - t0:13d}" for k in range(len(names))))
 d = tr[20:50, 0] - tr[19:49, 0]
 print("mean cycles per iteration (softmax thread):", d.float().mean().item())
