@@ -136,13 +136,58 @@ __device__ __forceinline__ float gelu_as(float x) {
   return fmaf(hx, er, hx);
 }
 
+// ---- packed fp32x2 arithmetic (FADD2 / FMUL2 / FFMA2 on sm_100): one issue slot for two elements.  The epilogues run at
+// ~0.25 instructions per cycle per warp with two warps per scheduler, so their time is proportional to the instruction count.
+struct f2 { float x, y; };
+__device__ __forceinline__ f2 add2(f2 a, f2 b) {
+  f2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 mul2(f2 a, f2 b) {
+  f2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rc, ra, rb;\n\tmov.b64 {%0, %1}, rc;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return r;
+}
+__device__ __forceinline__ f2 fma2(f2 a, f2 b, f2 c) {
+  f2 r;
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return r;
+}
+__device__ __forceinline__ f2 bc2(float v) { return f2{v, v}; }
+
+// gelu_as on a pair (same formula, same constants: results identical to the scalar version up to fma contraction)
+__device__ __forceinline__ f2 gelu_as2(f2 x) {
+  const f2 z = mul2(f2{fabsf(x.x), fabsf(x.y)}, bc2(0.70710678118654752440f));
+  const f2 den = fma2(bc2(0.3275911f), z, bc2(1.0f));
+  f2 t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.x) : "f"(den.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t.y) : "f"(den.y));
+  f2 pl = fma2(bc2(1.061405429f), t, bc2(-1.453152027f));
+  pl = fma2(pl, t, bc2(1.421413741f));
+  pl = fma2(pl, t, bc2(-0.284496736f));
+  pl = fma2(pl, t, bc2(0.254829592f));
+  pl = mul2(pl, t);
+  const f2 ze = mul2(mul2(z, z), bc2(-1.4426950408889634f));
+  const f2 e = f2{umma::ex2_approx(ze.x), umma::ex2_approx(ze.y)};
+  const f2 er0 = fma2(f2{-pl.x, -pl.y}, e, bc2(1.0f));
+  const f2 er = f2{copysignf(er0.x, x.x), copysignf(er0.y, x.y)};
+  const f2 hx = mul2(x, bc2(0.5f));
+  return fma2(hx, er, hx);
+}
+
 // activations: plane 0 rounded to bf16, plane 1 = exact residual truncated (|x - p0 - p1| <= 2^-17 |x|, unbiased because the
 // residual has either sign): 8 ALU/FMA-pipe ops per pair
 __device__ __forceinline__ void split_act_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   const uint32_t ua = __float_as_uint(a) + 0x8000u, ub = __float_as_uint(b) + 0x8000u;
   hi = __byte_perm(ua, ub, 0x7632);
-  const float ra = a - __uint_as_float(ua & 0xFFFF0000u), rb = b - __uint_as_float(ub & 0xFFFF0000u);
-  lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
+  // residual against the NEGATED plane-0 values (sign bit flipped in the same logic op) as one packed add
+  const f2 r = add2(f2{a, b}, f2{__uint_as_float((ua & 0xFFFF0000u) ^ 0x80000000u), __uint_as_float((ub & 0xFFFF0000u) ^ 0x80000000u)});
+  lo = __byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x7632);
 }
 
 // Epilogue-thread context of chain_emit_planes (kept out of line: it runs twice in kernels with a V job, and the chain
@@ -186,10 +231,9 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
       for (int u = 0; u < 8; ++u) { ww[u] = lds128(pw_ + u * 16); bb[u] = lds128(pb_ + u * 16); }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        v[4 * u + 0] = (v[4 * u + 0] - c.mean) * c.rstd * ww[u].x + bb[u].x;
-        v[4 * u + 1] = (v[4 * u + 1] - c.mean) * c.rstd * ww[u].y + bb[u].y;
-        v[4 * u + 2] = (v[4 * u + 2] - c.mean) * c.rstd * ww[u].z + bb[u].z;
-        v[4 * u + 3] = (v[4 * u + 3] - c.mean) * c.rstd * ww[u].w + bb[u].w;
+        const f2 h01 = fma2(mul2(add2(f2{v[4 * u], v[4 * u + 1]}, bc2(-c.mean)), bc2(c.rstd)), f2{ww[u].x, ww[u].y}, f2{bb[u].x, bb[u].y});
+        const f2 h23 = fma2(mul2(add2(f2{v[4 * u + 2], v[4 * u + 3]}, bc2(-c.mean)), bc2(c.rstd)), f2{ww[u].z, ww[u].w}, f2{bb[u].z, bb[u].w});
+        v[4 * u] = h01.x; v[4 * u + 1] = h01.y; v[4 * u + 2] = h23.x; v[4 * u + 3] = h23.y;
       }
     }
     if (rot) {
@@ -203,8 +247,9 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const float h0 = v[4 * u], h1 = v[4 * u + 1], h2 = v[4 * u + 2], h3 = v[4 * u + 3];
-        v[4 * u + 0] = h0 * cs[u].x - h1 * cs[u].y; v[4 * u + 1] = h1 * cs[u].x + h0 * cs[u].y;
-        v[4 * u + 2] = h2 * cs[u].z - h3 * cs[u].w; v[4 * u + 3] = h3 * cs[u].z + h2 * cs[u].w;
+        const f2 r01 = fma2(f2{h0, h1}, bc2(cs[u].x), mul2(f2{-h1, h0}, bc2(cs[u].y)));
+        const f2 r23 = fma2(f2{h2, h3}, bc2(cs[u].z), mul2(f2{-h3, h2}, bc2(cs[u].w)));
+        v[4 * u] = r01.x; v[4 * u + 1] = r01.y; v[4 * u + 2] = r23.x; v[4 * u + 3] = r23.y;
       }
     }
     uint32_t hi[16], lo[16];
@@ -520,11 +565,12 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int u = hf * 4 + k;
-          float4 o = make_float4(v[4 * u] + bb[k].x, v[4 * u + 1] + bb[k].y, v[4 * u + 2] + bb[k].z, v[4 * u + 3] + bb[k].w);
-          if (p.film_mode)
-            o = make_float4(xo[k].x + ((sc[k].x + 1.f) * o.x + sh[k].x), xo[k].y + ((sc[k].y + 1.f) * o.y + sh[k].y),
-                            xo[k].z + ((sc[k].z + 1.f) * o.z + sh[k].z), xo[k].w + ((sc[k].w + 1.f) * o.w + sh[k].w));
-          v[4 * u] = o.x; v[4 * u + 1] = o.y; v[4 * u + 2] = o.z; v[4 * u + 3] = o.w;
+          f2 o01 = add2(f2{v[4 * u], v[4 * u + 1]}, f2{bb[k].x, bb[k].y}), o23 = add2(f2{v[4 * u + 2], v[4 * u + 3]}, f2{bb[k].z, bb[k].w});
+          if (p.film_mode) {   // x + ((scale + 1) * (acc + b) + shift), same operation order as the unfused epilogue
+            o01 = add2(f2{xo[k].x, xo[k].y}, fma2(add2(f2{sc[k].x, sc[k].y}, bc2(1.f)), o01, f2{sh[k].x, sh[k].y}));
+            o23 = add2(f2{xo[k].z, xo[k].w}, fma2(add2(f2{sc[k].z, sc[k].w}, bc2(1.f)), o23, f2{sh[k].z, sh[k].w}));
+          }
+          v[4 * u] = o01.x; v[4 * u + 1] = o01.y; v[4 * u + 2] = o23.x; v[4 * u + 3] = o23.y;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -608,21 +654,19 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
             const float4 a = *reinterpret_cast<const float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2));
-            float o[4] = {a.x + bb.x, a.y + bb.y, a.z + bb.z, a.w + bb.w};
+            f2 o01 = add2(f2{a.x, a.y}, f2{bb.x, bb.y}), o23 = add2(f2{a.z, a.w}, f2{bb.z, bb.w});
             const int grow = m0 + wq * 32 + r;
             if (p.gelu) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] = gelu_as(o[j]);
+              o01 = gelu_as2(o01); o23 = gelu_as2(o23);
             } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o[j] *= osc;
+              o01 = mul2(o01, bc2(osc)); o23 = mul2(o23, bc2(osc));
             }
             if (!(col_ok && grow < p.M)) continue;
             long long orow = grow;
             if (p.remap_rps > 0) orow += (long long)(grow / p.remap_rps + 1) * p.remap_pad;
             uint32_t h0, l0, h1, l1;
-            split_act_pair(o[0], o[1], h0, l0);
-            split_act_pair(o[2], o[3], h1, l1);
+            split_act_pair(o01.x, o01.y, h0, l0);
+            split_act_pair(o23.x, o23.y, h1, l1);
             __nv_bfloat16* dst = p.Cp + orow * p.ldcp + col;
             *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
             *reinterpret_cast<uint2*>(dst + p.cp_plane_stride) = make_uint2(l0, l1);
