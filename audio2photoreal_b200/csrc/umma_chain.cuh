@@ -114,6 +114,11 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
   return v;
 }
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+  return v;
+}
 __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
   asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -190,6 +195,41 @@ __device__ __forceinline__ void split_act_pair(float a, float b, uint32_t& hi, u
   lo = __byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x7632);
 }
 
+// ---- 2-CTA cluster mode (CL = 2): the two CTAs of a cluster own neighbouring row tiles and SHARE every weight tile: each
+// CTA fetches half of the tile's rows from L2 and multicasts it into both CTAs' ring slots (the weight stream of 75 CTAs
+// is what saturates L2 -> SM bandwidth; profiles/r01k).  A slot may then be overwritten by the PEER's TMA, so every slot
+// release arrives on the empty barrier of BOTH CTAs (count 2) and the two CTAs walk the slot sequence in loose lockstep.
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t peer) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(umma::smem_u32(bar)), "r"(peer));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+}
+__device__ __forceinline__ void mma_commit_mc2(uint64_t* bar) {   // arrive on the same barrier of both CTAs when the MMAs complete
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(umma::smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc2(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      ::"r"(umma::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"((uint16_t)3)
+      : "memory");
+}
+template <int CL>
+__device__ __forceinline__ void slot_release(uint64_t* bar, uint32_t peer) {
+  umma::mbar_arrive(bar);
+  if (CL == 2) mbar_arrive_remote(bar, peer);
+}
+template <int CL>
+__device__ __forceinline__ void slot_release_commit(uint64_t* bar) {
+  if (CL == 2) mma_commit_mc2(bar);
+  else umma::mma_commit(bar);
+}
+
 // Epilogue-thread context of chain_emit_planes (kept out of line: it runs twice in kernels with a V job, and the chain
 // kernel is instruction-fetch sensitive -- every launch starts with a cold instruction cache).
 struct ChainEpiCtx {
@@ -198,10 +238,12 @@ struct ChainEpiCtx {
   uint64_t* s_full; uint64_t* s_empty;
   int wg, trow, ln_mode;
   float mean, rstd;
+  uint32_t peer;
 };
 
 // planes of (rotated) LayerNorm(x), written in place over x in tensor memory.  seq_x >= 0: the x chunks come from that
 // ring position (V job: tile re-read by TMA); otherwise from tensor memory.  rot: RoPE with table chunks at seq_tab.
+template <int CL>
 __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, int seq_x, int seq_tab) {
   const int rx = c.trow & 7;
 #pragma unroll 1
@@ -263,8 +305,8 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
     if (c.trow == 0) {
 #pragma unroll 1
       for (int cc = 0; cc < 4; ++cc) {
-        if (seq_x >= 0) umma::mbar_arrive(&c.s_empty[(seq_x + cc * 2 + c.wg) % CH_NS]);
-        if (rot) umma::mbar_arrive(&c.s_empty[(seq_tab + cc * 2 + c.wg) % CH_NS]);
+        if (seq_x >= 0) slot_release<CL>(&c.s_empty[(seq_x + cc * 2 + c.wg) % CH_NS], c.peer);
+        if (rot) slot_release<CL>(&c.s_empty[(seq_tab + cc * 2 + c.wg) % CH_NS], c.peer);
       }
     }
   }
@@ -274,6 +316,7 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
 
 #define CH_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && (cond)) p.trace[slot] = clock64(); } while (0)
 
+template <int CL>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -299,6 +342,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
+  const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u, peer = crank ^ 1u;
   const int kc0 = ceil_div(p.K0, 64);
   const int NH1 = ceil_div(p.N1, 128);
   const int n_acc = NH1 + (p.vjob ? 2 : 0);
@@ -315,7 +359,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (p.vjob) umma::prefetch_tmap(&tmW2);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], CL); }
     umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 256);
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 128); }
     umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 256); umma::mbar_init(x_stored, 1);
@@ -326,6 +370,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   pdl_trigger();
   umma::fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // the peer's barriers are initialised before anything is multicast / arrived remotely
   umma::fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t slots_u32 = umma::smem_u32(sSlots);
@@ -337,6 +382,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // Rolled nested loops (the fully unrolled form of this role alone was 25 KB of cold code), but no per-load decode
     // arithmetic: the load -> consume -> release -> reload round trip of a slot is the critical path of the GEMMs.
     int sl_ = 0; uint32_t ph_ = 0;
+    constexpr int KW = CL == 2 ? 3 : 0;   // weight tiles: 3 = my half of the rows, multicast to both CTAs of the cluster
     auto issue = [&](const CUtensorMap* tm, int kind, int c0, int c1, int c2) {   // kind 0: 3-D bf16 tile, 1: 2-D fp32 tile, 2: reserve
       umma::mbar_wait(&s_empty[sl_], ph_ ^ 1);
       if (umma::elect_one()) {
@@ -345,6 +391,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         } else {
           umma::mbar_expect_tx(&s_full[sl_], CH_TILE);
           if (kind == 0) umma::tma_load_3d(tm, &s_full[sl_], sSlots + sl_ * CH_TILE, c0, c1, c2);
+          else if (kind == 3) tma_load_3d_mc2(tm, &s_full[sl_], sSlots + sl_ * CH_TILE + crank * (CH_TILE / 2), c0, c1 + crank * 64, c2);
           else tma_load_2d(tm, &s_full[sl_], slots_u32 + sl_ * CH_TILE, c0, c1);
         }
       }
@@ -356,7 +403,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll 1
       for (int j = 0; j < 6; ++j) {
         if (j < 2) issue(&tmA0, 0, kc * 64, m0, j);
-        else issue(&tmW0, 0, kc * 64, ((j - 2) & 1) * 128, (j - 2) >> 1);
+        else issue(&tmW0, KW, kc * 64, ((j - 2) & 1) * 128, (j - 2) >> 1);
       }
     }
     CH_TRACE(24, lane == 0);
@@ -369,14 +416,14 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     CH_TRACE(25, lane == 0);
 #pragma unroll 1
-    for (int j = 0; j < 8 * NH1; ++j) issue(&tmW1, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
+    for (int j = 0; j < 8 * NH1; ++j) issue(&tmW1, KW, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
     CH_TRACE(26, lane == 0);
     if (p.vjob) {
       umma::mbar_wait(x_stored, 0);   // the x tile written by E_A is globally visible
 #pragma unroll 1
       for (int j = 0; j < 8; ++j) issue(&tmX, 1, ((j & 1) * 4 + (j >> 1)) * 32, m0, 0);
 #pragma unroll 1
-      for (int j = 0; j < 16; ++j) issue(&tmW2, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
+      for (int j = 0; j < 16; ++j) issue(&tmW2, KW, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
@@ -415,10 +462,10 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               for (int k = 0; k < 4; ++k)
                 umma::mma_bf16(d, umma::desc_make(lo0 + sa0 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, 1u);
             }
-            umma::mma_commit(&s_empty[s]);
+            slot_release_commit<CL>(&s_empty[s]);
             if (pw == 1 && nh == 1) {
-              umma::mma_commit(&s_empty[sa0]);
-              umma::mma_commit(&s_empty[sa1]);
+              slot_release_commit<CL>(&s_empty[sa0]);
+              slot_release_commit<CL>(&s_empty[sa1]);
               if (kc == kc0 - 1) umma::mma_commit(acc0_full);
             }
           }
@@ -455,7 +502,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
                                 (kc | pw | i | k) != 0 ? 1u : 0u);
               }
             }
-            umma::mma_commit(&s_empty[s]);
+            slot_release_commit<CL>(&s_empty[s]);
             if (kc == 3 && pw == 1) {
               umma::mma_commit(&acc1_full[buf]);
               if (h == NH1 - 1) umma::mma_commit(a_reads_done);
@@ -478,14 +525,14 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         tma_store_2d(&tmX, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, ((j & 1) * 4 + (j >> 1)) * 32, m0);
         bulk_commit();
       }
-      bulk_wait_read<7>(); umma::mbar_arrive(&s_empty[(seqEA + 0) % CH_NS]);
-      bulk_wait_read<6>(); umma::mbar_arrive(&s_empty[(seqEA + 1) % CH_NS]);
-      bulk_wait_read<5>(); umma::mbar_arrive(&s_empty[(seqEA + 2) % CH_NS]);
-      bulk_wait_read<4>(); umma::mbar_arrive(&s_empty[(seqEA + 3) % CH_NS]);
-      bulk_wait_read<3>(); umma::mbar_arrive(&s_empty[(seqEA + 4) % CH_NS]);
-      bulk_wait_read<2>(); umma::mbar_arrive(&s_empty[(seqEA + 5) % CH_NS]);
-      bulk_wait_read<1>(); umma::mbar_arrive(&s_empty[(seqEA + 6) % CH_NS]);
-      bulk_wait_read<0>(); umma::mbar_arrive(&s_empty[(seqEA + 7) % CH_NS]);
+      bulk_wait_read<7>(); slot_release<CL>(&s_empty[(seqEA + 0) % CH_NS], peer);
+      bulk_wait_read<6>(); slot_release<CL>(&s_empty[(seqEA + 1) % CH_NS], peer);
+      bulk_wait_read<5>(); slot_release<CL>(&s_empty[(seqEA + 2) % CH_NS], peer);
+      bulk_wait_read<4>(); slot_release<CL>(&s_empty[(seqEA + 3) % CH_NS], peer);
+      bulk_wait_read<3>(); slot_release<CL>(&s_empty[(seqEA + 4) % CH_NS], peer);
+      bulk_wait_read<2>(); slot_release<CL>(&s_empty[(seqEA + 5) % CH_NS], peer);
+      bulk_wait_read<1>(); slot_release<CL>(&s_empty[(seqEA + 6) % CH_NS], peer);
+      bulk_wait_read<0>(); slot_release<CL>(&s_empty[(seqEA + 7) % CH_NS], peer);
       bulk_wait_all();           // globally visible (the V job re-reads the tile; nothing may be in flight at exit)
       if (p.vjob) umma::mbar_arrive(x_stored);
     }
@@ -611,8 +658,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       rstd = rsqrtf((sRed[trow] + sRed[128 + trow]) / 256.f + 1e-5f);
     }
     CH_TRACE(4, et == 0);
-    ChainEpiCtx ectx{tmem_base + lane_addr, slots_u32, row_off, pb_u32, s_full, s_empty, wg, trow, p.ln_mode, mean, rstd};
-    chain_emit_planes(ectx, p.rope, -1, seqTab);
+    ChainEpiCtx ectx{tmem_base + lane_addr, slots_u32, row_off, pb_u32, s_full, s_empty, wg, trow, p.ln_mode, mean, rstd, peer};
+    chain_emit_planes<CL>(ectx, p.rope, -1, seqTab);
     umma::mbar_arrive(a_ready);
     CH_TRACE(5, et == 0);
 
@@ -624,7 +671,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (vj && !vprep_done) {
         umma::mbar_wait(a_reads_done, 0);    // every GEMM1 MMA has read the rotated planes
         umma::fence_after();
-        chain_emit_planes(ectx, 0, seqVx, 0);
+        chain_emit_planes<CL>(ectx, 0, seqVx, 0);
         umma::mbar_arrive(a2_ready);
         vprep_done = true;
       }
@@ -639,9 +686,10 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           umma::tmem_ld32(tmem_base + lane_addr + 256 + buf * 128 + c * 32, v);
           umma::tmem_ld_wait();
           if (c == 3) { umma::fence_before(); umma::mbar_arrive(&acc1_empty[buf]); }
+          const uint32_t stg_row = umma::smem_u32(stg) + lane * 128;
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            *reinterpret_cast<float4*>(stg + lane * 32 + ((q ^ (lane & 7)) << 2)) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            sts128(stg_row + ((q ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
         }
         __syncwarp();
         if (!vj) {
@@ -650,10 +698,13 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           const bool col_ok = col < p.N1;
           const float4 bb = lds128(pb_u32 + (CH_PB_BIAS1 + (col_ok ? col : 0)) * 4);
           const float osc = (p.scale_ncols != 0 && col >= p.scale_ncols) ? 1.f : p.out_scale;
+          const uint32_t stg_u32 = umma::smem_u32(stg);
+          const int remap_first = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_pad : 0;   // pad rows in front of the tile's first sample
+          const int remap_edge = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_rps : 0x7fffffff;   // first row of the next sample (T >= 128: at most one boundary per tile)
 #pragma unroll 2
           for (int it = 0; it < 8; ++it) {
             const int r = it * 4 + rsub;
-            const float4 a = *reinterpret_cast<const float4*>(stg + r * 32 + ((uq ^ (r & 7)) << 2));
+            const float4 a = lds128(stg_u32 + ((r * 32 + ((uq ^ (r & 7)) << 2)) << 2));
             f2 o01 = add2(f2{a.x, a.y}, f2{bb.x, bb.y}), o23 = add2(f2{a.z, a.w}, f2{bb.z, bb.w});
             const int grow = m0 + wq * 32 + r;
             if (p.gelu) {
@@ -662,8 +713,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
               o01 = mul2(o01, bc2(osc)); o23 = mul2(o23, bc2(osc));
             }
             if (!(col_ok && grow < p.M)) continue;
-            long long orow = grow;
-            if (p.remap_rps > 0) orow += (long long)(grow / p.remap_rps + 1) * p.remap_pad;
+            const long long orow = grow + remap_first + (grow >= remap_edge ? p.remap_pad : 0);
             uint32_t h0, l0, h1, l1;
             split_act_pair(o01.x, o01.y, h0, l0);
             split_act_pair(o23.x, o23.y, h1, l1);
@@ -674,10 +724,11 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         } else {
           // V job: the accumulator is V[tokens, channels]; store V^T: lane = channel, 32 consecutive tokens = 64 B per plane
           const int ch = (h - NH1) * 128 + c * 32 + lane;
-          const float b2 = sPB[CH_PB_BIAS2 + ch];
+          const float b2 = lds32(pb_u32 + (CH_PB_BIAS2 + ch) * 4);
+          const uint32_t stg_u32 = umma::smem_u32(stg);
           float t[32];
 #pragma unroll
-          for (int r = 0; r < 32; ++r) t[r] = stg[r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)] + b2;
+          for (int r = 0; r < 32; ++r) t[r] = lds32(stg_u32 + ((r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)) << 2)) + b2;
           const int tok0 = m0 + wq * 32;
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -697,6 +748,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     CH_TRACE(30, et == 0);
   }
   __syncthreads();
+  if (CL == 2) cluster_sync_all();     // no CTA leaves while its peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     umma::fence_after();
     umma::tmem_dealloc<512>(tmem_base);
@@ -719,6 +771,13 @@ inline int make_tmap_f32_2d(CUtensorMap* tm, const void* base, long long cols, l
   return 0;
 }
 
+// A2P_CHAIN_CLUSTER=2: pairs of CTAs share the weight stream through TMA multicast (default 1 until measured faster)
+inline int chain_cluster_size() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A2P_CHAIN_CLUSTER"); v = (e && atoi(e) == 2) ? 2 : 1; }
+  return v;
+}
+
 struct ChainOperands {
   const __nv_bfloat16* A0; long long a0_rows, a0_ld, a0_plane_stride;   // [2][a0_rows][a0_ld], K0 valid columns
   const __nv_bfloat16* W0; long long w0_plane_stride;                   // [2][256][K0]
@@ -735,21 +794,34 @@ inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaS
   if (p.rope && (!o.rope_ext || o.rope_ext_rows < p.T + 128)) A2P_FAIL("chain: RoPE needs the extended table (T + 128 rows)");
   CUtensorMap tA0, tW0, tW1, tW2, tX, tTab;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
+  const int cl = chain_cluster_size();
+  const int wbox = 128 / cl;            // weight tiles: every CTA of a cluster fetches 1/cl of the rows and multicasts it
   A2P_TRY(make_tmap_bf16_3d(&tA0, o.A0, p.K0, o.a0_rows, 2, o.a0_ld, o.a0_plane_stride, 64, 128, sw));
-  A2P_TRY(make_tmap_bf16_3d(&tW0, o.W0, p.K0, 256, 2, p.K0, o.w0_plane_stride, 64, 128, sw));
-  A2P_TRY(make_tmap_bf16_3d(&tW1, o.W1, 256, p.N1, 2, 256, o.w1_plane_stride, 64, 128, sw));
-  if (p.vjob) A2P_TRY(make_tmap_bf16_3d(&tW2, o.W2, 256, 256, 2, 256, o.w2_plane_stride, 64, 128, sw));
+  A2P_TRY(make_tmap_bf16_3d(&tW0, o.W0, p.K0, 256, 2, p.K0, o.w0_plane_stride, 64, wbox, sw));
+  A2P_TRY(make_tmap_bf16_3d(&tW1, o.W1, 256, p.N1, 2, 256, o.w1_plane_stride, 64, wbox, sw));
+  if (p.vjob) A2P_TRY(make_tmap_bf16_3d(&tW2, o.W2, 256, 256, 2, 256, o.w2_plane_stride, 64, wbox, sw));
   else tW2 = tW1;
   A2P_TRY(make_tmap_f32_2d(&tX, o.x, 256, p.M, 256, 32, 128));
   if (p.rope) A2P_TRY(make_tmap_f32_2d(&tTab, o.rope_ext, 256, o.rope_ext_rows, 256, 32, 128));
   else tTab = tX;
-  const int grid = ceil_div(p.M, 128);
-  A2P_CUDA(launch_pdl(umma_chain_kernel, dim3(grid), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, st, tA0, tW0, tW1, tW2, tX, tTab, p));
+  const int tiles = ceil_div(p.M, 128);
+  if (cl == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = CH_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    A2P_CUDA(cudaLaunchKernelEx(&cfg, umma_chain_kernel<2>, tA0, tW0, tW1, tW2, tX, tTab, p));
+  } else {
+    A2P_CUDA(launch_pdl(umma_chain_kernel<1>, dim3(tiles), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, st, tA0, tW0, tW1, tW2, tX, tTab, p));
+  }
   return 0;
 }
 
 inline int init_umma_chain() {
-  A2P_CUDA(cudaFuncSetAttribute(umma_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
+  A2P_CUDA(cudaFuncSetAttribute(umma_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
+  A2P_CUDA(cudaFuncSetAttribute(umma_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM_BYTES));
   return 0;
 }
 
