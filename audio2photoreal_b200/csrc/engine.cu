@@ -163,6 +163,7 @@ struct WsLayout {
   size_t tcnUP, tcnVP;              // TCN activation planes in the left-padded layout
   size_t qkP, vtS, kttP, vttT;      // tensor-core attention operands: Q|K planes, self V^T planes, time-token K / V^T planes
   size_t ropeX;                     // chain arm: RoPE table extended to T + 128 rows (one TMA box per 128-row tile)
+  size_t splitS, splitC;            // attention split-KV tail: partial results and per-tile arrival counters
 };
 WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
   WsLayout w{};
@@ -190,6 +191,7 @@ WsLayout ws_layout(const a2p_model_cfg& c, int B, int T) {
     w.qkP = take(P * R * T * 2 * D / 2 + 64); w.vtS = take(P * D * align_up(R * T, 8) / 2 + 64);
     w.kttP = take(P * (2 * R + 64) * c.L * D / 2 + 64); w.vttT = take(P * c.L * D * (8 * R) / 2 + 64);
     w.ropeX = take((size_t)(T + 128) * D);
+    w.splitS = take(attn2_split_scratch_floats()); w.splitC = take(attn2_split_counter_ints());
     if (c.fmt == A2P_FMT_POSE) {
       const size_t cm = c.C > 256 ? c.C : 256;
       w.tcnUP = take(P * R * (T + TCN_PAD) * cm / 2 + 64); w.tcnVP = take(P * R * (T + TCN_PAD) * cm / 2 + 64);
@@ -478,6 +480,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     o.Q = qkP; o.q_rows = MT; o.q_ld = 2 * D; o.q_plane_stride = (long long)MT * 2 * D;
     o.vt_rows = D;
     ap.skew_ns = h->attn_skew_ns;
+    if (P == 2) { ap.split_scratch = F(w.splitS); ap.split_counters = reinterpret_cast<int*>(wsb + w.splitC); }
     ap.T = T; ap.R = R; ap.D = D; ap.dh = dh; ap.q_col0 = 0; ap.Op = attP; ap.op_plane_stride = pstrideD; ap.o_ld = D; ap.O = nullptr;
     if (kind == 0) {
       o.K[0] = qkP; o.k_rows[0] = MT; o.k_ld[0] = 2 * D; o.k_plane_stride[0] = (long long)MT * 2 * D;
@@ -520,6 +523,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   // ===== fused row-chain arm (split_terms == 2, D == 256): per layer 4 chain launches + 3 attention launches =====
   const bool chain = P == 2 && D == 256 && tc_attn && T >= 128 && !chain_disabled();
   if (chain) {
+    A2P_CUDA(cudaMemsetAsync(wsb + w.splitC, 0, attn2_split_counter_ints() * sizeof(int), st));   // arrival counters of the split-KV tail
     float* ropeX = F(w.ropeX);
     rope_ext_kernel<<<ceil_div((T + 128) * (D / 2), 256), 256, 0, st>>>(h->rope_tab, reinterpret_cast<float2*>(ropeX), T, D / 2);
     h->launches++;
@@ -1338,7 +1342,8 @@ int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_d
 size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_extra) {
   const size_t Sp = align_up((size_t)S, 8), Xp = 8;
   return (align_up((size_t)3 * R * T * D, 512) + align_up((size_t)3 * R * S * D, 512) + align_up((size_t)3 * D * R * Sp, 512) +
-          align_up((size_t)3 * R * 8 * D, 512) + align_up((size_t)3 * D * R * Xp, 512)) * 2 + 8192 + 64 * 16 * 8;
+          align_up((size_t)3 * R * 8 * D, 512) + align_up((size_t)3 * D * R * Xp, 512)) * 2 + 8192 + 64 * 16 * 8 +
+         attn2_split_scratch_floats() * 4 + attn2_split_counter_ints() * 4 + 1024;
 }
 
 int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K,
@@ -1382,6 +1387,12 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   p.O = O; p.o_ld = D; p.Op = nullptr;
   p.skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : 0;
   p.trace = (iters < 0) ? reinterpret_cast<long long*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) : nullptr;   // iters < 0: trace mode
+  {  // split-KV scratch behind the trace area (the whole scratch buffer was zeroed above, counters included)
+    char* tail = reinterpret_cast<char*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) + 64 * 16 * 8;
+    tail += 512 - (reinterpret_cast<uintptr_t>(tail) & 255);
+    p.split_scratch = reinterpret_cast<float*>(tail);
+    p.split_counters = reinterpret_cast<int*>(tail + attn2_split_scratch_floats() * 4);
+  }
   auto launch = [&]() -> int { return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st); };
   A2P_TRY(launch());
   if (iters < 0) {

@@ -42,6 +42,9 @@ struct TcAttnParams {
   int vx_row0, vx_col_stride; // extra V^T tensor: row of group 0 (= layer * D), columns per sample (2)
   __nv_bfloat16* Op; long long op_plane_stride; long long o_ld;   // output planes [TERMS][R*T][o_ld]
   float* O;                                                       // optional fp32 output [R*T][o_ld] (tests)
+  // split-KV tail (umma_attention2.cuh): work items [0, split_full) are whole tiles; the remaining tiles are cut into
+  // split_parts key ranges each (one work item per range) whose partial (max, sum, O) are merged by the last finisher
+  float* split_scratch; int* split_counters; int split_full, split_parts, n_qt, n_groups;
   int skew_ns;                                                    // start delay of softmax warpgroup 1 (see kernel)
   long long* trace;                                               // optional [64 iters][16] clock64 timestamps of CTA (0,0,0) (diagnostics)
 };

@@ -100,7 +100,7 @@ __device__ __forceinline__ void split_prob_pair2(float a, float b, uint32_t& hi,
 #define A2P_ATTN2_TRACE 0   // 1: clock64 timeline of CTA (0,0,0) into TcAttnParams::trace (scripts/gpu_attn_trace.py 21)
 #endif
 #if A2P_ATTN2_TRACE
-#define A2_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (cond) && i < 64) p.trace[i * 16 + (slot)] = clock64(); } while (0)
+#define A2_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && (cond) && i < 64) p.trace[i * 16 + (slot)] = clock64(); } while (0)
 #else
 #define A2_TRACE(slot, cond) do { } while (0)
 #endif
@@ -130,11 +130,21 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, g = blockIdx.y, r = blockIdx.z;
+  // work item -> (tile, key range).  Tiles beyond split_full are cut into split_parts key ranges: a launch whose tile count is
+  // not a multiple of the SM count would otherwise leave most SMs idle during its last round (320 tiles on 148 SMs = 3 rounds
+  // for 2.16 rounds of work), and a small batch would not fill the machine at all.
+  int tile = blockIdx.x, part = 0, nparts = 1;
+  if ((int)blockIdx.x >= p.split_full) {
+    const int t_ = blockIdx.x - p.split_full;
+    tile = p.split_full + t_ / p.split_parts; part = t_ % p.split_parts; nparts = p.split_parts;
+  }
+  const int q0 = (tile % p.n_qt) * 128, g = (tile / p.n_qt) % p.n_groups, r = tile / (p.n_qt * p.n_groups);
   const int br = r >= p.rows_per_branch ? 1 : 0;
   const int rr = r - br * p.rows_per_branch;
   const int nb_main = ceil_div(p.n_keys, 64);
-  const int n_blocks = nb_main + (p.n_extra > 0 ? 1 : 0);
+  const int n_blocks_all = nb_main + (p.n_extra > 0 ? 1 : 0);
+  const int kb0 = part * n_blocks_all / nparts, kb1 = (part + 1) * n_blocks_all / nparts;
+  const int n_blocks = kb1 - kb0;        // key blocks [kb0, kb1) of this work item; local index i <-> global block kb0 + i
 
   if (warp == 0 && lane == 0) {
     umma::prefetch_tmap(&tmQ);
@@ -175,11 +185,12 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         umma::mbar_expect_tx(&kv_full[st], Cfg::KV_STAGE_BYTES);
         uint8_t* sk = sKV + st * Cfg::KV_STAGE_BYTES;
         uint8_t* sv = sk + 2 * 8192;
-        if (j < nb_main) {
+        const int gb = kb0 + j;
+        if (gb < nb_main) {
 #pragma unroll
-          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tK, &kv_full[st], sk + i * 8192, p.k_col0 + g * 64, k_row_base + j * 64, i);
+          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tK, &kv_full[st], sk + i * 8192, p.k_col0 + g * 64, k_row_base + gb * 64, i);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tV, &kv_full[st], sv + i * 8192, v_col_base + j * 64, g * 64, i);
+          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tV, &kv_full[st], sv + i * 8192, v_col_base + gb * 64, g * 64, i);
         } else {
 #pragma unroll
           for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmKx, &kv_full[st], sk + i * 8192, p.kx_col0 + g * 64, r * p.kx_row_stride, i);
@@ -299,7 +310,8 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       else umma::tmem_ld_wait();
       A2_TRACE(2, threadIdx.x == 128);
       if (MASKED) {
-        const int nvalid = (i < nb_main) ? ::min(64, p.n_keys - i * 64) : p.n_extra;   // warp-uniform
+        const int gb = kb0 + i;
+        const int nvalid = (gb < nb_main) ? ::min(64, p.n_keys - gb * 64) : p.n_extra;   // warp-uniform
 #pragma unroll
         for (int c = 0; c < 64; ++c) s[c] = c < nvalid ? s[c] : -INFINITY;
       }
@@ -360,16 +372,47 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       A2_TRACE(6, threadIdx.x == 128);
       alpha_pend = alpha;
     };
-    const int n_full = ::min(p.n_keys / 64, n_blocks);    // leading blocks whose 64 keys are all valid
+    const int n_full = ::max(0, ::min(p.n_keys / 64 - kb0, n_blocks));    // leading blocks whose 64 keys are all valid
     int i = 0;
 #pragma unroll 1
     for (; i < n_full; ++i) block(i, std::false_type{});
 #pragma unroll 1
     for (; i < n_blocks; ++i) block(i, std::true_type{});
     consume_pv(n_blocks - 1, alpha_pend);
+    bool writer = true;
+    if (nparts > 1) {
+      // ---- split tile: publish this key range's (max, sum, O); the LAST work item of the tile to finish merges them all
+      const int slot = tile - p.split_full;
+      float* my = p.split_scratch + ((size_t)(slot * nparts + part) * 2 + w) * 34 * 128 + trow;
+      my[0] = m; my[128] = l;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) my[(2 + c) * 128] = o[c];
+      __threadfence();
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      int* flag = reinterpret_cast<int*>(bars + 24);
+      if (threadIdx.x == 128) *flag = atomicAdd(p.split_counters + slot, 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      writer = (*flag == nparts - 1);
+      if (writer) {
+        __threadfence();
+#pragma unroll 1
+        for (int pp = 0; pp < nparts; ++pp) {
+          if (pp == part) continue;
+          const float* ot = p.split_scratch + ((size_t)(slot * nparts + pp) * 2 + w) * 34 * 128 + trow;
+          const float m1 = __ldcg(ot), l1 = __ldcg(ot + 128);
+          const float mm = fmaxf(m, m1);
+          const float w0 = umma::ex2_approx(m - mm), w1 = umma::ex2_approx(m1 - mm);   // exp2(-inf) = 0 for an empty range
+          l = l * w0 + l1 * w1;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = o[c] * w0 + __ldcg(ot + (2 + c) * 128) * w1;
+          m = mm;
+        }
+        if (threadIdx.x == 128) p.split_counters[slot] = 0;   // ready for the next launch
+      }
+    }
     // ---- normalise, store head w of this row
     const int row = q0 + trow;
-    if (row < p.T) {
+    if (writer && row < p.T) {
       const long long grow = (long long)r * p.T + row;
       const float inv = 1.f / l;
 #pragma unroll
@@ -404,6 +447,20 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+inline int attn2_num_sms() {
+  static int v = -1;
+  if (v < 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (v <= 0) v = 148; }
+  return v;
+}
+inline bool attn2_split_disabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("A2P_NO_SPLIT_KV") ? 1 : 0;
+  return v == 1;
+}
+// scratch for the split tiles of one launch: at most num_sms work items x 2 heads x (max, sum, 32 accumulators) x 128 rows
+inline size_t attn2_split_scratch_floats() { return (size_t)attn2_num_sms() * 2 * 34 * 128; }
+inline size_t attn2_split_counter_ints() { return (size_t)attn2_num_sms(); }
+
 template <int PT, int POLY>
 int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
   using Cfg = Attn2Cfg<PT>;
@@ -421,9 +478,22 @@ int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStre
   } else {
     tkx = tk[0]; tvx = tv[0];
   }
-  dim3 grid(ceil_div(p.T, 128), p.D / 64, p.R);
+  TcAttnParams q = p;
+  q.n_qt = ceil_div(p.T, 128); q.n_groups = p.D / 64;
+  const int n_tiles = q.n_qt * q.n_groups * p.R;
+  const int nb = ceil_div(p.n_keys, 64) + (p.n_extra > 0 ? 1 : 0);
+  const int sms = attn2_num_sms();
+  q.split_full = n_tiles; q.split_parts = 1;
+  const int rem = n_tiles % sms;
+  if (p.split_scratch && p.split_counters && rem > 0 && !attn2_split_disabled()) {
+    int parts = sms / rem;                         // work items that fit beside each other in the last round
+    if (parts > nb / 2) parts = nb / 2;            // at least two key blocks per range
+    if (parts > 8) parts = 8;
+    if (parts >= 2) { q.split_full = n_tiles - rem; q.split_parts = parts; }
+  }
+  dim3 grid(q.split_full + (n_tiles - q.split_full) * q.split_parts);
   A2P_CUDA(launch_pdl(umma_attn2_kernel<PT, POLY>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
-                      tkx, tvx, p));
+                      tkx, tvx, q));
   return 0;
 }
 
