@@ -52,14 +52,15 @@ struct ChainParams {
   long long* trace;          // optional [64] clock64 timeline of CTA 0 (A2P_CHAIN_TRACE=1 in the test hook)
 };
 
-constexpr int CH_THREADS = 384;
+constexpr int CH_NWG = 4;                           // epilogue warpgroups (thread = TMEM lane = row; a warpgroup owns 64 of the 256 columns in E_A)
+constexpr int CH_THREADS = 128 + 128 * CH_NWG;
 constexpr int CH_NS = 11;                          // ring slots
 constexpr int CH_TILE = 16384;                     // one slot: [128 rows][128 B], SWIZZLE_128B
-constexpr int CH_STG_BYTES = 8 * 4096;             // per epilogue warp: [32][32] fp32, 16-byte units XOR-swizzled by (row & 7)
+constexpr int CH_STG_BYTES = 4 * CH_NWG * 2048;    // per epilogue warp: [32 rows][16 cols] fp32, 16-byte unit q of row r stored at q ^ ((r >> 1) & 3)
 // parameter block (floats): bias0[256] | film[2 samples][scale 256 | shift 256] | ln_w[256] | ln_b[256] | bias1[1024] | bias2[256]
 constexpr int CH_PB_BIAS0 = 0, CH_PB_FILM = 256, CH_PB_LNW = 1280, CH_PB_LNB = 1536, CH_PB_BIAS1 = 1792, CH_PB_BIAS2 = 2816;
 constexpr int CH_PB_FLOATS = 3072;
-constexpr int CH_RED_BYTES = 1024;                 // [2 warpgroups][128 rows] fp32
+constexpr int CH_RED_BYTES = CH_NWG * 512;          // [warpgroups][128 rows] fp32
 constexpr int CH_SMEM_BYTES = CH_NS * CH_TILE + CH_STG_BYTES + CH_PB_FLOATS * 4 + CH_RED_BYTES + 512 + 1024;
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
@@ -81,6 +82,19 @@ __device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t* r) {
       ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
         "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8u(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -247,13 +261,12 @@ template <int CL>
 __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, int seq_x, int seq_tab) {
   const int rx = c.trow & 7;
 #pragma unroll 1
-  for (int cc = 0; cc < 4; ++cc) {
-    const int ch = c.wg * 4 + cc;
+  for (int cc = 0; cc < 8 / CH_NWG; ++cc) {
+    const int ch = c.wg * (8 / CH_NWG) + cc;
     float v[32];
-    int sx = -1, st = -1;
     if (seq_x >= 0) {
-      const int qx = seq_x + cc * 2 + c.wg;
-      sx = qx % CH_NS;
+      const int qx = seq_x + cc * CH_NWG + c.wg;
+      const int sx = qx % CH_NS;
       umma::mbar_wait(&c.s_full[sx], (qx / CH_NS) & 1);
       const uint32_t srow = c.slots_u32 + sx * CH_TILE + c.row_off;
 #pragma unroll
@@ -265,22 +278,26 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
       umma::tmem_ld32(c.tmem_row + ch * 32, v);
       umma::tmem_ld_wait();
     }
-    // all shared-memory loads of a stage are issued before its first dependent instruction (volatile asm keeps program order)
+    // the shared-memory loads of a group are issued before its first dependent instruction (volatile asm keeps program order)
     if (c.ln_mode) {
       const uint32_t pw_ = c.pb_u32 + (CH_PB_LNW + ch * 32) * 4, pb_ = c.pb_u32 + (CH_PB_LNB + ch * 32) * 4;
-      float4 ww[8], bb[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { ww[u] = lds128(pw_ + u * 16); bb[u] = lds128(pb_ + u * 16); }
+      for (int hf = 0; hf < 2; ++hf) {
+        float4 ww[4], bb[4];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const f2 h01 = fma2(mul2(add2(f2{v[4 * u], v[4 * u + 1]}, bc2(-c.mean)), bc2(c.rstd)), f2{ww[u].x, ww[u].y}, f2{bb[u].x, bb[u].y});
-        const f2 h23 = fma2(mul2(add2(f2{v[4 * u + 2], v[4 * u + 3]}, bc2(-c.mean)), bc2(c.rstd)), f2{ww[u].z, ww[u].w}, f2{bb[u].z, bb[u].w});
-        v[4 * u] = h01.x; v[4 * u + 1] = h01.y; v[4 * u + 2] = h23.x; v[4 * u + 3] = h23.y;
+        for (int k = 0; k < 4; ++k) { ww[k] = lds128(pw_ + (hf * 4 + k) * 16); bb[k] = lds128(pb_ + (hf * 4 + k) * 16); }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int u = hf * 4 + k;
+          const f2 h01 = fma2(mul2(add2(f2{v[4 * u], v[4 * u + 1]}, bc2(-c.mean)), bc2(c.rstd)), f2{ww[k].x, ww[k].y}, f2{bb[k].x, bb[k].y});
+          const f2 h23 = fma2(mul2(add2(f2{v[4 * u + 2], v[4 * u + 3]}, bc2(-c.mean)), bc2(c.rstd)), f2{ww[k].z, ww[k].w}, f2{bb[k].z, bb[k].w});
+          v[4 * u] = h01.x; v[4 * u + 1] = h01.y; v[4 * u + 2] = h23.x; v[4 * u + 3] = h23.y;
+        }
       }
     }
     if (rot) {
-      const int qt = seq_tab + cc * 2 + c.wg;
-      st = qt % CH_NS;
+      const int qt = seq_tab + cc * CH_NWG + c.wg;
+      const int st = qt % CH_NS;
       umma::mbar_wait(&c.s_full[st], (qt / CH_NS) & 1);
       const uint32_t trw = c.slots_u32 + st * CH_TILE + c.row_off;
       float4 cs[8];
@@ -294,19 +311,22 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
         v[4 * u] = r01.x; v[4 * u + 1] = r01.y; v[4 * u + 2] = r23.x; v[4 * u + 3] = r23.y;
       }
     }
-    uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int e = 0; e < 16; ++e) split_act_pair(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
-    tmem_st16u(c.tmem_row + ch * 32, hi);
-    tmem_st16u(c.tmem_row + ch * 32 + 16, lo);
+    for (int hf = 0; hf < 2; ++hf) {     // 8 pairs at a time: 8 + 8 packed registers live
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_act_pair(v[hf * 16 + 2 * e], v[hf * 16 + 2 * e + 1], hi[e], lo[e]);
+      tmem_st8u(c.tmem_row + ch * 32 + hf * 8, hi);
+      tmem_st8u(c.tmem_row + ch * 32 + 16 + hf * 8, lo);
+    }
   }
-  if (seq_x >= 0 || rot) {          // release the slots this warpgroup has finished reading (one barrier for all four chunks)
+  if (seq_x >= 0 || rot) {          // release the slots this warpgroup has finished reading (one barrier for its chunks)
     asm volatile("bar.sync %0, 128;" ::"r"(2 + c.wg) : "memory");
     if (c.trow == 0) {
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        if (seq_x >= 0) slot_release<CL>(&c.s_empty[(seq_x + cc * 2 + c.wg) % CH_NS], c.peer);
-        if (rot) slot_release<CL>(&c.s_empty[(seq_tab + cc * 2 + c.wg) % CH_NS], c.peer);
+      for (int cc = 0; cc < 8 / CH_NWG; ++cc) {
+        if (seq_x >= 0) slot_release<CL>(&c.s_empty[(seq_x + cc * CH_NWG + c.wg) % CH_NS], c.peer);
+        if (rot) slot_release<CL>(&c.s_empty[(seq_tab + cc * CH_NWG + c.wg) % CH_NS], c.peer);
       }
     }
   }
@@ -337,8 +357,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* a_reads_done = bars + 28;
   uint64_t* a2_ready = bars + 29;      // 256 arrivals
   uint64_t* x_stored = bars + 30;      // the x tile written by E_A is globally visible (store warp)
-  uint64_t* x_written = bars + 31;     // [2] 128 arrivals each: warpgroup w has written its four x chunks into the staging slots
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
+  uint64_t* x_written = bars + 31;     // [CH_NWG] 128 arrivals each: warpgroup w has written its x chunks into the staging slots
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31 + CH_NWG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -360,10 +380,10 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], CL); }
-    umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 256);
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 128); }
-    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 256); umma::mbar_init(x_stored, 1);
-    umma::mbar_init(&x_written[0], 128); umma::mbar_init(&x_written[1], 128);
+    umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 128 * CH_NWG);
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 64 * CH_NWG); }
+    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 128 * CH_NWG); umma::mbar_init(x_stored, 1);
+    for (int i = 0; i < CH_NWG; ++i) umma::mbar_init(&x_written[i], 128);
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
@@ -408,11 +428,11 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     CH_TRACE(24, lane == 0);
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) issue(&tmX, p.film_mode ? 1 : 2, ((j & 1) * 4 + (j >> 1)) * 32, m0, 0);
+    for (int j = 0; j < 8; ++j) issue(&tmX, p.film_mode ? 1 : 2, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0, 0);
     if (p.rope) {
       const int tab_row = m0 % p.T;
 #pragma unroll 1
-      for (int j = 0; j < 8; ++j) issue(&tmTab, 1, ((j & 1) * 4 + (j >> 1)) * 32, tab_row, 0);
+      for (int j = 0; j < 8; ++j) issue(&tmTab, 1, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, tab_row, 0);
     }
     CH_TRACE(25, lane == 0);
 #pragma unroll 1
@@ -421,7 +441,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (p.vjob) {
       umma::mbar_wait(x_stored, 0);   // the x tile written by E_A is globally visible
 #pragma unroll 1
-      for (int j = 0; j < 8; ++j) issue(&tmX, 1, ((j & 1) * 4 + (j >> 1)) * 32, m0, 0);
+      for (int j = 0; j < 8; ++j) issue(&tmX, 1, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0, 0);
 #pragma unroll 1
       for (int j = 0; j < 16; ++j) issue(&tmW2, KW, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
     }
@@ -516,13 +536,13 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else if (warp == 3) {
     // ================= store warp: x tile -> global by TMA, then hand the staging slots back =================
     if (lane == 0) {
-      umma::mbar_wait(&x_written[0], 0);
-      umma::mbar_wait(&x_written[1], 0);
+#pragma unroll 1
+      for (int g = 0; g < CH_NWG; ++g) umma::mbar_wait(&x_written[g], 0);
       // one bulk group per chunk, in ring order, so that each staging slot goes back to the producer as soon as ITS store
       // has read it (the RoPE-table chunks of pass 3 are waiting for these slots)
 #pragma unroll 1
       for (int j = 0; j < 8; ++j) {
-        tma_store_2d(&tmX, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, ((j & 1) * 4 + (j >> 1)) * 32, m0);
+        tma_store_2d(&tmX, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0);
         bulk_commit();
       }
       bulk_wait_read<7>(); slot_release<CL>(&s_empty[(seqEA + 0) % CH_NS], peer);
@@ -538,41 +558,41 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     __syncwarp();
   } else if (warp >= 4) {
-    // ================= epilogue warpgroups =================
+    // ================= epilogue warpgroups (CH_NWG x 4 warps; thread = TMEM lane = row) =================
+    constexpr int NCH = 8 / CH_NWG;                        // 32-column chunks per warpgroup in E_A
     const int wg = (warp - 4) >> 2;
     const int wq = warp & 3;
     const int trow = wq * 32 + lane;                       // row inside the tile == TMEM lane
-    const int et = threadIdx.x - 128;                      // 0..255
+    const int et = threadIdx.x - 128;                      // 0 .. 128 * CH_NWG - 1
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
-    float* stg = sStg + (warp - 4) * 1024;
-    const int rsub = lane >> 3, uq = lane & 7;
+    const uint32_t stg_u32 = umma::smem_u32(sStg) + (warp - 4) * 2048;   // this warp's [32][16] fp32 staging tile
     const uint32_t row_off = trow * 128;                   // byte offset of this thread's row inside a slot
     const int rx = trow & 7;
     const uint32_t pb_u32 = umma::smem_u32(sPB);
     const int grow_own = m0 + trow;
     const int s_first = m0 / p.T;
     const int sl = grow_own / p.T - s_first;               // 0 or 1 (T >= 128)
-    auto wg_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory"); };
+    constexpr int NE = 128 * CH_NWG;
 
     // ---------------- parameter block -> shared memory (hidden behind GEMM0)
     {
-      for (int i = et; i < 256; i += 256) {
+      for (int i = et; i < 256; i += NE) {
         sPB[CH_PB_BIAS0 + i] = p.bias0 ? __ldg(p.bias0 + i) : 0.f;
         sPB[CH_PB_LNW + i] = p.ln_mode ? __ldg(p.ln_w + i) : 1.f;
         sPB[CH_PB_LNB + i] = p.ln_mode ? __ldg(p.ln_b + i) : 0.f;
         sPB[CH_PB_BIAS2 + i] = (p.vjob && p.bias2) ? __ldg(p.bias2 + i) : 0.f;
       }
-      for (int i = et; i < 1024; i += 256) sPB[CH_PB_BIAS1 + i] = (p.bias1 && i < p.N1) ? __ldg(p.bias1 + i) : 0.f;
+      for (int i = et; i < 1024; i += NE) sPB[CH_PB_BIAS1 + i] = (p.bias1 && i < p.N1) ? __ldg(p.bias1 + i) : 0.f;
       if (p.film_mode) {
         const int n_samp = (p.M + p.T - 1) / p.T;
-        for (int i = et; i < 1024; i += 256) {
+        for (int i = et; i < 1024; i += NE) {
           const int s = i >> 9, j = i & 511;                // sample-local index, [scale 256 | shift 256]
           const int smp = ::min(s_first + s, n_samp - 1);
           const float* fs = p.film + (long long)smp * p.film_ld;
           sPB[CH_PB_FILM + i] = __ldg(fs + (j < 256 ? p.film_scale_off + j : p.film_shift_off + (j - 256)));
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NE) : "memory");
     }
     CH_TRACE(1, et == 0);
 
@@ -582,9 +602,9 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     CH_TRACE(2, et == 0);
     float sum = 0.f;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
-      const int c = wg * 4 + cc;
-      const int qx = seqEA + cc * 2 + wg;
+    for (int cc = 0; cc < NCH; ++cc) {
+      const int c = wg * NCH + cc;
+      const int qx = seqEA + cc * CH_NWG + wg;
       const int sx = qx % CH_NS;
       float v[32];
       umma::tmem_ld32(tmem_base + lane_addr + c * 32, v);
@@ -593,36 +613,30 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const uint32_t srow = slots_u32 + sx * CH_TILE + row_off;
       const uint32_t pbc = pb_u32 + (CH_PB_BIAS0 + c * 32) * 4;
       const uint32_t pfs = pb_u32 + (CH_PB_FILM + sl * 512 + c * 32) * 4;
-      // 16 columns at a time: ALL shared-memory loads of the group are issued before the first dependent instruction
-      // (the loads / stores are volatile asm and keep program order: interleaving them per 4 columns serialised eight
-      // load-latency bubbles per chunk)
+      // 8 columns at a time: all shared-memory loads of the group are issued before the first dependent instruction
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        float4 bb[4], xo[4], sc[4], sh[4];
+      for (int gq = 0; gq < 4; ++gq) {
+        float4 bb[2], xo[2], sc[2], sh[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) bb[k] = lds128(pbc + (hf * 4 + k) * 16);
+        for (int k = 0; k < 2; ++k) bb[k] = lds128(pbc + (gq * 2 + k) * 16);
         if (p.film_mode) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            xo[k] = lds128(srow + (((hf * 4 + k) ^ rx) << 4));
-            sc[k] = lds128(pfs + (hf * 4 + k) * 16);
-            sh[k] = lds128(pfs + 1024 + (hf * 4 + k) * 16);
+          for (int k = 0; k < 2; ++k) {
+            xo[k] = lds128(srow + (((gq * 2 + k) ^ rx) << 4));
+            sc[k] = lds128(pfs + (gq * 2 + k) * 16);
+            sh[k] = lds128(pfs + 1024 + (gq * 2 + k) * 16);
           }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int u = hf * 4 + k;
+        for (int k = 0; k < 2; ++k) {
+          const int u = gq * 2 + k;
           f2 o01 = add2(f2{v[4 * u], v[4 * u + 1]}, f2{bb[k].x, bb[k].y}), o23 = add2(f2{v[4 * u + 2], v[4 * u + 3]}, f2{bb[k].z, bb[k].w});
           if (p.film_mode) {   // x + ((scale + 1) * (acc + b) + shift), same operation order as the unfused epilogue
             o01 = add2(f2{xo[k].x, xo[k].y}, fma2(add2(f2{sc[k].x, sc[k].y}, bc2(1.f)), o01, f2{sh[k].x, sh[k].y}));
             o23 = add2(f2{xo[k].z, xo[k].w}, fma2(add2(f2{sc[k].z, sc[k].w}, bc2(1.f)), o23, f2{sh[k].z, sh[k].w}));
           }
           v[4 * u] = o01.x; v[4 * u + 1] = o01.y; v[4 * u + 2] = o23.x; v[4 * u + 3] = o23.y;
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int u = hf * 4 + k;
-          sts128(srow + ((u ^ rx) << 4), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+          sts128(srow + ((u ^ rx) << 4), make_float4(o01.x, o01.y, o23.x, o23.y));
         }
       }
       float s4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -637,25 +651,31 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     umma::mbar_arrive(&x_written[wg]);
     tmem_st_wait();
     CH_TRACE(3, et == 0);
-    // ---------------- row statistics (two-pass LayerNorm; the two warpgroups own 128 columns each)
+    // ---------------- row statistics (two-pass LayerNorm; every warpgroup owns 256 / CH_NWG columns)
     float mean = 0.f, rstd = 1.f;
     if (p.ln_mode) {
       sRed[wg * 128 + trow] = sum;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      mean = (sRed[trow] + sRed[128 + trow]) / 256.f;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NE) : "memory");
+      float tot = 0.f;
+#pragma unroll
+      for (int g = 0; g < CH_NWG; ++g) tot += sRed[g * 128 + trow];
+      mean = tot / 256.f;
+      asm volatile("bar.sync 1, %0;" ::"n"(NE) : "memory");
       float qs = 0.f;
 #pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
+      for (int cc = 0; cc < NCH; ++cc) {
         float v[32];
-        umma::tmem_ld32(tmem_base + lane_addr + (wg * 4 + cc) * 32, v);
+        umma::tmem_ld32(tmem_base + lane_addr + (wg * NCH + cc) * 32, v);
         umma::tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) { const float d_ = v[j] - mean; qs += d_ * d_; }
       }
       sRed[wg * 128 + trow] = qs;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-      rstd = rsqrtf((sRed[trow] + sRed[128 + trow]) / 256.f + 1e-5f);
+      asm volatile("bar.sync 1, %0;" ::"n"(NE) : "memory");
+      tot = 0.f;
+#pragma unroll
+      for (int g = 0; g < CH_NWG; ++g) tot += sRed[g * 128 + trow];
+      rstd = rsqrtf(tot / 256.f + 1e-5f);
     }
     CH_TRACE(4, et == 0);
     ChainEpiCtx ectx{tmem_base + lane_addr, slots_u32, row_off, pb_u32, s_full, s_empty, wg, trow, p.ln_mode, mean, rstd, peer};
@@ -663,10 +683,13 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     umma::mbar_arrive(a_ready);
     CH_TRACE(5, et == 0);
 
-    // ---------------- E_B: this warpgroup drains accumulator halves h = wg, wg + 2, ...
+    // ---------------- E_B: accumulator half h is drained by the warpgroup PAIR (h & 1): warpgroup `sub` of the pair takes 64 of
+    //                  its 128 columns (four 16-column chunks through this warp's staging tile)
+    const int pair = wg >> 1, sub = wg & 1;
+    const int r8 = lane >> 2, u4 = lane & 3;               // transposed phase: lane -> (row sub-index, 16-byte unit)
     bool vprep_done = false;
 #pragma unroll 1
-    for (int h = wg; h < n_acc; h += 2) {
+    for (int h = pair; h < n_acc; h += 2) {
       const bool vj = h >= NH1;
       if (vj && !vprep_done) {
         umma::mbar_wait(a_reads_done, 0);    // every GEMM1 MMA has read the rotated planes
@@ -679,32 +702,32 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       umma::mbar_wait(&acc1_full[buf], (h >> 1) & 1);
       umma::fence_after();
       CH_TRACE(6 + h, et == 0 && h < 10);
+      const int remap_first = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_pad : 0;   // pad rows in front of the tile's first sample
+      const int remap_edge = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_rps : 0x7fffffff;   // first row of the next sample (T >= 128)
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int k = 0; k < 4; ++k) {
+        const int c16 = sub * 4 + k;                       // 16-column chunk of the half
         {
-          float v[32];
-          umma::tmem_ld32(tmem_base + lane_addr + 256 + buf * 128 + c * 32, v);
+          float v[16];
+          tmem_ld16(tmem_base + lane_addr + 256 + buf * 128 + c16 * 16, v);
           umma::tmem_ld_wait();
-          if (c == 3) { umma::fence_before(); umma::mbar_arrive(&acc1_empty[buf]); }
-          const uint32_t stg_row = umma::smem_u32(stg) + lane * 128;
+          if (k == 3) { umma::fence_before(); umma::mbar_arrive(&acc1_empty[buf]); }
+          const uint32_t srow = stg_u32 + lane * 64;
 #pragma unroll
-          for (int q = 0; q < 8; ++q)
-            sts128(stg_row + ((q ^ (lane & 7)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          for (int q = 0; q < 4; ++q)
+            sts128(srow + ((q ^ ((lane >> 1) & 3)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
         }
         __syncwarp();
         if (!vj) {
-          // rows = tokens, columns = output features: 4 rows x 128 B per warp instruction
-          const int col = h * 128 + c * 32 + uq * 4;
+          // rows = tokens, columns = output features: 8 rows x 64 B per warp instruction
+          const int col = h * 128 + c16 * 16 + u4 * 4;
           const bool col_ok = col < p.N1;
           const float4 bb = lds128(pb_u32 + (CH_PB_BIAS1 + (col_ok ? col : 0)) * 4);
           const float osc = (p.scale_ncols != 0 && col >= p.scale_ncols) ? 1.f : p.out_scale;
-          const uint32_t stg_u32 = umma::smem_u32(stg);
-          const int remap_first = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_pad : 0;   // pad rows in front of the tile's first sample
-          const int remap_edge = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_rps : 0x7fffffff;   // first row of the next sample (T >= 128: at most one boundary per tile)
 #pragma unroll 2
-          for (int it = 0; it < 8; ++it) {
-            const int r = it * 4 + rsub;
-            const float4 a = lds128(stg_u32 + ((r * 32 + ((uq ^ (r & 7)) << 2)) << 2));
+          for (int it = 0; it < 4; ++it) {
+            const int r = it * 8 + r8;
+            const float4 a = lds128(stg_u32 + r * 64 + ((u4 ^ ((r >> 1) & 3)) << 4));
             f2 o01 = add2(f2{a.x, a.y}, f2{bb.x, bb.y}), o23 = add2(f2{a.z, a.w}, f2{bb.z, bb.w});
             const int grow = m0 + wq * 32 + r;
             if (p.gelu) {
@@ -722,20 +745,23 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             *reinterpret_cast<uint2*>(dst + p.cp_plane_stride) = make_uint2(l0, l1);
           }
         } else {
-          // V job: the accumulator is V[tokens, channels]; store V^T: lane = channel, 32 consecutive tokens = 64 B per plane
-          const int ch = (h - NH1) * 128 + c * 32 + lane;
+          // V job: the accumulator is V[tokens, channels]; store V^T: lane = (channel, token half), 16 consecutive tokens = 32 B per plane
+          const int chl = lane & 15, th = lane >> 4;
+          const int ch = (h - NH1) * 128 + c16 * 16 + chl;
           const float b2 = lds32(pb_u32 + (CH_PB_BIAS2 + ch) * 4);
-          const uint32_t stg_u32 = umma::smem_u32(stg);
-          float t[32];
+          float t[16];
 #pragma unroll
-          for (int r = 0; r < 32; ++r) t[r] = lds32(stg_u32 + ((r * 32 + (((lane >> 2) ^ (r & 7)) << 2) + (lane & 3)) << 2)) + b2;
-          const int tok0 = m0 + wq * 32;
-          uint32_t hi[16], lo[16];
+          for (int j = 0; j < 16; ++j) {
+            const int r = th * 16 + j;
+            t[j] = lds32(stg_u32 + r * 64 + ((((chl >> 2) ^ ((r >> 1) & 3)) << 4) | ((chl & 3) << 2))) + b2;
+          }
+          const int tok0 = m0 + wq * 32 + th * 16;
+          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int e = 0; e < 16; ++e) split_act_pair(t[2 * e], t[2 * e + 1], hi[e], lo[e]);
+          for (int e = 0; e < 8; ++e) split_act_pair(t[2 * e], t[2 * e + 1], hi[e], lo[e]);
           __nv_bfloat16* dst = p.Vt + (long long)ch * p.ldvt + tok0;
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < 2; ++u) {
             if (tok0 + 8 * u < p.M) {   // M % 8 == 0 (checked by the launcher)
               *reinterpret_cast<uint4*>(dst + 8 * u) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
               *reinterpret_cast<uint4*>(dst + p.vt_plane_stride + 8 * u) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
