@@ -65,14 +65,27 @@ inline bool pdl_enabled() {
   return v == 1;
 }
 
+// Scheduling priority of the NEXT launch_pdl() launches (0 = the stream's own).  When two forwards run as concurrent
+// streams, pending CTAs of a higher-priority kernel are placed before pending CTAs of a lower-priority one.
+inline int& launch_priority() { static int v = 0; return v; }
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (launch_priority() != 0) {
+    attr[n].id = cudaLaunchAttributePriority;
+    attr[n].val.priority = launch_priority();
+    ++n;
+  }
+  cfg.attrs = attr; cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

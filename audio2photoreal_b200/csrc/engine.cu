@@ -84,8 +84,13 @@ struct a2p_denoiser {
   int64_t graph_nodes = 0;
   cudaGraphExec_t gexec = nullptr;
   cudaStream_t cap_stream = nullptr;  // private stream used only to CAPTURE a step (the legacy default stream cannot capture)
-  cudaStream_t cond_stream = nullptr; // side stream: the per-step conditioning chain runs beside the first chain / self-attention launches
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // side streams (one per concurrently running forward): the per-step conditioning chain runs beside the first chain /
+  // self-attention launches
+  cudaStream_t cond_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
+  // CFG sampling loop: the unconditional forward runs on its own stream beside the conditional one (see sample_loop_impl)
+  cudaStream_t branch_stream = nullptr;
+  cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
   GraphKey gkey{};
   bool gvalid = false;
 };
@@ -258,7 +263,14 @@ struct Ctx {
   Prof* prof = nullptr;
   int cat = CAT_MISC;
   bool skinny = false;   // route the next FFMA GEMMs to the warp-per-column kernel (per-step conditioning linears)
+  int slot = 0;          // which set of side streams / events of the handle this forward uses
+  cudaEvent_t stagger_ev = nullptr;   // recorded after the stagger_after-th chain / attention launch of the fused arm
+  int stagger_after = 0, n_main = 0;
   std::string tag;
+  int mark() {           // one more chain / attention launch is in the stream
+    if (stagger_ev && ++n_main == stagger_after) { A2P_CUDA(cudaEventRecord(stagger_ev, st)); stagger_ev = nullptr; }
+    return 0;
+  }
   void begin() {
     if (!prof) return;
     cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); prof->ev.push_back(e); prof->cat.push_back(cat);
@@ -340,6 +352,27 @@ int attn2_variant() {
   return v;
 }
 
+// CFG sampling: run the conditional and the unconditional forward as two concurrent streams of launches (env
+// A2P_NO_BRANCH_STREAMS=1 keeps the single stacked forward).  A2P_BRANCH_STAGGER=n starts the unconditional forward after
+// the n-th chain / attention launch of the conditional one, so that one branch's 1-CTA-per-tile chain kernels (which
+// leave half of the SMs idle at small batches) overlap the other branch's attention kernels.
+bool branch_streams_disabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("A2P_NO_BRANCH_STREAMS") ? 1 : 0;
+  return v == 1;
+}
+int branch_stagger() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A2P_BRANCH_STAGGER"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
+  return v;
+}
+
+int chain_priority() {   // A2P_CHAIN_PRIO=p: launch priority of the chain kernels (negative = higher than the attention kernels)
+  static int v = 1 << 30;
+  if (v == (1 << 30)) { const char* e = getenv("A2P_CHAIN_PRIO"); v = e ? atoi(e) : 0; }
+  return v;
+}
+
 bool chain_disabled() {
   static int v = -1;
   if (v < 0) v = getenv("A2P_NO_CHAIN") ? 1 : 0;
@@ -398,13 +431,14 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   const bool side = chain_arm && !c.prof && !getenv("A2P_NO_SIDE_STREAM");
   cudaStream_t st_main = st;
   if (side) {
-    if (!h->cond_stream) A2P_CUDA(cudaStreamCreateWithFlags(&h->cond_stream, cudaStreamNonBlocking));
-    if (!h->ev_fork) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-    if (!h->ev_join) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
-    A2P_CUDA(cudaEventRecord(h->ev_fork, st_main));
-    A2P_CUDA(cudaStreamWaitEvent(h->cond_stream, h->ev_fork, 0));
-    st = h->cond_stream; c.st = st;
+    if (!h->cond_stream[c.slot]) A2P_CUDA(cudaStreamCreateWithFlags(&h->cond_stream[c.slot], cudaStreamNonBlocking));
+    if (!h->ev_fork[c.slot]) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_fork[c.slot], cudaEventDisableTiming));
+    if (!h->ev_join[c.slot]) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_join[c.slot], cudaEventDisableTiming));
+    A2P_CUDA(cudaEventRecord(h->ev_fork[c.slot], st_main));
+    A2P_CUDA(cudaStreamWaitEvent(h->cond_stream[c.slot], h->ev_fork[c.slot], 0));
+    st = h->cond_stream[c.slot]; c.st = st;
   }
+  cudaStream_t st_side = side ? h->cond_stream[c.slot] : st_main;
   c.cat = CAT_COND;
   c.skinny = true;
   time_embed_kernel<<<ceil_div(R * D / 2, 256), 256, 0, st>>>(ts, counter, B, R, D, h->time_freqs, e);
@@ -461,7 +495,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   const long long MT8 = (long long)align_up((size_t)MT, 8);
   const long long XP = 8LL * R;   // time-token V^T: 8 columns per sample (TMA needs 16-byte aligned box starts), 2 used
   if (tc_attn) {
-    if (side) { st = h->cond_stream; c.st = st; }
+    if (side) { st = st_side; c.st = st; }
     c.cat = CAT_COND;
     c.begin();
     A2P_TRY(launch_split_planes(P, ktt, (long long)L * D, kttP, (long long)2 * R * L * D, 2 * R, L * D, 1.f, st));
@@ -470,7 +504,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     c.end();
     h->launches += 3;
     if (side) {
-      A2P_CUDA(cudaEventRecord(h->ev_join, h->cond_stream));
+      A2P_CUDA(cudaEventRecord(h->ev_join[c.slot], st_side));
       st = st_main; c.st = st_main;
     }
   }
@@ -518,6 +552,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     c.end();
     c.cat = CAT_PROJ;
     h->launches++;
+    if (rc == 0) rc = c.mark();
     return rc;
   };
   // ===== fused row-chain arm (split_terms == 2, D == 256): per layer 4 chain launches + 3 attention launches =====
@@ -555,9 +590,12 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       c.cat = cat;
       if (c.prof) c.tag = tag;
       c.begin();
+      launch_priority() = chain_priority();
       int rc = launch_umma_chain(o, cp, st);
+      launch_priority() = 0;
       c.end();
       h->launches++;
+      if (rc == 0) rc = c.mark();
       return rc;
     };
     auto next_self = [&](int l) {   // LN1 + RoPE -> Q|K planes (Q pre-scaled), un-rotated LN1 -> V^T planes
@@ -579,7 +617,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       const LayerW& lw = h->lw[l];
       const int fo = l * nf * 2 * D;
       A2P_TRY(attn_tc(l, 0));
-      if (l == 0 && side) A2P_CUDA(cudaStreamWaitEvent(st, h->ev_join, 0));   // FiLM table + time-token K/V rows are ready
+      if (l == 0 && side) A2P_CUDA(cudaStreamWaitEvent(st, h->ev_join[c.slot], 0));   // FiLM table + time-token K/V rows are ready
       A2P_TRY(run_chain(CAT_PROJ, "chain sa_out->ln2->q", attP, MT, D, lw.sa.out_w, lw.sa.out_b, fo + 0 * 2 * D, next_q(lw.n2w, lw.n2b, lw.ca)));
       A2P_TRY(attn_tc(l, 1));
       const AttnW* last = &lw.ca;
@@ -902,9 +940,14 @@ void a2p_denoiser_destroy(a2p_denoiser_t* h) {
   if (!h) return;
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
-  if (h->cond_stream) cudaStreamDestroy(h->cond_stream);
-  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
-  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (int i = 0; i < 2; ++i) {
+    if (h->cond_stream[i]) cudaStreamDestroy(h->cond_stream[i]);
+    if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
+    if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+  }
+  if (h->branch_stream) cudaStreamDestroy(h->branch_stream);
+  if (h->ev_bfork) cudaEventDestroy(h->ev_bfork);
+  if (h->ev_bjoin) cudaEventDestroy(h->ev_bjoin);
   delete h;
 }
 
@@ -1044,7 +1087,9 @@ size_t a2p_conditioning_workspace_bytes(const a2p_model_cfg* cfg, int Bc, int S)
 
 size_t a2p_workspace_bytes(const a2p_model_cfg* cfg, int B, int T) {
   if (check_cfg(cfg) || B <= 0 || T <= 0) return 0;
-  return ws_layout(*cfg, B, T).total;
+  const size_t one = ws_layout(*cfg, B, T).total;
+  // the fused arm runs the two CFG branches of a sampling step as concurrent forwards, each in its own workspace region
+  return (cfg->split_terms == 2 && cfg->D == 256) ? 2 * align_up(one, 1024) : one;
 }
 
 int a2p_denoiser_set_conditioning(a2p_denoiser_t* h, int branch, int Bc, int S, int S2, const float* cond_tokens,
@@ -1183,11 +1228,37 @@ static int sample_loop_impl(a2p_denoiser_t* h, int kind, int B, int T, int n_ste
   int* counter = reinterpret_cast<int*>(wsb + w.counter);
   float* xin = reinterpret_cast<float*>(wsb + w.xin);
 
+  const size_t region = align_up(w.total, 1024);
+  const bool dual = branch_mask == A2P_MASK_BOTH && cf.split_terms == 2 && cf.D == 256 && (T % 8 == 0) && T >= 128 &&
+                    !chain_disabled() && !branch_streams_disabled() && ws_bytes >= 2 * region;
   auto step_body = [&]() -> int {
     A2P_TRY(transpose_in(c, x, xin, B, cf.C, T));
     const float *x0c = nullptr, *x0u = nullptr;
     long long sstride = 0;
-    A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, counter, branch_mask, wsb, &x0c, &x0u, &sstride));
+    if (dual) {
+      // two independent forwards (no op mixes batch rows): conditional on the caller's stream, unconditional on a second
+      // stream that forks from it (inside a capture: a parallel branch of the graph) and joins before the sampler update
+      if (!h->branch_stream) A2P_CUDA(cudaStreamCreateWithFlags(&h->branch_stream, cudaStreamNonBlocking));
+      if (!h->ev_bfork) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_bfork, cudaEventDisableTiming));
+      if (!h->ev_bjoin) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_bjoin, cudaEventDisableTiming));
+      const float* dummy = nullptr;
+      long long ss2 = 0;
+      Ctx ca{h, c.st};
+      ca.slot = 0;
+      const int stag = branch_stagger();
+      if (stag == 0) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));
+      else { ca.stagger_ev = h->ev_bfork; ca.stagger_after = stag; }
+      A2P_TRY(forward_core(ca, B, T, xin, (const long long*)timesteps, counter, A2P_MASK_COND, wsb, &x0c, &dummy, &sstride));
+      if (ca.stagger_ev) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));   // fewer launches than the stagger asked for
+      A2P_CUDA(cudaStreamWaitEvent(h->branch_stream, h->ev_bfork, 0));
+      Ctx cb{h, h->branch_stream};
+      cb.slot = 1;
+      A2P_TRY(forward_core(cb, B, T, xin, (const long long*)timesteps, counter, A2P_MASK_UNCOND, wsb + region, &dummy, &x0u, &ss2));
+      A2P_CUDA(cudaEventRecord(h->ev_bjoin, h->branch_stream));
+      A2P_CUDA(cudaStreamWaitEvent(c.st, h->ev_bjoin, 0));
+    } else {
+      A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, counter, branch_mask, wsb, &x0c, &x0u, &sstride));
+    }
     K3Params p{};
     p.x_t = x; p.x0c = x0c; p.x0u = x0u; p.scale = scale; p.coeffs = coeffs; p.step_counter = counter;
     p.noise = noise_tape; p.noise_step_stride = (long long)B * cf.C * T; p.n_steps = n_steps;

@@ -357,8 +357,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* a_reads_done = bars + 28;
   uint64_t* a2_ready = bars + 29;      // 256 arrivals
   uint64_t* x_stored = bars + 30;      // the x tile written by E_A is globally visible (store warp)
-  uint64_t* x_written = bars + 31;     // [CH_NWG] 128 arrivals each: warpgroup w has written its x chunks into the staging slots
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31 + CH_NWG);
+  uint64_t* x_written = bars + 31;     // [8] 128 arrivals each: x chunk at ring position seqEA + j is in its staging slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31 + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -383,7 +383,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 128 * CH_NWG);
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 64 * CH_NWG); }
     umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 128 * CH_NWG); umma::mbar_init(x_stored, 1);
-    for (int i = 0; i < CH_NWG; ++i) umma::mbar_init(&x_written[i], 128);
+    for (int i = 0; i < 8; ++i) umma::mbar_init(&x_written[i], 128);
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
@@ -536,23 +536,24 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   } else if (warp == 3) {
     // ================= store warp: x tile -> global by TMA, then hand the staging slots back =================
     if (lane == 0) {
+      // one bulk group per chunk, in ring order; a round of CH_NWG chunks (one per warpgroup) is stored and its staging
+      // slots handed back to the producer while the warpgroups are still working on the next round (the RoPE-table
+      // chunks of pass 3 are waiting for these slots)
 #pragma unroll 1
-      for (int g = 0; g < CH_NWG; ++g) umma::mbar_wait(&x_written[g], 0);
-      // one bulk group per chunk, in ring order, so that each staging slot goes back to the producer as soon as ITS store
-      // has read it (the RoPE-table chunks of pass 3 are waiting for these slots)
+      for (int r = 0; r < 8 / CH_NWG; ++r) {
 #pragma unroll 1
-      for (int j = 0; j < 8; ++j) {
-        tma_store_2d(&tmX, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0);
-        bulk_commit();
+        for (int g = 0; g < CH_NWG; ++g) {
+          const int j = r * CH_NWG + g;
+          umma::mbar_wait(&x_written[j], 0);
+          tma_store_2d(&tmX, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, (g * (8 / CH_NWG) + r) * 32, m0);
+          bulk_commit();
+        }
+        static_assert(CH_NWG == 4, "staggered waits below assume 4 stores per round");
+        bulk_wait_read<3>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 0) % CH_NS], peer);
+        bulk_wait_read<2>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 1) % CH_NS], peer);
+        bulk_wait_read<1>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 2) % CH_NS], peer);
+        bulk_wait_read<0>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 3) % CH_NS], peer);
       }
-      bulk_wait_read<7>(); slot_release<CL>(&s_empty[(seqEA + 0) % CH_NS], peer);
-      bulk_wait_read<6>(); slot_release<CL>(&s_empty[(seqEA + 1) % CH_NS], peer);
-      bulk_wait_read<5>(); slot_release<CL>(&s_empty[(seqEA + 2) % CH_NS], peer);
-      bulk_wait_read<4>(); slot_release<CL>(&s_empty[(seqEA + 3) % CH_NS], peer);
-      bulk_wait_read<3>(); slot_release<CL>(&s_empty[(seqEA + 4) % CH_NS], peer);
-      bulk_wait_read<2>(); slot_release<CL>(&s_empty[(seqEA + 5) % CH_NS], peer);
-      bulk_wait_read<1>(); slot_release<CL>(&s_empty[(seqEA + 6) % CH_NS], peer);
-      bulk_wait_read<0>(); slot_release<CL>(&s_empty[(seqEA + 7) % CH_NS], peer);
       bulk_wait_all();           // globally visible (the V job re-reads the tile; nothing may be in flight at exit)
       if (p.vjob) umma::mbar_arrive(x_stored);
     }
@@ -644,11 +645,11 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       for (int j = 0; j < 32; ++j) s4[j & 3] += v[j];
       sum += (s4[0] + s4[1]) + (s4[2] + s4[3]);
       tmem_st32(tmem_base + lane_addr + c * 32, v);
+      // the chunk leaves by TMA store from the STORE WARP (warp 3): this thread only makes its writes visible to the async
+      // proxy and signals; waiting for the stores to drain the staging slots is nobody's critical path
+      umma::fence_proxy_async();
+      umma::mbar_arrive(&x_written[cc * CH_NWG + wg]);
     }
-    // the x tile leaves by TMA store from the STORE WARP (warp 3): this thread only makes its writes visible to the async
-    // proxy and signals; waiting for the stores to drain the staging slots is nobody's critical path
-    umma::fence_proxy_async();
-    umma::mbar_arrive(&x_written[wg]);
     tmem_st_wait();
     CH_TRACE(3, et == 0);
     // ---------------- row statistics (two-pass LayerNorm; every warpgroup owns 256 / CH_NWG columns)
