@@ -22,6 +22,7 @@
 #include "umma_attention.cuh"
 #include "umma_chain.cuh"
 #include "umma_attention2.cuh"
+#include "umma_attention_short.cuh"
 #include "umma_microbench.cuh"
 #include "../../include/a2p_b200_testing.h"
 
@@ -548,7 +549,9 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     c.cat = kind == 0 ? CAT_ATT_SELF : (kind == 1 ? CAT_ATT_CROSS : CAT_ATT_CROSS2);
     c.begin();
     const int av = attn2_variant();
-    int rc = (P == 2 && dh == 32 && av > 0) ? launch_umma_attn2(av, o, ap, st) : launch_umma_attn(P, o, ap, st);
+    int rc;
+    if (P == 2 && av > 0 && kind == 2 && attn_short_ok(ap) && !attn_short_disabled()) rc = launch_umma_attn_short(o, ap, st);
+    else rc = (P == 2 && dh == 32 && av > 0) ? launch_umma_attn2(av, o, ap, st) : launch_umma_attn(P, o, ap, st);
     c.end();
     c.cat = CAT_PROJ;
     h->launches++;
@@ -1061,6 +1064,7 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
     A2P_TRY(init_umma_attn());
     A2P_TRY(init_umma_chain());
     A2P_TRY(init_umma_attn2());
+    A2P_TRY(init_umma_attn_short());
   }
   {
     int dev = 0;
@@ -1298,7 +1302,14 @@ static int sample_loop_impl(a2p_denoiser_t* h, int kind, int B, int T, int n_ste
     h->graph_nodes = 0;
     size_t nn = 0;
     cudaGraphGetNodes(graph, nullptr, &nn);
-    h->graph_nodes = (int64_t)nn;
+    {   // count the KERNEL nodes only (memset / empty join nodes are not launches of ours)
+      std::vector<cudaGraphNode_t> nodes(nn);
+      if (nn) cudaGraphGetNodes(graph, nodes.data(), &nn);
+      for (size_t i = 0; i < nn; ++i) {
+        cudaGraphNodeType ty;
+        if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) h->graph_nodes++;
+      }
+    }
     ce = cudaGraphInstantiate(&h->gexec, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) A2P_FAIL("graph instantiate failed: %s", cudaGetErrorString(ce));
@@ -1427,6 +1438,7 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   if (terms >= 20) { variant = terms - 19; terms = 2; }
   A2P_TRY(init_umma_attn());
   A2P_TRY(init_umma_attn2());
+  A2P_TRY(init_umma_attn_short());
   const long long Sp = (long long)align_up((size_t)S, 8), Xp = 8;
   __nv_bfloat16* Qp = (__nv_bfloat16*)scratch;
   __nv_bfloat16* Kp = Qp + align_up((size_t)3 * R * T * D, 512);
@@ -1464,7 +1476,10 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
     p.split_scratch = reinterpret_cast<float*>(tail);
     p.split_counters = reinterpret_cast<int*>(tail + attn2_split_scratch_floats() * 4);
   }
-  auto launch = [&]() -> int { return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st); };
+  auto launch = [&]() -> int {   // terms 24 (variant 5): the short-key-set kernel (umma_attention_short.cuh)
+    if (variant == 5) return launch_umma_attn_short(o, p, st);
+    return variant ? launch_umma_attn2(variant, o, p, st) : launch_umma_attn(terms, o, p, st);
+  };
   A2P_TRY(launch());
   if (iters < 0) {
     A2P_CUDA(cudaStreamSynchronize(st));

@@ -135,3 +135,9 @@ def test_tcgen05_attention_unit(terms, tol, R, T, D, dh, S, nx):
 def test_tcgen05_attention2_unit(terms, R, T, D, S, nx):
     """head-parallel attention kernel (dh = 32, two planes): same cases as above incl. ragged tiles / blocks / extra keys"""
     test_tcgen05_attention_unit(terms, 4e-5, R, T, D, 32, S, nx)
+
+
+@pytest.mark.parametrize("R,T,D,S", [(1, 128, 64, 64), (3, 600, 256, 20), (2, 100, 256, 33), (16, 600, 256, 20)])
+def test_tcgen05_attention_short_unit(R, T, D, S):
+    """short-key-set kernel (umma_attention_short.cuh, hook code 24): one CTA walks all head pairs of a row tile"""
+    test_tcgen05_attention_unit(24, 4e-5, R, T, D, 32, S, 0)
