@@ -13,7 +13,7 @@ SYMBOLS = [
     "a2p_abi_version", "a2p_last_error", "a2p_has_tcgen05", "a2p_denoiser_create", "a2p_denoiser_destroy",
     "a2p_packed_weight_bytes", "a2p_denoiser_bind_weights", "a2p_kv_cache_bytes", "a2p_denoiser_set_conditioning",
     "a2p_conditioning_workspace_bytes", "a2p_workspace_bytes", "a2p_denoiser_forward", "a2p_sampler_step",
-    "a2p_sample_loop", "a2p_sample_loop_rng", "a2p_sampler_step_rng", "a2p_profile_forward", "a2p_launch_count",
+    "a2p_sample_loop", "a2p_sample_loop_rng", "a2p_sampler_step_rng", "a2p_profile_forward", "a2p_profile_forward_rows", "a2p_loop_row_groups", "a2p_launch_count",
 ]
 
 
@@ -69,6 +69,10 @@ def load() -> C.CDLL:
     lib.a2p_sampler_step_rng.argtypes = [i32, i32, i32, i32, vp, vp, vp, vp, vp, C.c_uint64, i64, i64, i32, vp, vp, vp]
     lib.a2p_profile_forward.argtypes = [vp, i32, i32, vp, vp, i32, vp, sz, vp, vp, vp, i32]
     lib.a2p_profile_forward.restype = i32
+    lib.a2p_profile_forward_rows.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, sz, vp, vp, vp, i32]
+    lib.a2p_profile_forward_rows.restype = i32
+    lib.a2p_loop_row_groups.argtypes = [vp, i32, i32]
+    lib.a2p_loop_row_groups.restype = i32
     lib.a2p_launch_count.argtypes = [vp]
     lib.a2p_launch_count.restype = i64
     for name in ("a2p_denoiser_create", "a2p_denoiser_bind_weights", "a2p_denoiser_set_conditioning",

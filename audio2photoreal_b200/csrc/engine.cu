@@ -53,10 +53,11 @@ struct GraphKey {
   const void *coeffs, *ts, *scale, *x, *pred, *noise, *ws;
   const void *kv0, *kv1;
   unsigned long long seed; long long row0; int rng;
+  int units;   // how the step was cut into concurrent forwards when the graph was captured
   bool operator==(const GraphKey& o) const {
     return B == o.B && T == o.T && kind == o.kind && n_steps == o.n_steps && clip == o.clip && mask == o.mask &&
            coeffs == o.coeffs && ts == o.ts && scale == o.scale && x == o.x && pred == o.pred && noise == o.noise &&
-           ws == o.ws && kv0 == o.kv0 && kv1 == o.kv1 && seed == o.seed && row0 == o.row0 && rng == o.rng;
+           ws == o.ws && kv0 == o.kv0 && kv1 == o.kv1 && seed == o.seed && row0 == o.row0 && rng == o.rng && units == o.units;
   }
 };
 
@@ -85,13 +86,15 @@ struct a2p_denoiser {
   int64_t graph_nodes = 0;
   cudaGraphExec_t gexec = nullptr;
   cudaStream_t cap_stream = nullptr;  // private stream used only to CAPTURE a step (the legacy default stream cannot capture)
-  // side streams (one per concurrently running forward): the per-step conditioning chain runs beside the first chain /
-  // self-attention launches
-  cudaStream_t cond_stream[2] = {nullptr, nullptr};
-  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
-  // CFG sampling loop: the unconditional forward runs on its own stream beside the conditional one (see sample_loop_impl)
-  cudaStream_t branch_stream = nullptr;
-  cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
+  // A sampling step of the fused arm runs as up to MAXU concurrent forwards ("units" = CFG branch x group of batch rows,
+  // see sample_loop_impl).  Per unit: a side stream on which the per-step conditioning chain runs beside the first chain /
+  // self-attention launches, and (units > 0) the stream the unit's own launches go to.
+  static constexpr int MAXU = 8;
+  cudaStream_t cond_stream[MAXU] = {};
+  cudaEvent_t ev_fork[MAXU] = {}, ev_join[MAXU] = {};
+  cudaStream_t unit_stream[MAXU] = {};
+  cudaEvent_t ev_ujoin[MAXU] = {};
+  cudaEvent_t ev_bfork = nullptr;
   GraphKey gkey{};
   bool gvalid = false;
 };
@@ -357,11 +360,15 @@ int attn2_variant() {
 // A2P_NO_BRANCH_STREAMS=1 keeps the single stacked forward).  A2P_BRANCH_STAGGER=n starts the unconditional forward after
 // the n-th chain / attention launch of the conditional one, so that one branch's 1-CTA-per-tile chain kernels (which
 // leave half of the SMs idle at small batches) overlap the other branch's attention kernels.
-bool branch_streams_disabled() {
-  static int v = -1;
-  if (v < 0) v = getenv("A2P_NO_BRANCH_STREAMS") ? 1 : 0;
-  return v == 1;
+// A2P_BRANCH_GROUPS=g (1, 2 or 4): additionally cut the batch rows of every branch into g groups (units = 2 g forwards).
+// Default: 2 groups for 4..16 rows per branch, else 1 (measured, B = 8: 192.7 / 182.6 / 222.6 ms per 100 steps for g = 1 / 2 / 4;
+// B = 32: g = 2 is 2 % slower than g = 1 -- profiles/r01v_unit_groups_sweep.txt)
+int branch_groups(int B) {
+  const char* e = getenv("A2P_BRANCH_GROUPS");
+  const int v = e ? atoi(e) : ((B >= 4 && B <= 16) ? 2 : 1);
+  return v >= 4 ? 4 : (v >= 2 ? 2 : 1);
 }
+bool branch_streams_disabled() { return getenv("A2P_NO_BRANCH_STREAMS") != nullptr; }
 int branch_stagger() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("A2P_BRANCH_STAGGER"); v = e ? atoi(e) : 0; if (v < 0) v = 0; }
@@ -398,8 +405,11 @@ int check_cfg(const a2p_model_cfg* c) {
 
 // ---------------------------------------------------------------- one denoiser evaluation
 // xin: [B,T,C] (already transposed).  ts: per-row [B] int64 (counter == nullptr) or the step table.
+// b0 / B_total: this call evaluates batch rows [b0, b0 + B) of a batch of B_total rows (xin / ts already point at row b0;
+// only the per-sample conditioning caches are addressed with the offset).  b0 > 0 is supported by the fused arm only.
 int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, const int* counter, int mask, char* wsb,
-                 const float** x0_cond, const float** x0_uncond, long long* x0_sample_stride) {
+                 const float** x0_cond, const float** x0_uncond, long long* x0_sample_stride, int b0 = 0, int B_total = 0) {
+  if (B_total <= 0) B_total = B;
   a2p_denoiser* h = c.h;
   const a2p_model_cfg& cf = h->cfg;
   const int D = cf.D, L = cf.L, C = cf.C, nf = h->nf, H = cf.H, dh = h->dh;
@@ -410,7 +420,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   const CondSet& c1 = h->cond[1];
   if (!c0.set || (nb == 2 && !c1.set)) A2P_FAIL("conditioning not set for the requested branch(es)");
   if (nb == 2 && c0.S != c1.S) A2P_FAIL("cond/uncond token counts differ (%d vs %d)", c0.S, c1.S);
-  if ((c0.Bc != 1 && c0.Bc != B) || (nb == 2 && c1.Bc != 1 && c1.Bc != B)) A2P_FAIL("conditioning batch does not match B=%d", B);
+  if ((c0.Bc != 1 && c0.Bc != B_total) || (nb == 2 && c1.Bc != 1 && c1.Bc != B_total)) A2P_FAIL("conditioning batch does not match B=%d", B_total);
   const int S = c0.S;
   if (T > cf.max_pos || S + 2 > cf.max_pos) A2P_FAIL("T=%d / S+2=%d exceed cfg.max_pos=%d", T, S + 2, cf.max_pos);
   const WsLayout w = ws_layout(cf, B, T);
@@ -429,6 +439,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   // launch and the first self-attention (fork / join by events; inside a graph capture these become parallel branches) and
   // is joined before the first kernel that reads the FiLM table.
   const bool chain_arm = cf.split_terms == 2 && D == 256 && (T % 8 == 0) && T >= 128 && !chain_disabled();
+  if (b0 != 0 && !chain_arm) A2P_FAIL("forward: a batch-row offset needs the fused arm");
   const bool side = chain_arm && !c.prof && !getenv("A2P_NO_SIDE_STREAM");
   cudaStream_t st_main = st;
   if (side) {
@@ -447,8 +458,8 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
   A2P_TRY(gemm(c, e, D, R, h->time_w1, D, h->time_b1, 4 * D, D, th, 4 * D, EPI_MISH));
   {
     GemmParams ex{};
-    ex.rowvec.base[0] = c0.hidden; ex.rowvec.stride[0] = c0.Bc == 1 ? 0 : D;
-    ex.rowvec.base[1] = c1.hidden; ex.rowvec.stride[1] = c1.Bc == 1 ? 0 : D;
+    ex.rowvec.base[0] = c0.hidden + (c0.Bc == 1 ? 0 : (size_t)b0 * D); ex.rowvec.stride[0] = c0.Bc == 1 ? 0 : D;
+    ex.rowvec.base[1] = c1.hidden ? c1.hidden + (c1.Bc == 1 ? 0 : (size_t)b0 * D) : nullptr; ex.rowvec.stride[1] = c1.Bc == 1 ? 0 : D;
     ex.rowvec.rows_per_branch = B;
     A2P_TRY(gemm(c, th, 4 * D, R, h->time_w2, 4 * D, h->time_b2, D, 4 * D, mt, D, EPI_ADDROW_MISH, &ex));
   }
@@ -527,16 +538,19 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       for (int b = 0; b < nb; ++b) {
         float* base = cs[b]->base + kl[b]->per_layer * l;
         const long long Bc = cs[b]->Bc;
+        const long long bo = Bc == 1 ? 0 : b0;   // first sample of this call inside the per-sample caches
         if (kind == 1) {
-          o.K[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->kaP); o.k_rows[b] = Bc * S; o.k_ld[b] = D; o.k_plane_stride[b] = Bc * S * D;
-          o.Vt[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->vtaP); o.vt_cols[b] = Bc * (long long)kl[b]->Sp; o.vt_ld[b] = o.vt_cols[b];
-          o.vt_plane_stride[b] = (long long)D * o.vt_cols[b];
-          ap.k_row_stride[b] = Bc == 1 ? 0 : S; ap.v_col_stride[b] = Bc == 1 ? 0 : (long long)kl[b]->Sp;
+          const long long Sp = kl[b]->Sp;
+          o.K[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->kaP) + bo * S * D; o.k_rows[b] = (Bc - bo) * S; o.k_ld[b] = D; o.k_plane_stride[b] = Bc * S * D;
+          o.Vt[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->vtaP) + bo * Sp; o.vt_cols[b] = (Bc - bo) * Sp; o.vt_ld[b] = Bc * Sp;
+          o.vt_plane_stride[b] = (long long)D * Bc * Sp;
+          ap.k_row_stride[b] = Bc == 1 ? 0 : S; ap.v_col_stride[b] = Bc == 1 ? 0 : Sp;
         } else {
-          o.K[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->k2P); o.k_rows[b] = Bc * S2; o.k_ld[b] = D; o.k_plane_stride[b] = Bc * S2 * D;
-          o.Vt[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->vt2P); o.vt_cols[b] = Bc * (long long)kl[b]->S2p; o.vt_ld[b] = o.vt_cols[b];
-          o.vt_plane_stride[b] = (long long)D * o.vt_cols[b];
-          ap.k_row_stride[b] = Bc == 1 ? 0 : S2; ap.v_col_stride[b] = Bc == 1 ? 0 : (long long)kl[b]->S2p;
+          const long long S2p = kl[b]->S2p;
+          o.K[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->k2P) + bo * S2 * D; o.k_rows[b] = (Bc - bo) * S2; o.k_ld[b] = D; o.k_plane_stride[b] = Bc * S2 * D;
+          o.Vt[b] = reinterpret_cast<__nv_bfloat16*>(base + kl[b]->vt2P) + bo * S2p; o.vt_cols[b] = (Bc - bo) * S2p; o.vt_ld[b] = Bc * S2p;
+          o.vt_plane_stride[b] = (long long)D * Bc * S2p;
+          ap.k_row_stride[b] = Bc == 1 ? 0 : S2; ap.v_col_stride[b] = Bc == 1 ? 0 : S2p;
         }
       }
       ap.rows_per_branch = B; ap.k_col0 = 0; ap.n_keys = kind == 1 ? S : S2; ap.n_extra = 0;
@@ -943,14 +957,14 @@ void a2p_denoiser_destroy(a2p_denoiser_t* h) {
   if (!h) return;
   if (h->gexec) cudaGraphExecDestroy(h->gexec);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < a2p_denoiser::MAXU; ++i) {
     if (h->cond_stream[i]) cudaStreamDestroy(h->cond_stream[i]);
     if (h->ev_fork[i]) cudaEventDestroy(h->ev_fork[i]);
     if (h->ev_join[i]) cudaEventDestroy(h->ev_join[i]);
+    if (h->unit_stream[i]) cudaStreamDestroy(h->unit_stream[i]);
+    if (h->ev_ujoin[i]) cudaEventDestroy(h->ev_ujoin[i]);
   }
-  if (h->branch_stream) cudaStreamDestroy(h->branch_stream);
   if (h->ev_bfork) cudaEventDestroy(h->ev_bfork);
-  if (h->ev_bjoin) cudaEventDestroy(h->ev_bjoin);
   delete h;
 }
 
@@ -1092,8 +1106,15 @@ size_t a2p_conditioning_workspace_bytes(const a2p_model_cfg* cfg, int Bc, int S)
 size_t a2p_workspace_bytes(const a2p_model_cfg* cfg, int B, int T) {
   if (check_cfg(cfg) || B <= 0 || T <= 0) return 0;
   const size_t one = ws_layout(*cfg, B, T).total;
-  // the fused arm runs the two CFG branches of a sampling step as concurrent forwards, each in its own workspace region
-  return (cfg->split_terms == 2 && cfg->D == 256) ? 2 * align_up(one, 1024) : one;
+  if (!(cfg->split_terms == 2 && cfg->D == 256)) return one;
+  // the fused arm runs a CFG sampling step as 2 G concurrent forwards (sample_loop_impl), each in its own workspace region
+  size_t need = 2 * align_up(one, 1024);
+  for (int G = 2; G <= a2p_denoiser::MAXU / 2 && G <= B; G *= 2) {
+    const size_t region = align_up(ws_layout(*cfg, ceil_div(B, G), T).total, 1024);
+    const size_t n = 2 * (size_t)G * region + 256 + align_up((size_t)B * T * cfg->C * 4, 256);
+    if (n > need) need = n;
+  }
+  return need;
 }
 
 int a2p_denoiser_set_conditioning(a2p_denoiser_t* h, int branch, int Bc, int S, int S2, const float* cond_tokens,
@@ -1232,44 +1253,72 @@ static int sample_loop_impl(a2p_denoiser_t* h, int kind, int B, int T, int n_ste
   int* counter = reinterpret_cast<int*>(wsb + w.counter);
   float* xin = reinterpret_cast<float*>(wsb + w.xin);
 
-  const size_t region = align_up(w.total, 1024);
-  const bool dual = branch_mask == A2P_MASK_BOTH && cf.split_terms == 2 && cf.D == 256 && (T % 8 == 0) && T >= 128 &&
-                    !chain_disabled() && !branch_streams_disabled() && ws_bytes >= 2 * region;
+  // ---- concurrent forwards.  No op mixes batch rows, so a CFG step is cut into units = {cond, uncond} x G groups of batch
+  // rows; every unit is an independent forward with its own workspace region and stream (inside the capture: a parallel
+  // branch of the graph), forked after the input transpose and joined before the sampler update.  Each kernel then waits
+  // only for ITS predecessor, and launches that cannot fill the machine alone (38 chain CTAs, partial attention rounds)
+  // run beside the other units' launches.
+  const bool multi = branch_mask == A2P_MASK_BOTH && cf.split_terms == 2 && cf.D == 256 && (T % 8 == 0) && T >= 128 &&
+                     !chain_disabled() && !branch_streams_disabled();
+  int G = multi ? branch_groups(B) : 1;
+  if (G > B) G = B;
+  const int Bs_max = ceil_div(B, G);
+  const size_t region = align_up(ws_layout(cf, Bs_max, T).total, 1024);
+  const int units = 2 * G;
+  const size_t shared_off = (size_t)units * region;        // G > 1: step counter + transposed input behind the unit regions
+  const size_t need = G == 1 ? 2 * region : shared_off + 256 + align_up((size_t)B * T * cf.C * 4, 256);
+  const bool use_units = multi && ws_bytes >= need;
+  if (use_units && G > 1) {
+    counter = reinterpret_cast<int*>(wsb + shared_off);
+    xin = reinterpret_cast<float*>(wsb + shared_off + 256);
+  }
   auto step_body = [&]() -> int {
     A2P_TRY(transpose_in(c, x, xin, B, cf.C, T));
-    const float *x0c = nullptr, *x0u = nullptr;
+    const float *x0c[a2p_denoiser::MAXU] = {}, *x0u[a2p_denoiser::MAXU] = {};
+    int gb0[a2p_denoiser::MAXU] = {}, gB[a2p_denoiser::MAXU] = {};
     long long sstride = 0;
-    if (dual) {
-      // two independent forwards (no op mixes batch rows): conditional on the caller's stream, unconditional on a second
-      // stream that forks from it (inside a capture: a parallel branch of the graph) and joins before the sampler update
-      if (!h->branch_stream) A2P_CUDA(cudaStreamCreateWithFlags(&h->branch_stream, cudaStreamNonBlocking));
+    int n_groups = 1;
+    if (use_units) {
+      n_groups = G;
       if (!h->ev_bfork) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_bfork, cudaEventDisableTiming));
-      if (!h->ev_bjoin) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_bjoin, cudaEventDisableTiming));
-      const float* dummy = nullptr;
-      long long ss2 = 0;
-      Ctx ca{h, c.st};
-      ca.slot = 0;
       const int stag = branch_stagger();
-      if (stag == 0) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));
-      else { ca.stagger_ev = h->ev_bfork; ca.stagger_after = stag; }
-      A2P_TRY(forward_core(ca, B, T, xin, (const long long*)timesteps, counter, A2P_MASK_COND, wsb, &x0c, &dummy, &sstride));
-      if (ca.stagger_ev) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));   // fewer launches than the stagger asked for
-      A2P_CUDA(cudaStreamWaitEvent(h->branch_stream, h->ev_bfork, 0));
-      Ctx cb{h, h->branch_stream};
-      cb.slot = 1;
-      A2P_TRY(forward_core(cb, B, T, xin, (const long long*)timesteps, counter, A2P_MASK_UNCOND, wsb + region, &dummy, &x0u, &ss2));
-      A2P_CUDA(cudaEventRecord(h->ev_bjoin, h->branch_stream));
-      A2P_CUDA(cudaStreamWaitEvent(c.st, h->ev_bjoin, 0));
+      for (int u = 0; u < units; ++u) {
+        const int g = u >> 1, br = u & 1;                   // unit 0 = (cond, group 0) runs on the caller's stream
+        const int b0 = (int)((long long)B * g / G), b1 = (int)((long long)B * (g + 1) / G);
+        gb0[g] = b0; gB[g] = b1 - b0;
+        Ctx cu{h, c.st};
+        cu.slot = u;
+        if (u == 0) {
+          if (stag == 0) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));
+          else { cu.stagger_ev = h->ev_bfork; cu.stagger_after = stag; }
+        } else {
+          if (!h->unit_stream[u]) A2P_CUDA(cudaStreamCreateWithFlags(&h->unit_stream[u], cudaStreamNonBlocking));
+          if (!h->ev_ujoin[u]) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_ujoin[u], cudaEventDisableTiming));
+          A2P_CUDA(cudaStreamWaitEvent(h->unit_stream[u], h->ev_bfork, 0));
+          cu.st = h->unit_stream[u];
+        }
+        const float* dummy = nullptr;
+        A2P_TRY(forward_core(cu, b1 - b0, T, xin + (size_t)b0 * T * cf.C, (const long long*)timesteps, counter,
+                             br ? A2P_MASK_UNCOND : A2P_MASK_COND, wsb + (size_t)u * region, br ? &dummy : &x0c[g],
+                             br ? &x0u[g] : &dummy, &sstride, b0, B));
+        if (u == 0 && cu.stagger_ev) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));   // fewer launches than the stagger asked for
+        if (u > 0) A2P_CUDA(cudaEventRecord(h->ev_ujoin[u], h->unit_stream[u]));
+      }
+      for (int u = 1; u < units; ++u) A2P_CUDA(cudaStreamWaitEvent(c.st, h->ev_ujoin[u], 0));
     } else {
-      A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, counter, branch_mask, wsb, &x0c, &x0u, &sstride));
+      gB[0] = B;
+      A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, counter, branch_mask, wsb, &x0c[0], &x0u[0], &sstride));
     }
-    K3Params p{};
-    p.x_t = x; p.x0c = x0c; p.x0u = x0u; p.scale = scale; p.coeffs = coeffs; p.step_counter = counter;
-    p.noise = noise_tape; p.noise_step_stride = (long long)B * cf.C * T; p.n_steps = n_steps;
-    p.x_prev = x; p.pred = pred_xstart; p.B = B; p.C = cf.C; p.T = T; p.kind = kind; p.clip = clip_denoised;
-    p.x0_sample_stride = sstride;
-    p.rng = rng; p.seed = seed; p.rng_row0 = row0;
-    A2P_TRY(launch_k3(c, p));
+    for (int g = 0; g < n_groups; ++g) {
+      const size_t off = (size_t)gb0[g] * cf.C * T;
+      K3Params p{};
+      p.x_t = x + off; p.x0c = x0c[g]; p.x0u = x0u[g]; p.scale = scale ? scale + gb0[g] : nullptr; p.coeffs = coeffs; p.step_counter = counter;
+      p.noise = noise_tape ? noise_tape + off : nullptr; p.noise_step_stride = (long long)B * cf.C * T; p.n_steps = n_steps;
+      p.x_prev = x + off; p.pred = pred_xstart + off; p.B = gB[g]; p.C = cf.C; p.T = T; p.kind = kind; p.clip = clip_denoised;
+      p.x0_sample_stride = sstride;
+      p.rng = rng; p.seed = seed; p.rng_row0 = row0 + gb0[g];
+      A2P_TRY(launch_k3(c, p));
+    }
     step_dec_kernel<<<1, 1, 0, c.st>>>(counter);
     h->launches++;
     A2P_CUDA(cudaGetLastError());
@@ -1283,7 +1332,7 @@ static int sample_loop_impl(a2p_denoiser_t* h, int kind, int B, int T, int n_ste
     return 0;
   }
   GraphKey key{B, T, kind, n_steps, clip_denoised, branch_mask, coeffs, timesteps, scale, x, pred_xstart, noise_tape, ws,
-               h->cond[0].base, h->cond[1].base, seed, row0, rng};
+               h->cond[0].base, h->cond[1].base, seed, row0, rng, use_units ? units : 0};
   if (!h->gvalid || !(h->gkey == key)) {
     if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
     h->gvalid = false;
@@ -1350,17 +1399,19 @@ int a2p_sampler_step_rng(int kind, int B, int C, int T, const float* x_t, const 
   return launch_k3(c, p);
 }
 
-int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, const int64_t* timesteps, int branch_mask,
-                        void* ws, size_t ws_bytes, void* stream, float* ms_by_cat, int64_t* launches_by_cat, int ncat) {
+int a2p_profile_forward_rows(a2p_denoiser_t* h, int B_total, int b0, int Bs, int T, const float* x_btc, const int64_t* timesteps,
+                             int branch_mask, void* ws, size_t ws_bytes, void* stream, float* ms_by_cat,
+                             int64_t* launches_by_cat, int ncat) {
   if (!h || !h->bound) A2P_FAIL("profile_forward: weights not bound");
   if (ncat < CAT_N || !ms_by_cat || !launches_by_cat) A2P_FAIL("profile_forward: need %d categories", (int)CAT_N);
-  const WsLayout w = ws_layout(h->cfg, B, T);
+  if (b0 < 0 || Bs <= 0 || b0 + Bs > B_total) A2P_FAIL("profile_forward: bad row range");
+  const WsLayout w = ws_layout(h->cfg, Bs, T);
   if (ws_bytes < w.total) A2P_FAIL("profile_forward: workspace too small");
   Prof prof;
   Ctx c{h, (cudaStream_t)stream};
   c.prof = &prof;
   const float *x0c, *x0u; long long ss;
-  A2P_TRY(forward_core(c, B, T, x_btc, (const long long*)timesteps, nullptr, branch_mask, (char*)ws, &x0c, &x0u, &ss));
+  A2P_TRY(forward_core(c, Bs, T, x_btc, (const long long*)timesteps, nullptr, branch_mask, (char*)ws, &x0c, &x0u, &ss, b0, B_total));
   A2P_CUDA(cudaStreamSynchronize(c.st));
   for (int i = 0; i < ncat; ++i) { ms_by_cat[i] = 0.f; launches_by_cat[i] = 0; }
   const bool dump = getenv("A2P_PROFILE_DUMP") != nullptr;
@@ -1373,6 +1424,20 @@ int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, con
   }
   for (auto e : prof.ev) cudaEventDestroy(e);
   return 0;
+}
+
+int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, const int64_t* timesteps, int branch_mask,
+                        void* ws, size_t ws_bytes, void* stream, float* ms_by_cat, int64_t* launches_by_cat, int ncat) {
+  return a2p_profile_forward_rows(h, B, 0, B, T, x_btc, timesteps, branch_mask, ws, ws_bytes, stream, ms_by_cat, launches_by_cat, ncat);
+}
+
+int a2p_loop_row_groups(const a2p_denoiser_t* h, int B, int T) {
+  if (!h) return 1;
+  const a2p_model_cfg& cf = h->cfg;
+  const bool multi = cf.split_terms == 2 && cf.D == 256 && (T % 8 == 0) && T >= 128 && !chain_disabled() && !branch_streams_disabled();
+  if (!multi) return 0;                       // 0: one stacked forward for both branches
+  const int G = branch_groups(B);
+  return G > B ? B : G;
 }
 
 int64_t a2p_launch_count(const a2p_denoiser_t* h) { return h ? h->launches : 0; }

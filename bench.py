@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--diffusion-steps", type=int, default=1000, help="debug only; anything but 1000 is not the benchmark")
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="debug only; per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dump-out", default=None, help="debug only: save the result of the last timed loop as .npy")
     ap.add_argument("--split-terms", type=int, default=2, help="0: exact-fp32 FFMA arm; 2 (default, fused chain kernels) | 3: split-bf16 tcgen05 arms")
     a = ap.parse_args()
     global SPLIT_TERMS
@@ -254,6 +255,8 @@ def main():
     ms_step, out = timed(loop_resident, a.steps)
     clk = clocks.stop()
     launches = (model.launch_count() - launches0)
+    if a.dump_out and rank == 0:
+        np.save(a.dump_out, out.float().cpu().numpy())
     loop_e2e()
     ms_e2e, out_h = timed(loop_e2e, a.steps)
     assert out.shape[0] == B * world and torch.isfinite(out).all()
@@ -276,12 +279,26 @@ def main():
         ws = model._workspace(lib.a2p_workspace_bytes(C.byref(model._cfg), B, T), dev)
         acc = np.zeros(ncat)
         reps = 5
+        # the fused arm cuts a CFG step into concurrent forwards: {cond, uncond} x groups of batch rows (engine.cu,
+        # sample_loop_impl).  Profile the launches the loop really makes -- every (branch, row group) forward, every launch
+        # timed ALONE (in the loop the units overlap, so the per-kernel times add up to more than a step)
+        groups = int(lib.a2p_loop_row_groups(model._handle, B, T))      # 0: one stacked forward for both branches
+        units = [(3, 0, B)] if groups == 0 else [(mk, B * g // groups, B * (g + 1) // groups - B * g // groups)
+                                                 for g in range(groups) for mk in (1, 2)]
+        two_branch = groups > 0
+        rows_per_launch = 2 * B if groups == 0 else units[0][2]
+        n_tot = np.zeros(ncat, dtype=np.int64)
         for i in range(reps + 1):
-            _lib.check(lib.a2p_profile_forward(model._handle, B, T, x_btc.data_ptr(), ts.data_ptr(), 3, ws.data_ptr(),
-                                               ws.numel(), torch.cuda.current_stream().cuda_stream, ms_cat, n_cat, ncat))
-            if i:
-                acc += np.array(list(ms_cat))
+            for mk, b0, bs in units:
+                _lib.check(lib.a2p_profile_forward_rows(model._handle, B, b0, bs, T, x_btc[b0:].data_ptr(), ts[b0:].data_ptr(), mk,
+                                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream,
+                                                        ms_cat, n_cat, ncat))
+                if i:
+                    acc += np.array(list(ms_cat))
+                if i == 1:
+                    n_tot += np.array(list(n_cat), dtype=np.int64)
         acc /= reps
+        n_cat = [int(v) for v in n_tot]
         names = ["cond_gemm", "ln_rope", "attn_proj_gemm", "attn_self", "attn_cross_audio", "attn_cross_keyframe", "ffn_gemm",
                  "io_tcn_gemm", "misc"]
         # kernel families: the three attention categories are launches of ONE kernel (umma_attn2_kernel), likewise the
@@ -289,14 +306,15 @@ def main():
         # biggest category (the audio cross-attention launch / the FFN chain launches)
         fam_attn, fam_chain = acc[3] + acc[4] + acc[5], acc[2] + acc[6]
         dom = (4 if fam_attn >= fam_chain else int(np.argmax([0, 0, acc[2], 0, 0, 0, acc[6]]))) if SPLIT_TERMS == 2 else int(np.argmax(acc))
-        R = 2 * B
+        R = 2 * B          # rows of one step (both branches); per-launch figures below divide by the launch counts
         D, L = 256, w["layers"]
         # per-launch algorithmic FLOPs of each category (attention cores exactly; linears = category total / launches)
         lin_proj = (6 * T * D * D + 2 * T * D * D + 4 * T * D * D + 4 * T * D * D) * R * L
         lin_ffn = 4 * T * D * 1024 * R * L
         if SPLIT_TERMS == 2:   # fused chain arm: PROJ = {sa_out+q, ca_out+q} per layer, FFN = {out+ffn1, ffn2+next qkv} per layer
             lin_proj, lin_ffn = 8 * T * D * D * R * L, (2 * T * D * D + 4 * T * D * 1024 + 6 * T * D * D) * R * L
-        alg = {3: 4 * T * T * D * R, 4: 4 * T * (S + 2) * D * R, 5: 4 * T * 20 * D * R,
+        alg = {3: 4 * T * T * D * R * L / max(1, n_cat[3]), 4: 4 * T * (S + 2) * D * R * L / max(1, n_cat[4]),
+               5: 4 * T * 20 * D * R * L / max(1, n_cat[5]),
                2: lin_proj / max(1, n_cat[2]), 6: lin_ffn / max(1, n_cat[6])}
         peaks = {}
         try:
@@ -311,7 +329,7 @@ def main():
         traffic = None     # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")))
-            if tr.get("kernel") == names[dom] and B == WORKLOAD["B"]:
+            if tr.get("kernel") == names[dom] and B == WORKLOAD["B"] and tr.get("rows_per_launch", 2 * B) == rows_per_launch:
                 traffic = tr["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -321,6 +339,8 @@ def main():
                     "forward_ms_by_kernel": {n: round(float(v), 4) for n, v in zip(names, acc)},
                     "kernel_family_ms": {"attention(self+audio+keyframe)": round(float(fam_attn), 4), "chain(proj+ffn)": round(float(fam_chain), 4)},
                     "split_terms": SPLIT_TERMS,
+                    "launch_shape": (f"{rows_per_launch} rows of one CFG branch per launch ({len(units)} concurrent forwards per step), each launch "
+                                     "timed alone; in the loop the forwards overlap" if two_branch else "both CFG branches (2B rows) per launch"),
                     "note": ("algorithmic FLOPs (one product per MAC) over measured time; the split-bf16 arm spends %d tensor-core "
                              "products per MAC for fp32-level parity" % {0: 0, 1: 1, 2: 3, 3: 6}[SPLIT_TERMS])}
         if not a.no_cpu_baseline:

@@ -175,6 +175,14 @@ int a2p_sampler_step_rng(int kind, int B, int C, int T, const float* x_t, const 
 int a2p_profile_forward(a2p_denoiser_t* h, int B, int T, const float* x_btc, const int64_t* timesteps, int branch_mask,
                         void* ws, size_t ws_bytes, void* stream, float* ms_by_cat, int64_t* launches_by_cat, int ncat);
 
+/* Same for batch rows [b0, b0 + Bs) of a batch of B_total rows (x_btc / timesteps point at row b0): the launch shapes of the
+ * sampling loop of the fused arm, which cuts a CFG step into concurrent forwards over groups of rows. */
+int a2p_profile_forward_rows(a2p_denoiser_t* h, int B_total, int b0, int Bs, int T, const float* x_btc, const int64_t* timesteps,
+                             int branch_mask, void* ws, size_t ws_bytes, void* stream, float* ms_by_cat,
+                             int64_t* launches_by_cat, int ncat);
+/* Number of row groups per CFG branch the sampling loop uses for a batch of B rows (1 = whole branch per forward). */
+int a2p_loop_row_groups(const a2p_denoiser_t* h, int B, int T);
+
 /* kernels launched by this handle since creation (for bench.py's gpu_launches). */
 int64_t a2p_launch_count(const a2p_denoiser_t* h);
 

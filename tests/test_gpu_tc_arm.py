@@ -141,3 +141,30 @@ def test_tcgen05_attention2_unit(terms, R, T, D, S, nx):
 def test_tcgen05_attention_short_unit(R, T, D, S):
     """short-key-set kernel (umma_attention_short.cuh, hook code 24): one CTA walks all head pairs of a row tile"""
     test_tcgen05_attention_unit(24, 4e-5, R, T, D, 32, S, 0)
+
+
+def test_concurrent_forward_units_agree(monkeypatch):
+    """The fused arm cuts a CFG step into concurrent forwards (branches x groups of batch rows, engine.cu sample_loop_impl):
+    every cut must give the single stacked forward's result up to fp32 summation order (the attention's split-KV tail cuts
+    keys differently for different launch sizes)."""
+    case = CASES["pose_full"]
+    model, cfg, sampler = _build(case, "ddim5", 2)
+    B, T = 5, 240                      # 5 rows: uneven groups (2 + 3, 1 + 1 + 1 + 2); T / 30 = 8 keyframes
+    g = torch.Generator().manual_seed(3)
+    y = {"audio_embed": torch.randn(B, 400, 1024, generator=g).cuda(), "keyframes": torch.randn(B, T // 30, 104, generator=g),
+         "mask": torch.ones(B, 1, 1, T, dtype=torch.bool), "scale": torch.full((B,), 2.0).cuda()}
+    noise = torch.randn(B, 104, 1, T, generator=g).cuda()
+
+    def run(env):
+        for k in ("A2P_NO_BRANCH_STREAMS", "A2P_BRANCH_GROUPS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        model._cond_sig = None
+        return sampler.ddim_sample_loop(cfg, (B, 104, 1, T), noise=noise.clone(), clip_denoised=False,
+                                        model_kwargs={"y": dict(y)}).clone()
+
+    ref = run({"A2P_NO_BRANCH_STREAMS": "1"})
+    assert torch.isfinite(ref).all()
+    for env in ({}, {"A2P_BRANCH_GROUPS": "2"}, {"A2P_BRANCH_GROUPS": "4"}):
+        _close(run(env), ref.cpu(), True, f"units {env}")
