@@ -350,6 +350,11 @@ def main():
                         "sample": f"{CPU_SAMPLE_STEPS} of 1000 diffusion steps of {CPU_SAMPLE_ROWS} of the 8 batch rows (CFG, T=600, S=1998) "
                                   f"in {dt:.1f}s, scaled x1000/{CPU_SAMPLE_STEPS} x 8/{CPU_SAMPLE_ROWS}"}
         f_fwd = flops_per_sample_forward()
+        # whole-step view beside the per-launch one: the concurrent forwards share the machine, so the step as a whole sustains
+        # more than any single launch timed alone
+        step_tf = f_fwd * 2 * B * n_diff / (ms_step * 1e-3) / 1e12
+        roofline["step_level"] = {"achieved": step_tf, "frac": step_tf / peak_tf, "concurrent_forwards": len(units),
+                                  "note": "algorithmic FLOPs of a whole loop / loop time on this GPU"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
