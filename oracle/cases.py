@@ -69,3 +69,14 @@ def make_inputs(case: Case, n_noise: int = 0) -> Dict[str, torch.Tensor]:
 def weights_of(case: Case):
     from audio2photoreal_b200.weights import synthetic_state_dict
     return synthetic_state_dict(dims_of(case), seed=case.wseed)
+
+
+def layer_inputs(case, seed=11):
+    """fixed (x, mem, t, mem2) for ONE decoder layer; regenerated from the seed by the tests"""
+    D = dims_of(case).D
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(case.B, case.T, D, generator=g)
+    mem = torch.randn(case.B, min(case.S, 64) + 2, D, generator=g)
+    t = torch.randn(case.B, D, generator=g)
+    mem2 = torch.randn(case.B, 20, D, generator=g) if case.fmt == "pose" else None
+    return x, mem, t, mem2

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 
 from oracle import a2p_oracle as O  # noqa: E402
 from oracle import ref_harness as RH  # noqa: E402
-from oracle.cases import CASES, make_inputs, weights_of, dims_of  # noqa: E402
+from oracle.cases import CASES, make_inputs, weights_of, dims_of, layer_inputs  # noqa: E402
 
 GOLD = os.path.join(ROOT, "tests", "golden")
 TABLES = ["betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod",
@@ -86,6 +86,21 @@ def golden_forward(name):
     print(f"fwd_{name}.npz written")
 
 
+def golden_layer(name):
+    """FiLMTransformerDecoderLayer.forward (transformer_modules.py:190-217) of the reference's layer 1 on fixed inputs"""
+    case = CASES[name]
+    ref, model, _, sd = _ref_model(case, "ddim10")
+    x, mem, t, mem2 = layer_inputs(case)
+    layer = model.seqTransDecoder.stack[1]
+    with torch.no_grad():
+        out = layer(x, mem, t, memory2=mem2)
+    mine = O.decoder_layer(x, mem, t, mem2, sd, "seqTransDecoder.stack.1", case.H)
+    _close(mine, out, name + "/decoder_layer")
+    np.savez_compressed(os.path.join(GOLD, f"layer_{name}.npz"), out=out.numpy(),
+                        x_sha1=hashlib.sha1(x.numpy().tobytes()).hexdigest())
+    print(f"layer_{name}.npz written")
+
+
 def golden_loop(name, respacing, kind, eta=0.0):
     case = CASES[name]
     ref, model, diffusion, sd = _ref_model(case, respacing)
@@ -129,6 +144,8 @@ def main():
     golden_schedule()
     for n in ["pose_small", "pose_small_h4", "face_small", "pose_full", "face_full"]:
         golden_forward(n)
+    for n in ["pose_small", "face_small"]:
+        golden_layer(n)
     golden_loop("pose_small", "ddim10", "ddim")
     golden_loop("pose_small", "ddim10", "ddim", eta=0.5)
     golden_loop("pose_small", "ddim100", "ddim")

@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import a2p_oracle as O
-from oracle.cases import CASES, make_inputs, weights_of
+from oracle.cases import CASES, layer_inputs, make_inputs, weights_of
 
 
 def _check(got, ref, atol=2e-5, rtol=1e-5):
@@ -24,6 +24,16 @@ def test_forward_matches_reference(golden_dir, name):
     _check(O.denoiser_forward(*a, 0.0), g["cond"])
     _check(O.denoiser_forward(*a, 1.0), g["uncond"])
     _check(O.cfg_forward(*a, inp["scale"]), g["cfg"], atol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["pose_small", "face_small"])
+def test_decoder_layer_matches_reference(golden_dir, name):
+    """one FiLMTransformerDecoderLayer (transformer_modules.py:190-217) of the reference on fixed (x, mem, t, mem2)"""
+    import hashlib
+    case, g = CASES[name], np.load(os.path.join(golden_dir, f"layer_{name}.npz"))
+    x, mem, t, mem2 = layer_inputs(case)
+    assert hashlib.sha1(x.numpy().tobytes()).hexdigest() == str(g["x_sha1"])
+    _check(O.decoder_layer(x, mem, t, mem2, weights_of(case), "seqTransDecoder.stack.1", case.H), g["out"])
 
 
 def test_forward_full_size_pose(golden_dir):
