@@ -172,6 +172,9 @@ def main():
     ap.add_argument("--diffusion-steps", type=int, default=1000, help="debug only; anything but 1000 is not the benchmark")
     ap.add_argument("--batch", type=int, default=WORKLOAD["B"], help="debug only; per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-cfg", action="store_true",
+                    help="secondary measurement (SURVEY 8d, config 2 'no-CFG variant'): the bare denoiser, one forward per step; "
+                         "not the benchmark line")
     ap.add_argument("--dump-out", default=None, help="debug only: save the result of the last timed loop as .npy")
     ap.add_argument("--split-terms", type=int, default=2, help="0: exact-fp32 FFMA arm; 2 (default, fused chain kernels) | 3: split-bf16 tcgen05 arms")
     a = ap.parse_args()
@@ -201,7 +204,8 @@ def main():
     model, sampler = create_model_and_diffusion(model_args(resp), "test")
     load_model(model, synthetic_state_dict(model.dims, seed=1))
     model = model.to(dev).eval()
-    cfg = CFGDenoiser(model)
+    cfg = model if a.no_cfg else CFGDenoiser(model)
+    nbr = 1 if a.no_cfg else 2          # denoiser evaluations per row and step
     n_diff = sampler.num_timesteps
     shape = (B, w["C"], 1, T)
 
@@ -285,8 +289,10 @@ def main():
         groups = int(lib.a2p_loop_row_groups(model._handle, B, T))      # 0: one stacked forward for both branches
         units = [(3, 0, B)] if groups == 0 else [(mk, B * g // groups, B * (g + 1) // groups - B * g // groups)
                                                  for g in range(groups) for mk in (1, 2)]
+        if a.no_cfg:
+            groups, units = 0, [(1, 0, B)]
         two_branch = groups > 0
-        rows_per_launch = 2 * B if groups == 0 else units[0][2]
+        rows_per_launch = nbr * B if groups == 0 else units[0][2]
         n_tot = np.zeros(ncat, dtype=np.int64)
         for i in range(reps + 1):
             for mk, b0, bs in units:
@@ -306,7 +312,7 @@ def main():
         # biggest category (the audio cross-attention launch / the FFN chain launches)
         fam_attn, fam_chain = acc[3] + acc[4] + acc[5], acc[2] + acc[6]
         dom = (4 if fam_attn >= fam_chain else int(np.argmax([0, 0, acc[2], 0, 0, 0, acc[6]]))) if SPLIT_TERMS == 2 else int(np.argmax(acc))
-        R = 2 * B          # rows of one step (both branches); per-launch figures below divide by the launch counts
+        R = nbr * B        # rows of one step (both branches); per-launch figures below divide by the launch counts
         D, L = 256, w["layers"]
         # per-launch algorithmic FLOPs of each category (attention cores exactly; linears = category total / launches)
         lin_proj = (6 * T * D * D + 2 * T * D * D + 4 * T * D * D + 4 * T * D * D) * R * L
@@ -339,7 +345,7 @@ def main():
                     "forward_ms_by_kernel": {n: round(float(v), 4) for n, v in zip(names, acc)},
                     "kernel_family_ms": {"attention(self+audio+keyframe)": round(float(fam_attn), 4), "chain(proj+ffn)": round(float(fam_chain), 4)},
                     "split_terms": SPLIT_TERMS,
-                    "launch_shape": (f"{rows_per_launch} rows of one CFG branch per launch ({len(units)} concurrent forwards per step), each launch "
+                    "launch_shape": ("bare denoiser, no CFG: one forward of B rows per step" if a.no_cfg else f"{rows_per_launch} rows of one CFG branch per launch ({len(units)} concurrent forwards per step), each launch "
                                      "timed alone; in the loop the forwards overlap" if two_branch else "both CFG branches (2B rows) per launch"),
                     "note": ("algorithmic FLOPs (one product per MAC) over measured time; the split-bf16 arm spends %d tensor-core "
                              "products per MAC for fp32-level parity" % {0: 0, 1: 1, 2: 3, 3: 6}[SPLIT_TERMS])}
@@ -352,7 +358,7 @@ def main():
         f_fwd = flops_per_sample_forward()
         # whole-step view beside the per-launch one: the concurrent forwards share the machine, so the step as a whole sustains
         # more than any single launch timed alone
-        step_tf = f_fwd * 2 * B * n_diff / (ms_step * 1e-3) / 1e12
+        step_tf = f_fwd * nbr * B * n_diff / (ms_step * 1e-3) / 1e12
         roofline["step_level"] = {"achieved": step_tf, "frac": step_tf / peak_tf, "concurrent_forwards": len(units),
                                   "note": "algorithmic FLOPs of a whole loop / loop time on this GPU"}
         line = {
@@ -360,16 +366,16 @@ def main():
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if SPLIT_TERMS == 0 else f"bf16x{SPLIT_TERMS} split (fp32-equivalent), fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": f"pose body diffusion, {n_diff} steps, T={T}, C=104, batch {B}/GPU, CFG g=2.0, "
+            "config": {"workload": f"pose body diffusion, {n_diff} steps, T={T}, C=104, batch {B}/GPU, {'NO CFG (bare denoiser)' if a.no_cfg else 'CFG g=2.0'}, "
                                    f"L=6 D=256 H=8, synthetic wav2vec features [B,{S},1024] (BASELINE configs[1])",
                        "global_batch": B * world, "parallelism": f"batch-sharded x{world}, 1 all-gather",
                        "l2": "inputs_larger_than_l2 (K/V caches %d MB + activations per step)" % (B * 25),
-                       "algorithmic_gflop_per_loop": f_fwd * 2 * B * world * n_diff / 1e9},
+                       "algorithmic_gflop_per_loop": f_fwd * nbr * B * world * n_diff / 1e9},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e},
             "roofline": roofline, "cpu_baseline": cpu_base,
-            "model_tflops": f_fwd * 2 * B * world * n_diff / (ms_step * 1e-3) / 1e12,
+            "model_tflops": f_fwd * nbr * B * world * n_diff / (ms_step * 1e-3) / 1e12,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
