@@ -83,3 +83,23 @@ def test_shard_helpers():
     y = {"audio_embed": torch.arange(8).view(8, 1), "scale": torch.ones(8), "name": "x"}
     s = shard_y(y, 2, 5, 8)
     assert s["audio_embed"].flatten().tolist() == [2, 3, 4] and s["scale"].shape == (3,) and s["name"] == "x"
+
+
+def test_workspace_query_covers_every_cut_of_a_step():
+    """a2p_workspace_bytes (host-only query): the fused arm needs one region per concurrent forward of a CFG step
+    (2 branches x up to 4 row groups, engine.cu sample_loop_impl) plus the shared step counter / transposed input;
+    the other arms need exactly one stacked-forward layout."""
+    import ctypes as C
+    lib = _lib.load()
+    mk = lambda terms, D=256: _lib.ModelCfg(fmt=0, C=104, D=D, L=6, H=8, FF=1024, S2=20, max_pos=2000, split_terms=terms, reserved=0)
+    T = 600
+    exact = [lib.a2p_workspace_bytes(C.byref(mk(0)), B, T) for B in (1, 2, 8, 32)]
+    fused = [lib.a2p_workspace_bytes(C.byref(mk(2)), B, T) for B in (1, 2, 8, 32)]
+    assert all(e > 0 for e in exact) and exact == sorted(exact)
+    assert fused == sorted(fused)
+    # two regions of the full two-plane layout at least, and the query is monotonic in the batch
+    for B, f in zip((1, 2, 8, 32), fused):
+        one_region_floor = 2 * B * T * 256 * 4            # the fp32 residual stream of both branches alone
+        assert f >= 2 * one_region_floor
+    assert lib.a2p_workspace_bytes(C.byref(mk(2)), 0, T) == 0 and lib.a2p_workspace_bytes(C.byref(mk(2, D=300)), 8, T) == 0
+    assert lib.a2p_loop_row_groups(None, 8, T) == 1       # null handle: defined answer, no crash
