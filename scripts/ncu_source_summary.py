@@ -1,8 +1,9 @@
 """Summarise an ncu report's source page: top stalled SASS instructions and stall-reason totals."""
 import collections, csv, subprocess, sys
 
-def main(path, top=28):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+def main(path, top=28, skip=0):
+    sel = ["--launch-skip", str(skip), "--launch-count", "1"]     # one launch of a multi-launch report
+    raw = subprocess.run(["ncu", "-i", path] + sel + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, vals = rows[0], rows[1], rows[2]
     keep = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__cycles_active.avg",
@@ -11,11 +12,11 @@ def main(path, top=28):
             "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
             "sm__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sectors_srcunit_tex_op_read.sum",
             "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active"]
-    print(f"# {path}: {vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else ''}")
+    print(f"# {path} (launch {skip}): {vals[hdr.index('Kernel Name')] if 'Kernel Name' in hdr else ''}")
     for h, u, v in zip(hdr, units, vals):
         if h in keep:
             print(f"{h} [{u}] = {v}")
-    src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    src = subprocess.run(["ncu", "-i", path] + sel + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(src.splitlines()))
     hdr = rows[1]
     ci, cs, cx = hdr.index("Source"), hdr.index("# Samples"), hdr.index("Instructions Executed")
@@ -40,4 +41,4 @@ def main(path, top=28):
         print(f"{100*sm/tot:5.1f}% exec={ex:>9} {why[6:]:<14} {s[:96]}")
 
 if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 28)
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 28, int(sys.argv[3]) if len(sys.argv) > 3 else 0)
