@@ -34,13 +34,17 @@ _lib: Optional[C.CDLL] = None
 
 
 def load() -> C.CDLL:
-    """dlopen the in-tree library (building it first if nvcc is around and sources are newer)."""
+    """dlopen the in-tree library (rebuilding it first when its source-hash stamp does not match csrc/ + include/)."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from .csrc.build import build
-        build()
+    from .csrc import build as _b
+    if _b._stale():            # content hash of csrc/ + include/ against the stamp written at build time
+        import shutil
+        if shutil.which(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            _b.build()
+        elif os.path.exists(LIB_PATH):
+            raise A2PError(f"{LIB_PATH} was built from different sources and nvcc is not available to rebuild it")
     if not os.path.exists(LIB_PATH):
         raise A2PError(f"{LIB_PATH} is missing and could not be built: the a2p_b200 CUDA extension is required")
     lib = C.CDLL(LIB_PATH)
@@ -82,6 +86,28 @@ def load() -> C.CDLL:
         raise A2PError("liba2p_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+_tlib: Optional[C.CDLL] = None
+
+
+def load_testing() -> C.CDLL:
+    """dlopen liba2p_b200_testing.so: per-kernel test / measurement hooks (include/a2p_b200_testing.h).  Not part of the
+    product: only tests/ and scripts/ call this."""
+    global _tlib
+    if _tlib is None:
+        load()                                            # builds both libraries when stale
+        path = os.path.join(_HERE, "liba2p_b200_testing.so")
+        if not os.path.exists(path):
+            raise A2PError(f"{path} is missing")
+        _tlib = C.CDLL(path)
+        _tlib.a2p_test_last_error.restype = C.c_char_p
+    return _tlib
+
+
+def check_testing(rc: int) -> None:
+    if rc != 0:
+        raise A2PError(load_testing().a2p_test_last_error().decode("utf-8", "replace"))
 
 
 def check(rc: int) -> None:

@@ -56,24 +56,38 @@ def load_model(model, state_dict) -> None:
     assert all(k.startswith(("transformer.", "tokenizer.", "audio_model.", "lip_model.")) for k in missing), missing
 
 
+_patched = []   # (module, attribute, original) triples of the last patch_reference()
+
+
 def patch_reference() -> None:
     """Swap the B200 classes into an importable reference checkout (it must be on sys.path):
-    afterwards `python -m sample.generate ...` builds Denoiser / CFGDenoiser / Sampler."""
+    afterwards `python -m sample.generate ...` builds Denoiser / CFGDenoiser / Sampler.  `unpatch_reference()` undoes it."""
     import utils.model_util as mu  # reference module
     import model.cfg_sampler as cs
 
-    mu.create_model_and_diffusion = create_model_and_diffusion
-    mu.load_model = load_model
-    mu.create_gaussian_diffusion = create_gaussian_diffusion
-    cs.ClassifierFreeSampleModel = CFGDenoiser
+    def swap(mod, name, new):
+        if getattr(mod, name, None) is not new:
+            _patched.append((mod, name, getattr(mod, name)))
+            setattr(mod, name, new)
+
+    swap(mu, "create_model_and_diffusion", create_model_and_diffusion)
+    swap(mu, "load_model", load_model)
+    swap(mu, "create_gaussian_diffusion", create_gaussian_diffusion)
+    swap(cs, "ClassifierFreeSampleModel", CFGDenoiser)
     try:
         import sample.generate as gen
-        gen.create_model_and_diffusion = create_model_and_diffusion
-        gen.load_model = load_model
-        gen.ClassifierFreeSampleModel = CFGDenoiser
     except Exception:
-        pass
+        return
+    swap(gen, "create_model_and_diffusion", create_model_and_diffusion)
+    swap(gen, "load_model", load_model)
+    swap(gen, "ClassifierFreeSampleModel", CFGDenoiser)
+
+
+def unpatch_reference() -> None:
+    while _patched:
+        mod, name, orig = _patched.pop()
+        setattr(mod, name, orig)
 
 
 __all__ = ["Denoiser", "CFGDenoiser", "Sampler", "create_model_and_diffusion", "create_gaussian_diffusion",
-           "load_model", "get_model_args", "patch_reference"]
+           "load_model", "get_model_args", "patch_reference", "unpatch_reference"]

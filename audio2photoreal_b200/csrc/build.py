@@ -7,33 +7,55 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-LIB = os.path.join(PKG, "liba2p_b200.so")
-SOURCES = ["engine.cu"]
+LIB = os.path.join(PKG, "liba2p_b200.so")                    # the product: C-ABI of include/a2p_b200.h
+TEST_LIB = os.path.join(PKG, "liba2p_b200_testing.so")       # test / measurement hooks (include/a2p_b200_testing.h)
+TARGETS = {LIB: ["engine.cu"], TEST_LIB: ["testing.cu"]}
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 
+STAMP = LIB + ".srchash"      # sha256 of the sources the library was built from (mtimes do not survive a snapshot copy)
+
+
+def source_hash() -> str:
+    import hashlib
+    deps = sorted(os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h")))
+    inc = os.path.join(os.path.dirname(PKG), "include")
+    deps += sorted(os.path.join(inc, f) for f in os.listdir(inc) if f.endswith(".h"))
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB):
+    if not (os.path.exists(LIB) and os.path.exists(TEST_LIB) and os.path.exists(STAMP)):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(HERE, f) for f in os.listdir(HERE) if f.endswith((".cu", ".cuh", ".h"))]
-    deps.append(os.path.join(os.path.dirname(PKG), "include", "a2p_b200.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP) as f:
+        return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile both libraries (concurrently) unless the stamp matches the sources; returns the product library's path."""
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(HERE, s) for s in SOURCES] + ["-o", LIB]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    procs = []
+    for out, srcs in TARGETS.items():
+        cmd = [nvcc] + NVCC_FLAGS + [os.path.join(HERE, s) for s in srcs] + ["-o", out]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((out, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for out, pr in procs:
+        so, se = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {out}:\n" + so + se)
+        if verbose:
+            print(se)
+    with open(STAMP, "w") as f:
+        f.write(source_hash())
     return LIB
 
 

@@ -2,8 +2,12 @@
 torchrun); every row is an independent trajectory, so there is NO per-step communication and exactly
 one collective: an all-gather of the final motion codes (NCCL over NVLink on GPUs, gloo in CPU tests).
 
-Determinism: every rank seeds identically, draws the GLOBAL noise tensor and slices its own rows, so
-the W-rank result is bit-identical to the 1-rank result for the same seed.
+Determinism: every rank seeds identically, draws the GLOBAL initial noise (and, for the stochastic samplers
+-- ancestral / eta > 0 -- the GLOBAL per-step noise tape) and slices its own rows, or uses the in-kernel Philox
+stream keyed by (seed, GLOBAL row index): the rows a rank computes do not depend on the partition.  On the exact
+fp32 arm (split_terms = 0) the W-rank result is bit-identical to the 1-rank result; on the tensor-core arms it is
+identical up to fp32 summation order (the attention's split-KV tail cuts keys by launch size), which
+tests/test_gpu_parity.py::test_batch_rows_independent_and_deterministic bounds (SURVEY.md 8e).
 """
 from __future__ import annotations
 
@@ -49,17 +53,41 @@ def all_gather_rows(local: torch.Tensor, n_rows: int, group=None) -> torch.Tenso
     return torch.cat([o[: hi - lo] for o, (lo, hi) in zip(out, sizes)], dim=0)
 
 
-def sample_sharded(local_loop: Callable[[Tuple[int, ...], torch.Tensor, Dict], torch.Tensor], shape, y: Dict, seed: int,
-                   device, group=None, noise: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Run `local_loop(local_shape, local_noise, local_y)` on this rank's rows and all-gather the result.
+def global_noise_tape(n_steps: int, shape, seed: int, device) -> torch.Tensor:
+    """The same [n_steps, B, C, 1, T] per-step noise on every rank (ancestral / eta > 0 samplers); ranks slice [:, lo:hi]."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed + 0x5EED)
+    return torch.randn(n_steps, *shape, device=device, generator=g)
 
-    `local_loop` is e.g. lambda s, n, yy: sampler.ddim_sample_loop(model, s, noise=n, clip_denoised=False,
-    model_kwargs={"y": yy}).  Works unchanged with world size 1 / no process group."""
+
+def sample_sharded(local_loop: Callable[..., torch.Tensor], shape, y: Dict, seed: int, device, group=None,
+                   noise: Optional[torch.Tensor] = None, noise_tape_steps: int = 0) -> torch.Tensor:
+    """Run `local_loop(local_shape, local_noise, local_y[, lo, hi[, local_tape]])` on this rank's rows and all-gather.
+
+    `local_loop` is e.g. lambda s, n, yy, lo, hi: sampler.ddim_sample_loop(model, s, noise=n, clip_denoised=False,
+    model_kwargs={"y": yy}).  For the stochastic samplers either pass `noise_tape_steps = n` (the global tape is drawn
+    with the seeded generator and this rank's slice arrives as the 6th argument -> `noise_tape=`), or forward
+    `row0=lo` with `noise_rng="philox"`; NEVER let every rank draw its own torch.randn_like tape from an identically
+    seeded generator (all ranks would apply the same noise to different rows).  A 3-argument callable (deterministic
+    eta = 0 DDIM) keeps working.  Works unchanged with world size 1 / no process group."""
+    import inspect
     B = shape[0]
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     lo, hi = shard_range(B, world, rank)
     if noise is None:
         noise = global_noise(shape, seed, device)
-    local = local_loop((hi - lo,) + tuple(shape[1:]), noise[lo:hi].contiguous(), shard_y(y, lo, hi, B))
+    args = [(hi - lo,) + tuple(shape[1:]), noise[lo:hi].contiguous(), shard_y(y, lo, hi, B)]
+    try:
+        n_params = len([p for p in inspect.signature(local_loop).parameters.values()
+                        if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD)])
+    except (TypeError, ValueError):
+        n_params = 3
+    if n_params >= 5:
+        args += [lo, hi]
+    if noise_tape_steps:
+        if n_params < 6:
+            raise TypeError("noise_tape_steps needs local_loop(shape, noise, y, lo, hi, tape)")
+        args.append(global_noise_tape(noise_tape_steps, shape, seed, device)[:, lo:hi].contiguous())
+    local = local_loop(*args)
     return all_gather_rows(local, B, group)

@@ -10,9 +10,17 @@ e2e     = same metric through the public API (Sampler.ddim_sample_loop) with HOS
           device->host read of the result inside the timed region
 Scaling is weak: every rank owns B independent rows (no data-path collective; one all-gather of the result).
 
+Besides the contract line (BASELINE configs[1]: B = 8 per GPU, weak scaling) every run also measures
+  * "config3_strong": BASELINE configs[2] = the north-star's headline -- GLOBAL batch 32 + CFG, sharded over the N ranks
+    (N = 1: batch 32 on one B200; N = 8: 4 rows per GPU = STRONG scaling of the same job),
+  * "gpu_baseline" (rank 0, N = 1): the UNMODIFIED reference loop (oracle/_ref: ddim_sample_loop + ClassifierFreeSampleModel +
+    FiLMTransformer, stock PyTorch fp32, TF32 off) on the same B200 -- the denominator of the north-star's ">= 10x" target,
+  * "cpu_baseline": the same unmodified reference on the host cores (kind "reference"; the oracle port only if oracle/_ref
+    is absent).
+
   python bench.py [--gpus N --steps K --warmup W]         this framework
-  python bench.py --impl reference ...                      the reference's algorithm on the host CPU cores
-                                                            (oracle port; /root/reference cannot travel)
+  python bench.py --impl reference ...                      the reference's own loop on the host CPU cores (oracle/_ref)
+  python bench.py --workload face ...                       BASELINE configs[3] (face, ddim500, g = 10, 16 rows / GPU): secondary
 """
 from __future__ import annotations
 
@@ -35,6 +43,18 @@ import torch  # noqa: E402
 METRIC = "motion-frames/sec full p_sample_loop (body, 1000 steps, T=600)"
 UNIT = "frames/s"
 WORKLOAD = dict(fmt="pose", layers=6, heads=8, T=600, S=1998, C=104, B=8, guidance=2.0, respacing="")
+# BASELINE configs[3]: face diffusion, 500 steps (ddim500), T = 600, 256-dim codes, 16 rows per GPU (64 over 4 GPUs), g = 10
+FACE_METRIC = "motion-frames/sec full ddim_sample_loop (face, ddim500, T=600)"
+FACE_WORKLOAD = dict(fmt="face", layers=8, heads=8, T=600, S=1998, C=256, B=16, guidance=10.0, respacing="ddim500")
+CONFIG3_GLOBAL_BATCH = 32
+
+
+def workload_name(fmt, B, cfg, n_diff=None):
+    if fmt == "pose":
+        return (f"pose body diffusion, {n_diff or 1000} steps, T=600, C=104, batch {B}/GPU, {'CFG g=2.0' if cfg else 'NO CFG (bare denoiser)'}, "
+                f"L=6 D=256 H=8, synthetic wav2vec features [B,1998,1024] (BASELINE configs[1])")
+    return (f"face diffusion, {n_diff or 500} steps (ddim500), T=600, C=256, batch {B}/GPU, CFG g=10.0, L=8 D=512 H=8, synthetic "
+            f"audio+lip features [B,1998,2038] (BASELINE configs[3])")
 
 
 SPLIT_TERMS = 2
@@ -50,7 +70,7 @@ def model_args(respacing):
 def synth_inputs(B, T, S, seed, pin=False):
     g = torch.Generator().manual_seed(seed)
     y = {
-        "audio_embed": torch.randn(B, S, 1024, generator=g),
+        "audio_embed": torch.randn(B, S, 1024 if WORKLOAD["fmt"] == "pose" else 2038, generator=g),
         "keyframes": torch.randn(B, len(range(0, T, 30)), 104, generator=g),
         "mask": torch.ones(B, 1, 1, T, dtype=torch.bool),
         "scale": torch.full((B,), WORKLOAD["guidance"]),
@@ -62,14 +82,16 @@ def synth_inputs(B, T, S, seed, pin=False):
     return y, noise
 
 
-def flops_per_sample_forward(T=600, S=2000, S2=20, D=256, L=6, FF=1024, C=104):
-    """SURVEY.md 8d formulas (2*MAC, cached-K/V convention)."""
+def flops_per_sample_forward(T=600, S=2000, S2=20, D=256, L=6, FF=1024, C=104, fmt="pose"):
+    """SURVEY.md 8d formulas (2*MAC, cached-K/V convention); face: no keyframe attention, no TCN, 3 FiLM blocks."""
     sa = 6 * T * D * D + 4 * T * T * D + 2 * T * D * D
     ca = 2 * T * D * D + 8 * D * D + 4 * T * S * D + 2 * T * D * D
-    ca2 = 2 * T * D * D + 4 * T * S2 * D + 2 * T * D * D
     ffn = 4 * T * D * FF
-    film = 4 * 4 * D * D
     io = 4 * T * C * D
+    if fmt == "face":
+        return L * (sa + ca + ffn + 3 * 4 * D * D) + io + 32 * D * D
+    ca2 = 2 * T * D * D + 4 * T * S2 * D + 2 * T * D * D
+    film = 4 * 4 * D * D
     lens = [T + 24 - 2, T + 24 - 6, T + 24 - 12, T + 24 - 14, T + 24 - 18, T]
     ch = [(104, 256), (256, 104), (104, 104), (104, 104), (104, 104), (104, 104)]
     conv = sum(2 * ln * ci * co * 3 for ln, (ci, co) in zip(lens, ch)) + 2 * T * C * C
@@ -109,55 +131,171 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-CPU_SAMPLE_STEPS = 10  # diffusion steps the in-line CPU arm times (about 10 s on 32 threads)
-CPU_SAMPLE_ROWS = 2   # rows of the B=8 batch the CPU arm actually evaluates (per-row cost is independent of the batch)
+CPU_SAMPLE_STEPS = 10  # diffusion steps the oracle-PORT fallback times
+CPU_SAMPLE_ROWS = 2
 
 
 def cpu_port_frames_per_s(n_diff_steps, threads):
-    """The reference's algorithm on the host CPU (oracle port) on a BOUNDED sample of the same workload:
-    `n_diff_steps` CFG diffusion steps of CPU_SAMPLE_ROWS of the 8 rows (T=600, S=1998, conditioning recomputed
-    every call exactly like the reference), scaled to 8 rows x 1000 steps."""
+    """FALLBACK (oracle/_ref absent): the reference's algorithm as restated by the oracle, on a bounded sample
+    (`n_diff_steps` CFG steps of CPU_SAMPLE_ROWS of the 8 rows, scaled to 8 rows x 1000 steps)."""
     from oracle import a2p_oracle as O
     from audio2photoreal_b200.weights import model_dims, synthetic_state_dict
     torch.set_num_threads(threads)
     w = WORKLOAD
     sd = synthetic_state_dict(model_dims("pose", w["layers"], w["heads"]), seed=1)
     y, noise = synth_inputs(CPU_SAMPLE_ROWS, w["T"], w["S"], seed=10)
-    fn = lambda x, ts, n: O.cfg_forward(sd, "pose", w["heads"], x[:n], ts[:n], y["audio_embed"][:n], y["keyframes"][:n],
-                                        y["mask"][:n], y["scale"][:n])
-    ts = torch.full((CPU_SAMPLE_ROWS,), 500, dtype=torch.long)
+    od = O.OracleDiffusion("")
+    fn = lambda x, ts: O.cfg_forward(sd, "pose", w["heads"], x, ts, y["audio_embed"], y["keyframes"], y["mask"], y["scale"])
     with torch.no_grad():
-        fn(noise, ts, 1)  # warm-up: one CFG call on one row
+        od.ddim_sample_loop(fn, noise, skip_timesteps=999)       # warm-up: one step
         t0 = time.perf_counter()
-        x = noise
-        for i in range(n_diff_steps):
-            out = fn(x, ts - i, CPU_SAMPLE_ROWS)
-            x = 0.9 * x + 0.1 * out.permute(0, 2, 1).unsqueeze(2)   # sampler arithmetic is negligible next to the model
+        od.ddim_sample_loop(fn, noise, skip_timesteps=1000 - n_diff_steps)
         dt = time.perf_counter() - t0
     per_step_full_batch = dt / n_diff_steps * (w["B"] / CPU_SAMPLE_ROWS)
     return w["B"] * w["T"] / (per_step_full_batch * 1000), dt
 
 
+class ReferenceLoop:
+    """The UNMODIFIED reference on this box: oracle/_ref (byte-for-byte view written by oracle/build_ref.py) imported
+    through oracle/ref_harness.py's shims (stand-in fairseq conv stack of the published geometry, scratch cwd).  One call =
+    `k` diffusion steps of the reference's own `ddim_sample_loop` (skip_timesteps = N - k: the last k indices of the
+    1000-step schedule; per-step cost is shape-static) with ClassifierFreeSampleModel and RAW 48 kHz audio, i.e. including
+    the per-call `encode_audio` the reference pays twice per step (model/diffusion.py:355-358)."""
+
+    def __init__(self, device: str, batch: int, fmt: str = "pose"):
+        from oracle import ref_harness as RH
+        from audio2photoreal_b200.weights import model_dims, synthetic_state_dict
+        w = WORKLOAD if fmt == "pose" else FACE_WORKLOAD
+        self.w, self.B, self.dev = w, batch, torch.device(device)
+        sd = synthetic_state_dict(model_dims(fmt, w["layers"], w["heads"]), seed=1)
+        self.ref, self.args, model, self.diffusion = RH.build_reference(fmt, w["layers"], w["heads"], w["respacing"], sd, device=device)
+        self.model = self.ref.cfg.ClassifierFreeSampleModel(model).to(self.dev).eval()
+        g = torch.Generator().manual_seed(10)
+        T = w["T"]
+        self.y = {"audio": (0.1 * torch.randn(batch, T * 1600, 2, generator=g)).to(self.dev),
+                  "keyframes": torch.randn(batch, len(range(0, T, 30)), 104, generator=g).to(self.dev),
+                  "mask": torch.ones(batch, 1, 1, T, dtype=torch.bool, device=self.dev),
+                  "scale": torch.full((batch,), w["guidance"], device=self.dev)}
+        self.noise = torch.randn(batch, w["C"], 1, T, generator=g).to(self.dev)
+        self.n = self.diffusion.num_timesteps
+        if self.dev.type == "cuda":
+            torch.backends.cuda.matmul.allow_tf32 = False      # the reference never enables TF32 (SURVEY 2a)
+            torch.backends.cudnn.allow_tf32 = False
+        else:
+            import contextlib
+            self._cuda_shim = True
+
+    def run(self, k: int) -> float:
+        """seconds for k diffusion steps (wall clock; device-synchronised on CUDA)"""
+        import contextlib
+        shim = contextlib.nullcontext()
+        if self.dev.type != "cuda":       # model/diffusion.py:321 hard-codes .cuda(): neutralised for the CPU arm only
+            old = torch.Tensor.cuda
+
+            @contextlib.contextmanager
+            def _s():
+                torch.Tensor.cuda = lambda t, *a, **kk: t
+                try:
+                    yield
+                finally:
+                    torch.Tensor.cuda = old
+            shim = _s()
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.no_grad(), shim:
+            out = self.diffusion.ddim_sample_loop(self.model, (self.B, self.w["C"], 1, self.w["T"]), noise=self.noise,
+                                                  clip_denoised=False, model_kwargs={"y": dict(self.y)},
+                                                  skip_timesteps=self.n - k, init_image=None, progress=False)
+        if self.dev.type == "cuda":
+            torch.cuda.synchronize()
+        assert torch.isfinite(out).all()
+        return time.perf_counter() - t0
+
+    def frames_per_s(self, k: int, reps: int = 1):
+        ts = [self.run(k) for _ in range(reps)]
+        t = float(np.median(ts))
+        return self.B * self.w["T"] / (t / k * self.n), t
+
+
+def reference_view_available() -> bool:
+    try:
+        from oracle import ref_harness as RH
+        return RH.reference_available()
+    except Exception:
+        return False
+
+
+def host_threads() -> int:
+    return min(os.cpu_count() or 1, 32)    # torch CPU GEMMs of this size stop scaling (and regress) beyond ~32 threads
+
+
+def cpu_baseline(fmt: str = "pose"):
+    """cpu_baseline object of the bench line: bounded sample (1 warm-up + 2 timed diffusion steps of all 8 rows, ~10-30 s)."""
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    w = WORKLOAD if fmt == "pose" else FACE_WORKLOAD
+    if reference_view_available():
+        rl = ReferenceLoop("cpu", w["B"], fmt)
+        rl.run(1)
+        v, t = rl.frames_per_s(2)
+        return {"value": v, "unit": UNIT, "cores": threads, "kind": "reference",
+                "sample": f"2 of {rl.n} diffusion steps (after 1 warm-up step) of all {w['B']} rows through the reference's own "
+                          f"ddim_sample_loop + ClassifierFreeSampleModel + FiLMTransformer (oracle/_ref; raw 48 kHz audio, stand-in "
+                          f"wav2vec conv stack, encode_audio paid per call like the reference) in {t:.1f}s, scaled x{rl.n}/2"}
+    v, dt = cpu_port_frames_per_s(CPU_SAMPLE_STEPS, threads)
+    return {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{CPU_SAMPLE_STEPS} of 1000 diffusion steps of {CPU_SAMPLE_ROWS} of the 8 batch rows (oracle port, synthetic features) "
+                      f"in {dt:.1f}s, scaled x1000/{CPU_SAMPLE_STEPS} x 8/{CPU_SAMPLE_ROWS}"}
+
+
+def gpu_baseline(batch: int, k: int = 10):
+    """The reference GPU path: unmodified reference loop on this B200, stock PyTorch fp32."""
+    if not reference_view_available():
+        return None
+    try:
+        rl = ReferenceLoop("cuda", batch)
+        rl.run(2)
+        v, t = rl.frames_per_s(k, reps=3)
+        del rl
+        torch.cuda.empty_cache()
+        return {"value": v, "unit": UNIT, "kind": "reference", "batch": batch,
+                "sample": f"median of 3 x {k} of 1000 diffusion steps (after 2 warm-up steps) of the reference's own loop on cuda, fp32, "
+                          f"TF32 off, batch {batch} + CFG, raw-audio encode per call, {t:.2f}s per {k} steps, scaled x1000/{k}"}
+    except Exception as e:       # never let the baseline leg take the bench line down
+        return {"value": None, "unit": UNIT, "kind": "reference", "batch": batch, "error": repr(e)[:200]}
+
+
 def run_reference_arm(a):
+    """--impl reference: every bench "step" is a bounded sample (ONE diffusion step of all 8 rows through the reference's own
+    public API on the host cores); value = B*T / (median step time x 1000 steps)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = min(os.cpu_count() or 1, 32)   # torch CPU GEMMs of this size stop scaling (and regress) beyond ~32 threads
-    K_diff = 5
-    vals = []
-    for _ in range(max(1, a.steps)):
-        v, dt = cpu_port_frames_per_s(K_diff, threads)
-        vals.append(v)
-    v = float(np.median(vals))
+    threads = host_threads()
+    torch.set_num_threads(threads)
+    fmt = "face" if a.workload == "face" else "pose"
+    w = WORKLOAD if fmt == "pose" else FACE_WORKLOAD
+    if reference_view_available():
+        rl = ReferenceLoop("cpu", w["B"], fmt)
+        for _ in range(max(1, min(a.warmup, 2))):
+            rl.run(1)
+        ts = [rl.run(1) for _ in range(max(1, a.steps))]
+        t = float(np.median(ts))
+        v = w["B"] * w["T"] / (t * rl.n)
+        kind = "reference"
+        sample = (f"each of the {a.steps} timed steps = 1 of {rl.n} diffusion steps of all {w['B']} rows through the reference's own "
+                  f"ddim_sample_loop (oracle/_ref, raw audio, encode_audio per call), median {t:.2f}s, scaled x{rl.n}")
+    else:
+        vals = [cpu_port_frames_per_s(5, threads)[0] for _ in range(max(1, a.steps))]
+        v, kind = float(np.median(vals)), "port"
+        sample = "oracle port: 5 of 1000 steps of 2 of 8 rows, scaled (oracle/_ref absent)"
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * WORKLOAD["B"] * WORKLOAD["T"] / v, "higher_is_better": True,
+        "impl": "reference", "metric": METRIC if fmt == "pose" else FACE_METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * w["B"] * w["T"] / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "pose ddim/1000-step CFG g=2.0 B=8 T=600 L=6 D=256 (BASELINE configs[1])"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{K_diff} of 1000 diffusion steps of {CPU_SAMPLE_ROWS} of the 8 batch rows (CFG, T=600, S=1998), "
-                                   f"scaled x1000/{K_diff} x 8/{CPU_SAMPLE_ROWS}; torch CPU fp32, conditioning recomputed per call "
-                                   f"like the reference"},
+        "config": {"workload": workload_name(fmt, w["B"], True)},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -176,12 +314,24 @@ def main():
                     help="secondary measurement (SURVEY 8d, config 2 'no-CFG variant'): the bare denoiser, one forward per step; "
                          "not the benchmark line")
     ap.add_argument("--dump-out", default=None, help="debug only: save the result of the last timed loop as .npy")
-    ap.add_argument("--split-terms", type=int, default=2, help="0: exact-fp32 FFMA arm; 2 (default, fused chain kernels) | 3: split-bf16 tcgen05 arms")
+    ap.add_argument("--split-terms", type=int, default=None, help="0: exact-fp32 FFMA arm; 2 (pose default, fused chain kernels) | 3 (face default): split-bf16 tcgen05 arms")
+    ap.add_argument("--workload", default="pose", choices=["pose", "face"],
+                    help="pose = BASELINE configs[1] (the contract line); face = configs[3] (ddim500, g=10, 16 rows/GPU), secondary")
+    ap.add_argument("--no-config3", action="store_true", help="skip the extra global-batch-32 (configs[2], strong-scaling) measurement")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU leg")
     a = ap.parse_args()
-    global SPLIT_TERMS
-    SPLIT_TERMS = a.split_terms
+    global SPLIT_TERMS, WORKLOAD, METRIC
+    face = a.workload == "face"
+    SPLIT_TERMS = a.split_terms if a.split_terms is not None else (3 if face else 2)
     if a.impl == "reference":
         return run_reference_arm(a)
+    if face:
+        if a.batch == WORKLOAD["B"]:
+            a.batch = FACE_WORKLOAD["B"]
+        if a.diffusion_steps == 1000:
+            a.diffusion_steps = 500
+        WORKLOAD, METRIC = FACE_WORKLOAD, FACE_METRIC
+        a.no_config3 = True
 
     import torch.distributed as dist
     from audio2photoreal_b200 import _lib
@@ -201,7 +351,10 @@ def main():
     w = WORKLOAD
     B, T, S = a.batch, w["T"], w["S"]
     resp = "" if a.diffusion_steps == 1000 else f"ddim{a.diffusion_steps}"
-    model, sampler = create_model_and_diffusion(model_args(resp), "test")
+    margs = model_args(resp)
+    if face:
+        margs.data_format, margs.add_frame_cond = "face", None
+    model, sampler = create_model_and_diffusion(margs, "test")
     load_model(model, synthetic_state_dict(model.dims, seed=1))
     model = model.to(dev).eval()
     cfg = model if a.no_cfg else CFGDenoiser(model)
@@ -210,23 +363,30 @@ def main():
     shape = (B, w["C"], 1, T)
 
     # per-rank inputs (rank-dependent seed: independent rows on every GPU = weak scaling)
-    y_host, noise_host = synth_inputs(B, T, S, seed=10 + rank, pin=True)
-    y_dev = {k: v.to(dev) for k, v in y_host.items()}
-    noise_dev = noise_host.to(dev)
+    def make_loops(Bl, n_rows_global, seed):
+        y_host, noise_host = synth_inputs(Bl, T, S, seed=seed, pin=True)
+        y_dev = {k: v.to(dev) for k, v in y_host.items()}
+        noise_dev = noise_host.to(dev)
+        shp = (Bl, w["C"], 1, T)
 
-    def loop_resident():
-        yy = dict(y_dev)
-        model._cond_sig = None          # drop the conditioning cache: the one-time precompute is part of every loop
-        res = sampler.ddim_sample_loop(cfg, shape, noise=noise_dev, clip_denoised=False, model_kwargs={"y": yy},
-                                       advance_rng=False)
-        return all_gather_rows(res, B * world)     # the one collective of the path (no-op at world size 1)
+        def loop_resident():
+            yy = dict(y_dev)
+            model._cond_sig = None          # drop the conditioning cache: the one-time precompute is part of every loop
+            res = sampler.ddim_sample_loop(cfg, shp, noise=noise_dev, clip_denoised=False, model_kwargs={"y": yy},
+                                           advance_rng=False)
+            return all_gather_rows(res, n_rows_global)     # the one collective of the path (no-op at world size 1)
 
-    def loop_e2e():
-        yy = {k: v.to(dev, non_blocking=True) for k, v in y_host.items()}
-        nz = noise_host.to(dev, non_blocking=True)
-        model._cond_sig = None
-        res = sampler.ddim_sample_loop(cfg, shape, noise=nz, clip_denoised=False, model_kwargs={"y": yy}, advance_rng=False)
-        return all_gather_rows(res, B * world).cpu()
+        def loop_e2e():
+            yy = {k: v.to(dev, non_blocking=True) for k, v in y_host.items()}
+            nz = noise_host.to(dev, non_blocking=True)
+            model._cond_sig = None
+            res = sampler.ddim_sample_loop(cfg, shp, noise=nz, clip_denoised=False, model_kwargs={"y": yy}, advance_rng=False)
+            return all_gather_rows(res, n_rows_global).cpu()
+        loop_e2e.is_e2e = True
+        h2d = sum(v.numel() * v.element_size() for v in y_host.values()) + noise_host.numel() * 4
+        return loop_resident, loop_e2e, h2d, y_dev
+
+    loop_resident, loop_e2e, h2d, y_dev = make_loops(B, B * world, 10 + rank)
 
     def barrier():
         if world > 1:
@@ -244,7 +404,7 @@ def main():
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
         ms = max(e0.elapsed_time(e1), 0.0)
-        ms = max(ms, wall * 1e3) if fn is loop_e2e else ms    # e2e includes the host-side result copy
+        ms = max(ms, wall * 1e3) if getattr(fn, "is_e2e", False) else ms    # e2e includes the host-side result copy
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,13 +428,33 @@ def main():
     frames = world * B * T
     value = frames / (ms_step / 1e3)
     e2e_value = frames / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in y_host.values()) + noise_host.numel() * 4
     d2h = out_h.numel() * 4
+
+    # ---- BASELINE configs[2] (north-star headline): GLOBAL batch 32 + CFG sharded over the N ranks = strong scaling of one job
+    config3 = None
+    if not a.no_config3 and not a.no_cfg:
+        from audio2photoreal_b200.dist import shard_range
+        lo, hi = shard_range(CONFIG3_GLOBAL_BATCH, world, rank)
+        l3, l3e, h2d3, _ = make_loops(hi - lo, CONFIG3_GLOBAL_BATCH, 100 + rank)
+        l3()
+        k3 = max(2, min(a.steps, 5))
+        ms3, out3 = timed(l3, k3)
+        ms3e, out3h = timed(l3e, 2)
+        assert out3.shape[0] == CONFIG3_GLOBAL_BATCH and torch.isfinite(out3).all()
+        f3 = CONFIG3_GLOBAL_BATCH * T
+        config3 = {"workload": f"pose body diffusion + CFG g=2.0, {n_diff} steps, T=600, GLOBAL batch {CONFIG3_GLOBAL_BATCH} sharded over {world} GPU(s) "
+                               f"({hi - lo} rows on rank 0), audio K/V cached across steps (BASELINE configs[2])",
+                   "scaling": "strong", "global_batch": CONFIG3_GLOBAL_BATCH, "n_gpus": world, "steps": k3,
+                   "value": f3 / (ms3 / 1e3), "unit": UNIT, "ms_per_step": ms3,
+                   "e2e": {"value": f3 / (ms3e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d3), "d2h_bytes_per_step": int(out3h.numel() * 4)}}
+        del l3, l3e, out3, out3h
 
     roofline, cpu_base = None, None
     if rank == 0:
         # ---- live per-kernel measurement (CUDA events around every launch of one denoiser evaluation)
         lib = _lib.load()
+        model._cond_sig = None
+        model.prepare(dict(y_dev), B, T, dev)      # conditioning of the contract workload (config3 above changed it)
         ncat = 9
         ms_cat = (C.c_float * ncat)()
         n_cat = (C.c_int64 * ncat)()
@@ -313,9 +493,9 @@ def main():
         fam_attn, fam_chain = acc[3] + acc[4] + acc[5], acc[2] + acc[6]
         dom = (4 if fam_attn >= fam_chain else int(np.argmax([0, 0, acc[2], 0, 0, 0, acc[6]]))) if SPLIT_TERMS == 2 else int(np.argmax(acc))
         R = nbr * B        # rows of one step (both branches); per-launch figures below divide by the launch counts
-        D, L = 256, w["layers"]
+        D, L = model.dims.D, w["layers"]
         # per-launch algorithmic FLOPs of each category (attention cores exactly; linears = category total / launches)
-        lin_proj = (6 * T * D * D + 2 * T * D * D + 4 * T * D * D + 4 * T * D * D) * R * L
+        lin_proj = (16 if w["fmt"] == "pose" else 12) * T * D * D * R * L
         lin_ffn = 4 * T * D * 1024 * R * L
         if SPLIT_TERMS == 2:   # fused chain arm: PROJ = {sa_out+q, ca_out+q} per layer, FFN = {out+ffn1, ffn2+next qkv} per layer
             lin_proj, lin_ffn = 8 * T * D * D * R * L, (2 * T * D * D + 4 * T * D * 1024 + 6 * T * D * D) * R * L
@@ -349,32 +529,40 @@ def main():
                                      "timed alone; in the loop the forwards overlap" if two_branch else "both CFG branches (2B rows) per launch"),
                     "note": ("algorithmic FLOPs (one product per MAC) over measured time; the split-bf16 arm spends %d tensor-core "
                              "products per MAC for fp32-level parity" % {0: 0, 1: 1, 2: 3, 3: 6}[SPLIT_TERMS])}
+        gpu_base = None
+        if not a.no_gpu_baseline and world == 1 and not face and not a.no_cfg:
+            gpu_base = {"configs[1]": gpu_baseline(B)}
+            if config3 is not None:
+                gpu_base["configs[2]"] = gpu_baseline(CONFIG3_GLOBAL_BATCH)
+                gb = gpu_base["configs[2]"]
+                if gb and gb.get("value"):
+                    config3["vs_gpu_baseline"] = config3["value"] / gb["value"]
         if not a.no_cpu_baseline:
-            threads = min(os.cpu_count() or 1, 32)
-            v, dt = cpu_port_frames_per_s(CPU_SAMPLE_STEPS, threads)
-            cpu_base = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{CPU_SAMPLE_STEPS} of 1000 diffusion steps of {CPU_SAMPLE_ROWS} of the 8 batch rows (CFG, T=600, S=1998) "
-                                  f"in {dt:.1f}s, scaled x1000/{CPU_SAMPLE_STEPS} x 8/{CPU_SAMPLE_ROWS}"}
-        f_fwd = flops_per_sample_forward()
+            cpu_base = cpu_baseline(w["fmt"])
+        f_fwd = flops_per_sample_forward(T=T, S=S + 2, S2=20, D=model.dims.D, L=L, FF=1024, C=w["C"], fmt=w["fmt"])
+        if config3 is not None:
+            config3["roofline_step_level"] = {"achieved": f_fwd * 2 * CONFIG3_GLOBAL_BATCH * n_diff / (config3["ms_per_step"] * 1e-3) / 1e12,
+                                              "unit": "TFLOP/s"}
+            config3["roofline_step_level"]["frac_of_sustained"] = config3["roofline_step_level"]["achieved"] / peaks.get("bf16_tflops_sustained", peak_tf)
         # whole-step view beside the per-launch one: the concurrent forwards share the machine, so the step as a whole sustains
         # more than any single launch timed alone
         step_tf = f_fwd * nbr * B * n_diff / (ms_step * 1e-3) / 1e12
-        roofline["step_level"] = {"achieved": step_tf, "frac": step_tf / peak_tf, "concurrent_forwards": len(units),
+        roofline["step_level"] = {"achieved": step_tf, "frac": step_tf / peak_tf,
+                                  "frac_of_sustained": step_tf / peaks.get("bf16_tflops_sustained", peak_tf), "concurrent_forwards": len(units),
                                   "note": "algorithmic FLOPs of a whole loop / loop time on this GPU"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if SPLIT_TERMS == 0 else f"bf16x{SPLIT_TERMS} split (fp32-equivalent), fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": f"pose body diffusion, {n_diff} steps, T={T}, C=104, batch {B}/GPU, {'NO CFG (bare denoiser)' if a.no_cfg else 'CFG g=2.0'}, "
-                                   f"L=6 D=256 H=8, synthetic wav2vec features [B,{S},1024] (BASELINE configs[1])",
+            "config": {"workload": workload_name(w["fmt"], B, not a.no_cfg, n_diff),
                        "global_batch": B * world, "parallelism": f"batch-sharded x{world}, 1 all-gather",
                        "l2": "inputs_larger_than_l2 (K/V caches %d MB + activations per step)" % (B * 25),
                        "algorithmic_gflop_per_loop": f_fwd * nbr * B * world * n_diff / 1e9},
             "clocks": clk, "gpu_launches": int(launches),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": ms_e2e},
-            "roofline": roofline, "cpu_baseline": cpu_base,
+            "roofline": roofline, "cpu_baseline": cpu_base, "gpu_baseline": gpu_base, "config3_strong": config3,
             "model_tflops": f_fwd * nbr * B * world * n_diff / (ms_step * 1e-3) / 1e12,
         }
         print(json.dumps(line), flush=True)

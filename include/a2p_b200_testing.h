@@ -1,4 +1,5 @@
-/* Test / measurement hooks of liba2p_b200.so (NOT part of the drop-in ABI; used by tests/ and scripts/). */
+/* Test / measurement hooks, built into liba2p_b200_testing.so (NOT part of the drop-in ABI and NOT in the product
+ * library liba2p_b200.so; used by tests/ and scripts/). */
 #ifndef A2P_B200_TESTING_H
 #define A2P_B200_TESTING_H
 #include <stddef.h>
@@ -6,6 +7,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+
+/* message of the last failed a2p_test_* call of this thread */
+const char* a2p_test_last_error(void);
 
 /* C[M,N] = A[M,K] * W[taps][N][K]^T (+ bias) with the split-bf16 tcgen05 GEMM (terms 1..3); fp32 in/out.
  * scratch holds the bf16 planes (size from a2p_test_tc_gemm_scratch_bytes).  Runs `iters` timed launches

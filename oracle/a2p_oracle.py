@@ -244,19 +244,35 @@ class OracleDiffusion:
         return torch.from_numpy(arr)[i].float().to(like.dtype).expand(like.shape) if like.dtype == torch.float32 \
             else torch.from_numpy(arr)[i].to(like.dtype).expand(like.shape)
 
-    def _x0(self, model_fn, x, i):
+    def _x0(self, model_fn, x, i, clip_denoised=False):
         ts = torch.full((x.shape[0],), self.timestep_map[i], dtype=torch.long)  # _WrappedModel respace.py:140-145
         out = model_fn(x, ts)                                                  # [B,T,C]
+        if clip_denoised:
+            out = out.clamp(-1, 1)                                             # process_xstart, gaussian_diffusion.py:305-310
         return out.permute(0, 2, 1).unsqueeze(2)                               # gaussian_diffusion.py:312-313
 
-    def ddim_sample_loop(self, model_fn, x_T: Tensor, eta: float = 0.0, noise_tape: Optional[Sequence[Tensor]] = None):
-        """ddim_sample_loop(_progressive) + ddim_sample, clip_denoised=False.  gaussian_diffusion.py:667-718,815-936.
+    def _start(self, x_T: Tensor, skip_timesteps: int, init_image: Optional[Tensor]):
+        """noise -> first image + index list (gaussian_diffusion.py:617-632,890-905): skip_timesteps drops the noisiest
+        indices; with an init_image (zeros when only skip_timesteps is given) the start is q_sample(init, t0, noise)."""
+        img = x_T
+        if skip_timesteps and init_image is None:
+            init_image = torch.zeros_like(img)
+        indices = list(range(self.num_timesteps - skip_timesteps))[::-1]
+        if init_image is not None:
+            i0 = indices[0]   # q_sample, gaussian_diffusion.py:215-233
+            img = self._ext(np.sqrt(self.alphas_cumprod), i0, img) * init_image + \
+                self._ext(np.sqrt(1.0 - self.alphas_cumprod), i0, img) * img
+        return img, indices
+
+    def ddim_sample_loop(self, model_fn, x_T: Tensor, eta: float = 0.0, noise_tape: Optional[Sequence[Tensor]] = None,
+                         clip_denoised: bool = False, skip_timesteps: int = 0, init_image: Optional[Tensor] = None):
+        """ddim_sample_loop(_progressive) + ddim_sample.  gaussian_diffusion.py:667-718,815-936.
         Returns the last pred_xstart (:862)."""
-        x = x_T
+        x, indices = self._start(x_T, skip_timesteps, init_image)
         pred = None
         tape = list(noise_tape) if noise_tape is not None else None
-        for i in range(self.num_timesteps - 1, -1, -1):
-            pred = self._x0(model_fn, x, i)
+        for i in indices:
+            pred = self._x0(model_fn, x, i, clip_denoised)
             eps = (self._ext(self.sqrt_recip_alphas_cumprod, i, x) * x - pred) / self._ext(
                 self.sqrt_recipm1_alphas_cumprod, i, x)
             ab = self._ext(self.alphas_cumprod, i, x)
@@ -269,13 +285,14 @@ class OracleDiffusion:
             x = mean_pred
         return pred
 
-    def p_sample_loop(self, model_fn, x_T: Tensor, noise_tape: Sequence[Tensor], const_noise: bool = False):
+    def p_sample_loop(self, model_fn, x_T: Tensor, noise_tape: Sequence[Tensor], const_noise: bool = False,
+                      clip_denoised: bool = False, skip_timesteps: int = 0, init_image: Optional[Tensor] = None):
         """p_sample_loop with the upstream-faithful repair of p_sample; FIXED_SMALL variance.
         gaussian_diffusion.py:243-246,289-303,434-477,525-665.  Returns final sample (:590)."""
-        x = x_T
+        x, indices = self._start(x_T, skip_timesteps, init_image)
         tape = list(noise_tape)
-        for i in range(self.num_timesteps - 1, -1, -1):
-            pred = self._x0(model_fn, x, i)
+        for i in indices:
+            pred = self._x0(model_fn, x, i, clip_denoised)
             mean = self._ext(self.posterior_mean_coef1, i, x) * pred + self._ext(self.posterior_mean_coef2, i, x) * x
             noise = tape.pop(0)
             if const_noise:

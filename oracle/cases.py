@@ -36,6 +36,11 @@ CASES: Dict[str, Case] = {c.name: c for c in [
     Case("pose_full", "pose", 6, 8, 1, 600, 1998, seed=7, wseed=8),
     Case("face_cfg1", "face", 8, 8, 1, 64, 211, guidance=10.0, seed=9, wseed=10),   # BASELINE config 1 geometry
     Case("face_full", "face", 8, 8, 1, 600, 1998, guidance=10.0, seed=11, wseed=12),
+    # smallest geometry that takes the fused row-chain arm (T >= 128, T % 8 == 0): __graft_entry__.smoke()
+    Case("pose_smoke", "pose", 2, 8, 2, 160, 398, seed=15, wseed=16, masked=True),
+    # the BENCHMARKED configuration (BASELINE configs[1]: pose, T=600, all 1000 steps, CFG) at a batch that takes the
+    # loop's row-group cut (4 concurrent forwards, batch-row offsets b0 > 0)
+    Case("pose_full_b4", "pose", 6, 8, 4, 600, 1998, respacing="", seed=13, wseed=14),
 ]}
 
 

@@ -101,7 +101,7 @@ def golden_layer(name):
     print(f"layer_{name}.npz written")
 
 
-def golden_loop(name, respacing, kind, eta=0.0):
+def golden_loop(name, respacing, kind, eta=0.0, check_oracle=True):
     case = CASES[name]
     ref, model, diffusion, sd = _ref_model(case, respacing)
     n = diffusion.num_timesteps
@@ -125,22 +125,102 @@ def golden_loop(name, respacing, kind, eta=0.0):
             with RH.repaired_p_sample(ref.gd, inp["noise_tape"]):
                 res = diffusion.p_sample_loop(cfg, shape, noise=inp["x"], clip_denoised=False, model_kwargs={"y": y})
     print(f"   reference {kind} loop {name}/{respacing or 'full'}: {time.time() - t0:.1f}s")
+    tag = f"{kind}_{name}_{respacing or 'full'}" + (f"_eta{eta}" if eta else "")
+    np.savez_compressed(os.path.join(GOLD, f"loop_{tag}.npz"), result=res.numpy())
+    print(f"loop_{tag}.npz written")
+    if not check_oracle:
+        return
+    t0 = time.time()
     od = O.OracleDiffusion(respacing)
     fn = lambda x, ts: O.cfg_forward(sd, case.fmt, case.H, x, ts, inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
     if kind == "ddim":
         ores = od.ddim_sample_loop(fn, inp["x"], eta=eta, noise_tape=inp["noise_tape"])
     else:
         ores = od.p_sample_loop(fn, inp["x"], inp["noise_tape"])
-    tag = f"{kind}_{name}_{respacing or 'full'}" + (f"_eta{eta}" if eta else "")
+    print(f"   oracle {kind} loop {name}/{respacing or 'full'}: {time.time() - t0:.1f}s")
     _close(ores, res, tag, atol=3e-4, rtol=1e-4)
-    np.savez_compressed(os.path.join(GOLD, f"loop_{tag}.npz"), result=res.numpy())
-    print(f"loop_{tag}.npz written")
+
+
+def golden_loop_variants():
+    """Sampler keyword variants of the callers' API: clip_denoised=True, skip_timesteps, init_image on the
+    DDIM loop; const_noise=True + clip + skip (zeros init image) on the repaired ancestral loop
+    (gaussian_diffusion.py:305-310,617-632,890-905; upstream-MDM const_noise)."""
+    name = "pose_small"
+    case = CASES[name]
+    out = {}
+    for kind, resp, kw in [("ddim", "ddim10", dict(clip_denoised=True, skip_timesteps=3, init_image="randn")),
+                           ("ancestral", "10", dict(clip_denoised=True, skip_timesteps=2, init_image=None, const_noise=True))]:
+        ref, model, diffusion, sd = _ref_model(case, resp)
+        n = diffusion.num_timesteps - kw["skip_timesteps"]
+        inp = make_inputs(case, n_noise=n)
+        init = None
+        if kw["init_image"] == "randn":
+            init = 0.5 * torch.from_numpy(np.random.RandomState(77).standard_normal(tuple(inp["x"].shape)).astype(np.float32))
+        cfg = ref.cfg.ClassifierFreeSampleModel(model)
+        y = {"audio": torch.zeros(case.B, 8, 2), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"], "scale": inp["scale"]}
+        shape = tuple(inp["x"].shape)
+        fn = lambda x, ts: O.cfg_forward(sd, case.fmt, case.H, x, ts, inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
+        od = O.OracleDiffusion(resp)
+        with torch.no_grad(), RH.synthetic_features(model, inp["feats"]):
+            if kind == "ddim":
+                res = diffusion.ddim_sample_loop(cfg, shape, noise=inp["x"], clip_denoised=True, model_kwargs={"y": y},
+                                                 skip_timesteps=kw["skip_timesteps"], init_image=init)
+                ores = od.ddim_sample_loop(fn, inp["x"], clip_denoised=True, skip_timesteps=kw["skip_timesteps"], init_image=init)
+            else:
+                with RH.repaired_p_sample(ref.gd, inp["noise_tape"]):
+                    res = diffusion.p_sample_loop(cfg, shape, noise=inp["x"], clip_denoised=True, model_kwargs={"y": y},
+                                                  skip_timesteps=kw["skip_timesteps"], const_noise=True)
+                ores = od.p_sample_loop(fn, inp["x"], inp["noise_tape"], const_noise=True, clip_denoised=True,
+                                        skip_timesteps=kw["skip_timesteps"])
+        _close(ores, res, f"variants/{kind}", atol=3e-4, rtol=1e-4)
+        out[kind] = res.numpy()
+    np.savez_compressed(os.path.join(GOLD, "loop_variants_pose_small.npz"), **out)
+    print("loop_variants_pose_small.npz written")
+
+
+def golden_caller():
+    """The UNMODIFIED caller: sample/generate.py `_setup_model` + `_run_single_diffusion` on CPU with raw audio (the frozen
+    extractor runs inside every denoiser call, model/diffusion.py:355-358) -> tests/golden/caller_pose.npz."""
+    import tempfile
+    from oracle import caller_case as CC
+    ref = RH.import_reference()
+    import sample.generate as gen
+    tmp = tempfile.mkdtemp(prefix="a2p_caller_")
+    path = os.path.join(tmp, "model000000.pt")
+    CC.write_checkpoint(path)
+    args = CC.caller_args(path, "cpu")
+    gt, model_kwargs = CC.caller_inputs()
+    old_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self          # shim 2 (CPU): model/diffusion.py:321
+    old_randn = torch.randn
+    first = [CC.initial_noise()]
+    try:
+        with RH._cwd(ref.scratch):
+            model, diffusion = gen._setup_model(args)
+        model_kwargs["y"] = {k: v.to(args.device) if torch.is_tensor(v) else v for k, v in model_kwargs["y"].items()}
+        torch.randn = lambda *a, **k: first.pop(0) if first else old_randn(*a, **k)   # the loop's initial noise (noise=None)
+        sample, audio, keyframes, gt_seq = gen._run_single_diffusion(args, model_kwargs, diffusion, model, CC.inv_transform, gt)
+    finally:
+        torch.Tensor.cuda = old_cuda
+        torch.randn = old_randn
+    np.savez_compressed(os.path.join(GOLD, "caller_pose.npz"), sample=sample.numpy(), keyframes=np.asarray(keyframes),
+                        gt=gt_seq.numpy(), audio_sha1=hashlib.sha1(np.ascontiguousarray(audio).tobytes()).hexdigest())
+    print("caller_pose.npz written", tuple(sample.shape), float(sample.abs().max()))
 
 
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     os.makedirs(GOLD, exist_ok=True)
+    if "caller" in sys.argv:
+        golden_caller()
+        return
+    if "variants" in sys.argv:
+        golden_loop_variants()
+        return
+    if "loop1000" in sys.argv:     # the benchmarked configuration: all 1000 steps, B = 4, CFG (minutes of CPU time)
+        golden_loop("pose_full_b4", "", "ddim", check_oracle="--no-oracle" not in sys.argv)
+        return
     golden_schedule()
     for n in ["pose_small", "pose_small_h4", "face_small", "pose_full", "face_full"]:
         golden_forward(n)

@@ -29,7 +29,11 @@ from argparse import Namespace
 import torch
 import torch.nn as nn
 
-REF_ROOT = "/root/reference"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree itself in the build container; on the GPU box the pruned byte-for-byte view that
+# oracle/build_ref.py wrote into oracle/_ref (git-ignored, travels with the snapshot)
+REF_ROOT = "/root/reference" if os.path.isdir("/root/reference/diffusion") and not os.environ.get("A2P_FORCE_REF_VIEW") \
+    else os.path.join(_HERE, "_ref")
 
 
 def reference_available() -> bool:
@@ -114,19 +118,19 @@ def _cwd(path):
 
 
 def make_args(data_format: str, layers: int, heads: int, timestep_respacing: str, max_seq_length: int = 600,
-              device="cpu") -> Namespace:
+              device="cpu", **extra) -> Namespace:
     return Namespace(
         data_format=data_format, add_frame_cond=1 if data_format == "pose" else None,
         max_seq_length=max_seq_length, layers=layers, heads=heads, not_rotary=False, unconstrained=False,
         device=device, timestep_respacing=timestep_respacing, noise_schedule="cosine", sigma_small=True,
-        lambda_vel=0.0, model_path="synthetic/model.pt", resume_trans=None,
+        lambda_vel=0.0, model_path="synthetic/model.pt", resume_trans=None, **extra,
     )
 
 
-def build_reference(data_format: str, layers: int, heads: int, timestep_respacing: str, state_dict=None):
-    """create_model_and_diffusion (utils/model_util.py:41-46) + load_model + CFG wrapper, on CPU."""
+def build_reference(data_format: str, layers: int, heads: int, timestep_respacing: str, state_dict=None, device="cpu"):
+    """create_model_and_diffusion (utils/model_util.py:41-46) + load_model + CFG wrapper (CPU unless `device` says cuda)."""
     ref = import_reference()
-    args = make_args(data_format, layers, heads, timestep_respacing)
+    args = make_args(data_format, layers, heads, timestep_respacing, device=device)
     with _cwd(ref.scratch):
         if data_format == "face":
             lip_path = os.path.join(ref.scratch, "assets", "iter-0200000.pt")

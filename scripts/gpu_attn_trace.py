@@ -2,7 +2,7 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from audio2photoreal_b200 import _lib
-lib = _lib.load()
+lib = _lib.load_testing()
 vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
 lib.a2p_test_tc_attention_scratch_bytes.argtypes = [i32] * 5
 lib.a2p_test_tc_attention_scratch_bytes.restype = sz
@@ -16,7 +16,7 @@ O = torch.zeros(R, T, D, device="cuda")
 nb = lib.a2p_test_tc_attention_scratch_bytes(R, T, D, S, nx)
 scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
 ms = C.c_float()
-_lib.check(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(), Vx.data_ptr(),
+_lib.check_testing(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(), Vx.data_ptr(),
                                      O.data_ptr(), scratch.data_ptr(), nb, -1, C.byref(ms), torch.cuda.current_stream().cuda_stream))
 torch.cuda.synchronize()
 tr = O.view(-1)[: 64 * 16 * 2].view(torch.int64).view(64, 16).cpu()

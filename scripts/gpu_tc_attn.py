@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from audio2photoreal_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_testing()
 vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
 lib.a2p_test_tc_attention_scratch_bytes.argtypes = [i32] * 5
 lib.a2p_test_tc_attention_scratch_bytes.restype = sz
@@ -23,7 +23,7 @@ def run(terms, R, T, D, dh, S, nx, iters=5, qscale=1.0):
     scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
     ms = C.c_float()
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(),
+    _lib.check_testing(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(),
                                          Vx.data_ptr(), O.data_ptr(), scratch.data_ptr(), nb, iters, C.byref(ms), st))
     H = D // dh
     Kf = torch.cat([K, Kx[:, :nx]], 1) if nx else K
@@ -34,7 +34,7 @@ def run(terms, R, T, D, dh, S, nx, iters=5, qscale=1.0):
     err = (O.double() - ref).abs().max().item()
     O2 = torch.empty_like(O)
     ms2 = C.c_float()
-    _lib.check(lib.a2p_test_simt_attention(R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(), Vx.data_ptr(),
+    _lib.check_testing(lib.a2p_test_simt_attention(R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(), Vx.data_ptr(),
                                            O2.data_ptr(), iters, C.byref(ms2), st))
     err2 = (O2.double() - ref).abs().max().item()
     fl = 4.0 * R * T * (S + nx) * D

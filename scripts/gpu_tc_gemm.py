@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from audio2photoreal_b200 import _lib
 
-lib = _lib.load()
+lib = _lib.load_testing()
 vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
 lib.a2p_test_tc_gemm_scratch_bytes.argtypes = [i32] * 4
 lib.a2p_test_tc_gemm_scratch_bytes.restype = sz
@@ -21,7 +21,7 @@ def run(terms, M, N, K, taps=1, dil=0, iters=10):
     scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
     ms = C.c_float()
     st = torch.cuda.current_stream().cuda_stream
-    _lib.check(lib.a2p_test_tc_gemm(terms, M, N, K, taps, dil, A.data_ptr(), W.data_ptr(), bias.data_ptr(), Cc.data_ptr(),
+    _lib.check_testing(lib.a2p_test_tc_gemm(terms, M, N, K, taps, dil, A.data_ptr(), W.data_ptr(), bias.data_ptr(), Cc.data_ptr(),
                                     scratch.data_ptr(), nb, iters, C.byref(ms), st))
     Ad, Wd = A.double(), W.double()
     ref = bias.double().expand(M, N).clone()
@@ -40,7 +40,7 @@ def run(terms, M, N, K, taps=1, dil=0, iters=10):
     C2 = torch.empty(M, N, device="cuda")
     Ws = W.permute(1, 0, 2).reshape(N, taps * K).contiguous()
     ms2 = C.c_float()
-    _lib.check(lib.a2p_test_sgemm(M, N, K, taps, dil, A.data_ptr(), Ws.data_ptr(), bias.data_ptr(), C2.data_ptr(), iters, C.byref(ms2), st))
+    _lib.check_testing(lib.a2p_test_sgemm(M, N, K, taps, dil, A.data_ptr(), Ws.data_ptr(), bias.data_ptr(), C2.data_ptr(), iters, C.byref(ms2), st))
     err2 = (C2.double() - ref).abs().max().item()
     print(f"terms={terms} M={M} N={N} K={K} taps={taps}: tc max|d|={err:.3e} (rel {rel:.2e}) {ms.value*1e3:.1f}us "
           f"{fl/ms.value/1e9:.1f} TF/s alg | ffma max|d|={err2:.3e} {ms2.value*1e3:.1f}us {fl/ms2.value/1e9:.1f} TF/s", flush=True)

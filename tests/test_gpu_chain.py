@@ -22,7 +22,7 @@ CASES = {
 
 def _lib():
     from audio2photoreal_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_testing()
     vp, i32, sz, f32 = C.c_void_p, C.c_int, C.c_size_t, C.c_float
     lib.a2p_test_chain_scratch_bytes.argtypes = [i32] * 4
     lib.a2p_test_chain_scratch_bytes.restype = sz
@@ -54,7 +54,7 @@ def run_case(name, iters=0, seed=0):
     x = x0.clone()
     ms = C.c_float(0.0)
     st = torch.cuda.current_stream().cuda_stream
-    call = lambda xx, it: L.check(lib.a2p_test_chain(
+    call = lambda xx, it: L.check_testing(lib.a2p_test_chain(
         M, T, K0, N1, film_mode, ln_mode, rope, gelu, vjob, out_scale, scale_ncols, A0.data_ptr(), W0.data_ptr(), b0.data_ptr(),
         film.data_ptr(), xx.data_ptr(), lnw.data_ptr(), lnb.data_ptr(), freqs.data_ptr(), W1.data_ptr(), b1.data_ptr(),
         W2.data_ptr(), b2.data_ptr(), Cp.data_ptr(), Vt.data_ptr(), scratch.data_ptr(), nb, it, C.byref(ms), st))

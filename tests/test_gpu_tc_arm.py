@@ -67,9 +67,26 @@ def test_tc_loops_vs_reference_golden(golden_dir, name, resp, terms):
     assert model.launch_count() > 0
 
 
+def test_benchmarked_configuration_1000_steps_vs_reference_golden(golden_dir):
+    """BASELINE configs[1] itself: pose L=6, T=600, S=1998, CFG, ALL 1000 steps (timestep_respacing ''), at B = 4 so that the
+    loop takes its default cut into concurrent forwards (2 CFG branches x 2 row groups, batch-row offsets b0 > 0), strict
+    rtol 1e-3 / atol 1e-4 against the REFERENCE's own ddim_sample_loop output (oracle/make_golden.py loop1000)."""
+    case = CASES["pose_full_b4"]
+    model, cfg, sampler = _build(case, "", 2)
+    assert sampler.num_timesteps == 1000
+    inp = make_inputs(case)
+    y = {"audio_embed": inp["feats"].cuda(), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"], "scale": inp["scale"].cuda()}
+    ref = np.load(os.path.join(golden_dir, "loop_ddim_pose_full_b4_full.npz"))["result"]
+    from audio2photoreal_b200 import _lib as L
+    assert L.load().a2p_loop_row_groups(model._handle, case.B, case.T) in (0, 2) or True
+    res = sampler.ddim_sample_loop(cfg, tuple(inp["x"].shape), noise=inp["x"].cuda(), clip_denoised=False, model_kwargs={"y": y})
+    assert L.load().a2p_loop_row_groups(model._handle, case.B, case.T) == 2      # the 4-concurrent-forward path ran
+    _close(res, ref, True, "pose_full_b4/1000 steps/terms2")
+
+
 def _lib():
     from audio2photoreal_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_testing()
     vp, i32, sz = C.c_void_p, C.c_int, C.c_size_t
     lib.a2p_test_tc_gemm_scratch_bytes.argtypes = [i32] * 4
     lib.a2p_test_tc_gemm_scratch_bytes.restype = sz
@@ -94,7 +111,7 @@ def test_tcgen05_gemm_unit(terms, tol, M, N, K, taps, dil):
     nb = lib.a2p_test_tc_gemm_scratch_bytes(M, N, K, taps)
     scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
     ms = C.c_float()
-    _l.check(lib.a2p_test_tc_gemm(terms, M, N, K, taps, dil, A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(),
+    _l.check_testing(lib.a2p_test_tc_gemm(terms, M, N, K, taps, dil, A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr(),
                                   scratch.data_ptr(), nb, 1, C.byref(ms), torch.cuda.current_stream().cuda_stream))
     ref = b.double().expand(M, N).clone()
     for j in range(taps):
@@ -118,7 +135,7 @@ def test_tcgen05_attention_unit(terms, tol, R, T, D, dh, S, nx):
     nb = lib.a2p_test_tc_attention_scratch_bytes(R, T, D, S, nx)
     scratch = torch.empty(nb, dtype=torch.uint8, device="cuda")
     ms = C.c_float()
-    _l.check(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(),
+    _l.check_testing(lib.a2p_test_tc_attention(terms, R, T, D, dh, S, nx, Q.data_ptr(), K.data_ptr(), V.data_ptr(), Kx.data_ptr(),
                                        Vx.data_ptr(), O.data_ptr(), scratch.data_ptr(), nb, 1, C.byref(ms),
                                        torch.cuda.current_stream().cuda_stream))
     H = D // dh

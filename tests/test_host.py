@@ -30,6 +30,17 @@ def test_cabi_library_exports_every_declared_symbol():
     assert lib.a2p_abi_version() == 1
 
 
+def test_test_hooks_live_in_their_own_library():
+    """include/a2p_b200_testing.h is served by liba2p_b200_testing.so; the product library exports no a2p_test_* symbol."""
+    header = open(os.path.join(ROOT, "include", "a2p_b200_testing.h")).read()
+    declared = set(re.findall(r"\b(a2p_test_[a-z0-9_]+)\s*\(", header))
+    tlib, lib = _lib.load_testing(), _lib.load()
+    assert declared
+    for s in declared:
+        assert hasattr(tlib, s), s
+        assert not hasattr(lib, s), s
+
+
 def test_create_fails_loudly_without_gpu_or_bad_cfg():
     import ctypes as C
     lib = _lib.load()

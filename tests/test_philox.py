@@ -26,7 +26,7 @@ def _philox_np(c, k):
 
 def test_philox_known_answers_host_build():
     from audio2photoreal_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load_testing()
     lib.a2p_test_philox.argtypes = [C.c_uint32] * 6 + [C.POINTER(C.c_uint32)]
     lib.a2p_test_philox.restype = None
     out = (C.c_uint32 * 4)()
