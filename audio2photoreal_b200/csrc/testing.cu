@@ -147,6 +147,8 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   return 0;
 }
 
+void a2p_test_chain_set_mode(int cl) { chain_mode_override() = (cl == 1 || cl == 2) ? cl : 0; }
+
 size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T) {
   return ((size_t)2 * align_up((size_t)M, 128) * K0 + (size_t)2 * 256 * K0 + (size_t)2 * N1 * 256 + (size_t)2 * 256 * 256) * 2 +
          (size_t)T * 128 * 8 + (size_t)(T + 128) * 128 * 8 + 4096 + 1024;

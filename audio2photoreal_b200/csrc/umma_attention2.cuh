@@ -395,9 +395,16 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       writer = (*flag == nparts - 1);
       if (writer) {
         __threadfence();
+        // Fold the key ranges in INDEX order starting from range 0 (this CTA's own partial is re-read like the others):
+        // the fp32 result must not depend on which work item happened to finish last (bit-identical reruns).
+        {
+          const float* o0 = p.split_scratch + ((size_t)(slot * nparts + 0) * 2 + w) * 34 * 128 + trow;
+          m = __ldcg(o0); l = __ldcg(o0 + 128);
+#pragma unroll
+          for (int c = 0; c < 32; ++c) o[c] = __ldcg(o0 + (2 + c) * 128);
+        }
 #pragma unroll 1
-        for (int pp = 0; pp < nparts; ++pp) {
-          if (pp == part) continue;
+        for (int pp = 1; pp < nparts; ++pp) {
           const float* ot = p.split_scratch + ((size_t)(slot * nparts + pp) * 2 + w) * 34 * 128 + trow;
           const float m1 = __ldcg(ot), l1 = __ldcg(ot + 128);
           const float mm = fmaxf(m, m1);

@@ -209,39 +209,88 @@ __device__ __forceinline__ void split_act_pair(float a, float b, uint32_t& hi, u
   lo = __byte_perm(__float_as_uint(r.x), __float_as_uint(r.y), 0x7632);
 }
 
-// ---- 2-CTA cluster mode (CL = 2): the two CTAs of a cluster own neighbouring row tiles and SHARE every weight tile: each
-// CTA fetches half of the tile's rows from L2 and multicasts it into both CTAs' ring slots (the weight stream of 75 CTAs
-// is what saturates L2 -> SM bandwidth; profiles/r01k).  A slot may then be overwritten by the PEER's TMA, so every slot
-// release arrives on the empty barrier of BOTH CTAs (count 2) and the two CTAs walk the slot sequence in loose lockstep.
+// ---- CTA-pair mode (CL = 2): the two CTAs of a cluster (one TPC) own neighbouring 128-row tiles and run every GEMM as
+// `tcgen05.mma.cta_group::2` instructions of shape M = 256 issued by the leader (cluster rank 0): each CTA supplies ITS rows of
+// A (shared memory or tensor memory) and HALF of the weight tile (N / 2 rows of W), and gets its 128 rows of D in its own
+// tensor memory.  A CTA therefore streams half of every weight matrix: the per-SM ingress that bounds GEMM0 / GEMM1
+// (profiles/r01w_source_chain_*: 46 % of the warp samples in operand waits; at B = 32 all 148 SMs pull W from L2 at once)
+// drops from A + W to A + W / 2.  Protocol:
+//   * both producers walk the same slot sequence; a tile consumed by the MMA warp signals the LEADER's full barrier
+//     (`cp.async.bulk.tensor...cta_group::2` with the barrier address mapped to rank 0), which expects the bytes of both CTAs;
+//   * the leader's commits are multicast to the same barrier of both CTAs (slot releases, accumulator-full signals);
+//   * barriers the MMA warp waits on besides the ring (planes ready, accumulator drained) collect the arrivals of both CTAs'
+//     epilogue warps (the peer arrives remotely).
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t peer) {
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t rank) {
   uint32_t ra;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(umma::smem_u32(bar)), "r"(peer));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
+  return ra;
 }
-__device__ __forceinline__ void mma_commit_mc2(uint64_t* bar) {   // arrive on the same barrier of both CTAs when the MMAs complete
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_rank(umma::smem_u32(bar), rank)) : "memory");
+}
+// arrive on a barrier the MMA warp (leader CTA) waits on: local for the leader, remote for the peer
+template <int CL>
+__device__ __forceinline__ void arrive_at_leader(uint64_t* bar, uint32_t crank) {
+  if (CL == 2 && crank != 0) mbar_arrive_remote(bar, 0);
+  else umma::mbar_arrive(bar);
+}
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {   // arrive on the same barrier of BOTH CTAs when the MMAs complete
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(umma::smem_u32(bar)), "h"((uint16_t)3) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d_mc2(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+template <int CL>
+__device__ __forceinline__ void chain_commit(uint64_t* bar) {
+  if (CL == 2) mma_commit_pair(bar);
+  else umma::mma_commit(bar);
+}
+// D[tmem] (+)= A * B^T over the CTA pair (M = 256: 128 rows per CTA; every CTA holds N / 2 rows of B)
+__device__ __forceinline__ void mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;"
-      ::"r"(umma::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(umma::smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"((uint16_t)3)
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_tmem_a_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 template <int CL>
-__device__ __forceinline__ void slot_release(uint64_t* bar, uint32_t peer) {
-  umma::mbar_arrive(bar);
-  if (CL == 2) mbar_arrive_remote(bar, peer);
+__device__ __forceinline__ void chain_mma_ss(uint32_t d, uint64_t a, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (CL == 2) mma_bf16_pair(d, a, b, idesc, acc);
+  else umma::mma_bf16(d, a, b, idesc, acc);
 }
 template <int CL>
-__device__ __forceinline__ void slot_release_commit(uint64_t* bar) {
-  if (CL == 2) mma_commit_mc2(bar);
-  else umma::mma_commit(bar);
+__device__ __forceinline__ void chain_mma_ts(uint32_t d, uint32_t a_tmem, uint64_t b, uint32_t idesc, uint32_t acc) {
+  if (CL == 2) mma_bf16_tmem_a_pair(d, a_tmem, b, idesc, acc);
+  else mma_bf16_tmem_a(d, a_tmem, b, idesc, acc);
+}
+// TMA tile load of a CTA pair: data into THIS CTA's shared memory, bytes counted on the barrier `bar_cluster_addr`
+// (a shared::cluster address: the leader's full barrier)
+__device__ __forceinline__ void tma_load_3d_pair(const CUtensorMap* m, uint32_t bar_cluster_addr, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(umma::smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* slot_in_smem) {  // whole warp, the same warp of BOTH CTAs
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(umma::smem_u32(slot_in_smem)), "n"(NCOLS));
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+}
+template <int NCOLS>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS));
 }
 
 // Epilogue-thread context of chain_emit_planes (kept out of line: it runs twice in kernels with a V job, and the chain
@@ -325,8 +374,8 @@ __device__ __forceinline__ void chain_emit_planes(const ChainEpiCtx c, int rot, 
     if (c.trow == 0) {
 #pragma unroll 1
       for (int cc = 0; cc < 8 / CH_NWG; ++cc) {
-        if (seq_x >= 0) slot_release<CL>(&c.s_empty[(seq_x + cc * CH_NWG + c.wg) % CH_NS], c.peer);
-        if (rot) slot_release<CL>(&c.s_empty[(seq_tab + cc * CH_NWG + c.wg) % CH_NS], c.peer);
+        if (seq_x >= 0) umma::mbar_arrive(&c.s_empty[(seq_x + cc * CH_NWG + c.wg) % CH_NS]);
+        if (rot) umma::mbar_arrive(&c.s_empty[(seq_tab + cc * CH_NWG + c.wg) % CH_NS]);
       }
     }
   }
@@ -367,11 +416,15 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   const int NH1 = ceil_div(p.N1, 128);
   const int n_acc = NH1 + (p.vjob ? 2 : 0);
   // ring positions of the slot sequence (identical arithmetic in every role)
-  const int seqEA = 6 * kc0;                      // 8 x chunks (loaded, or only reserved as store buffers if !film_mode)
+  // single CTA: per 64-wide K chunk of GEMM0 two A0 tiles + four W0 tiles (plane x 128-row half), per 128-column half of
+  // GEMM1 / the V job eight W tiles (K chunk x plane).  CTA pair: every CTA fetches HALF of the weight rows -- two A0 tiles +
+  // two W0 tiles (plane; its 128 of the 256 rows) per K chunk, four W tiles per accumulator half (K chunk; both planes of its 64 rows)
+  constexpr int G0S = CL == 2 ? 4 : 6, G1S = CL == 2 ? 4 : 8;
+  const int seqEA = G0S * kc0;                    // 8 x chunks (loaded, or only reserved as store buffers if !film_mode)
   const int seqTab = seqEA + 8;                   // 8 RoPE-table chunks (if rope)
-  const int seqG1 = seqTab + (p.rope ? 8 : 0);    // NH1 * 8 W1 tiles
-  const int seqVx = seqG1 + 8 * NH1;              // 8 x chunks again (V job)
-  const int seqV = seqVx + 8;                     // 16 W2 tiles
+  const int seqG1 = seqTab + (p.rope ? 8 : 0);    // NH1 * G1S W1 tiles
+  const int seqVx = seqG1 + G1S * NH1;            // 8 x chunks again (V job)
+  const int seqV = seqVx + 8;                     // 2 * G1S W2 tiles
 
   if (warp == 0 && lane == 0) {
     umma::prefetch_tmap(&tmA0); umma::prefetch_tmap(&tmW0); umma::prefetch_tmap(&tmW1); umma::prefetch_tmap(&tmX);
@@ -379,18 +432,20 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     if (p.vjob) umma::prefetch_tmap(&tmW2);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], CL); }
-    umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 128 * CH_NWG);
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 64 * CH_NWG); }
-    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 128 * CH_NWG); umma::mbar_init(x_stored, 1);
+    // a_ready / a2_ready / acc1_empty are waited on by the MMA warp (leader CTA in pair mode): one arrival per epilogue WARP
+    // (4 * CH_NWG warps write the planes, 2 * CH_NWG drain an accumulator half) of each of the CL CTAs
+    for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 1); }
+    umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 4 * CH_NWG * CL);
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 2 * CH_NWG * CL); }
+    umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 4 * CH_NWG * CL); umma::mbar_init(x_stored, 1);
     for (int i = 0; i < 8; ++i) umma::mbar_init(&x_written[i], 128);
     umma::fence_barrier_init();
   }
-  if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
+  if (warp == 2) { if (CL == 2) tmem_alloc_pair<512>(tmem_slot); else umma::tmem_alloc<512>(tmem_slot); }
   pdl_trigger();
   umma::fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();     // the peer's barriers are initialised before anything is multicast / arrived remotely
+  if (CL == 2) cluster_sync_all();     // the peer's barriers and tensor memory exist before anything is committed / arrived remotely
   umma::fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t slots_u32 = umma::smem_u32(sSlots);
@@ -402,17 +457,23 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // Rolled nested loops (the fully unrolled form of this role alone was 25 KB of cold code), but no per-load decode
     // arithmetic: the load -> consume -> release -> reload round trip of a slot is the critical path of the GEMMs.
     int sl_ = 0; uint32_t ph_ = 0;
-    constexpr int KW = CL == 2 ? 3 : 0;   // weight tiles: 3 = my half of the rows, multicast to both CTAs of the cluster
-    auto issue = [&](const CUtensorMap* tm, int kind, int c0, int c1, int c2) {   // kind 0: 3-D bf16 tile, 1: 2-D fp32 tile, 2: reserve
+    // kind 0: bf16 tile read by the MMA warp (3-D map), 1: fp32 tile read by this CTA's epilogue warps (2-D map), 2: reserve only
+    auto issue = [&](const CUtensorMap* tm, int kind, int c0, int c1, int c2) {
       umma::mbar_wait(&s_empty[sl_], ph_ ^ 1);
       if (umma::elect_one()) {
         if (kind == 2) {
           umma::mbar_arrive(&s_full[sl_]);
+        } else if (kind == 1) {
+          umma::mbar_expect_tx(&s_full[sl_], CH_TILE);
+          tma_load_2d(tm, &s_full[sl_], slots_u32 + sl_ * CH_TILE, c0, c1);
+        } else if (CL == 2) {
+          // the leader's barrier counts the tiles of both CTAs; the peer only keeps its own (unused) barrier's phase in step
+          if (crank == 0) umma::mbar_expect_tx(&s_full[sl_], 2 * CH_TILE);
+          else umma::mbar_arrive(&s_full[sl_]);
+          tma_load_3d_pair(tm, mapa_rank(umma::smem_u32(&s_full[sl_]), 0), sSlots + sl_ * CH_TILE, c0, c1, c2);
         } else {
           umma::mbar_expect_tx(&s_full[sl_], CH_TILE);
-          if (kind == 0) umma::tma_load_3d(tm, &s_full[sl_], sSlots + sl_ * CH_TILE, c0, c1, c2);
-          else if (kind == 3) tma_load_3d_mc2(tm, &s_full[sl_], sSlots + sl_ * CH_TILE + crank * (CH_TILE / 2), c0, c1 + crank * 64, c2);
-          else tma_load_2d(tm, &s_full[sl_], slots_u32 + sl_ * CH_TILE, c0, c1);
+          umma::tma_load_3d(tm, &s_full[sl_], sSlots + sl_ * CH_TILE, c0, c1, c2);
         }
       }
       __syncwarp();
@@ -421,9 +482,10 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 #pragma unroll 1
     for (int kc = 0; kc < kc0; ++kc) {
 #pragma unroll 1
-      for (int j = 0; j < 6; ++j) {
+      for (int j = 0; j < G0S; ++j) {
         if (j < 2) issue(&tmA0, 0, kc * 64, m0, j);
-        else issue(&tmW0, KW, kc * 64, ((j - 2) & 1) * 128, (j - 2) >> 1);
+        else if (CL == 2) issue(&tmW0, 0, kc * 64, (int)crank * 128, j - 2);            // my 128 of the 256 rows, plane j - 2
+        else issue(&tmW0, 0, kc * 64, ((j - 2) & 1) * 128, (j - 2) >> 1);
       }
     }
     CH_TRACE(24, lane == 0);
@@ -436,21 +498,28 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     CH_TRACE(25, lane == 0);
 #pragma unroll 1
-    for (int j = 0; j < 8 * NH1; ++j) issue(&tmW1, KW, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
+    for (int j = 0; j < G1S * NH1; ++j) {
+      if (CL == 2) issue(&tmW1, 0, (j & 3) * 64, (j >> 2) * 128 + (int)crank * 64, 0);  // box = both planes of my 64 rows
+      else issue(&tmW1, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
+    }
     CH_TRACE(26, lane == 0);
     if (p.vjob) {
       umma::mbar_wait(x_stored, 0);   // the x tile written by E_A is globally visible
 #pragma unroll 1
       for (int j = 0; j < 8; ++j) issue(&tmX, 1, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0, 0);
 #pragma unroll 1
-      for (int j = 0; j < 16; ++j) issue(&tmW2, KW, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
+      for (int j = 0; j < 2 * G1S; ++j) {
+        if (CL == 2) issue(&tmW2, 0, (j & 3) * 64, (j >> 2) * 128 + (int)crank * 64, 0);
+        else issue(&tmW2, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
+      }
     }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    constexpr uint32_t idesc = umma::idesc_bf16_f32(128, 128);
+  } else if (warp == 1 && (CL == 1 || crank == 0)) {
+    // ================= MMA issuer (pair mode: the leader CTA issues for both) =================
+    constexpr uint32_t idesc = CL == 2 ? umma::idesc_bf16_f32(256, 128) : umma::idesc_bf16_f32(128, 128);
+    constexpr uint32_t idesc0 = CL == 2 ? umma::idesc_bf16_f32(256, 256) : idesc;     // GEMM0 of a pair: one N = 256 accumulator
     constexpr uint32_t TU = CH_TILE >> 4;
     const uint32_t lo0 = umma::desc_lo(slots_u32);
-    // ---- GEMM0 (A0 and W0 both from ring slots): both 128-column halves of acc0 advance together
+    // ---- GEMM0 (A0 and W0 both from ring slots).  Single CTA: both 128-column halves of acc0 advance together.
     int q = 0;
     CH_TRACE(16, lane == 0);
 #pragma unroll 1
@@ -460,8 +529,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       umma::mbar_wait(&s_full[sa1], ((q + 1) / CH_NS) & 1);
       q += 2;
 #pragma unroll 1
-      for (int st4 = 0; st4 < 4; ++st4) {
-        const int pw = st4 >> 1, nh = st4 & 1;
+      for (int st4 = 0; st4 < G0S - 2; ++st4) {
+        const int pw = CL == 2 ? st4 : st4 >> 1, nh = CL == 2 ? 1 : st4 & 1;   // weight plane; last tile of the plane
         {
           const int s = q % CH_NS;
           umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
@@ -469,24 +538,24 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           umma::fence_after();
           if (umma::elect_one()) {
             const uint32_t lob = lo0 + s * TU;
-            const uint32_t d = tmem_base + nh * 128;
+            const uint32_t d = tmem_base + (CL == 2 ? 0 : (st4 & 1) * 128);
             if (pw == 0) {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma::mma_bf16(d, umma::desc_make(lo0 + sa0 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, (kc | k) != 0 ? 1u : 0u);
+                chain_mma_ss<CL>(d, umma::desc_make(lo0 + sa0 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc0, (kc | k) != 0 ? 1u : 0u);
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma::mma_bf16(d, umma::desc_make(lo0 + sa1 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, 1u);
+                chain_mma_ss<CL>(d, umma::desc_make(lo0 + sa1 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc0, 1u);
             } else {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                umma::mma_bf16(d, umma::desc_make(lo0 + sa0 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc, 1u);
+                chain_mma_ss<CL>(d, umma::desc_make(lo0 + sa0 * TU + 2 * k), umma::desc_make(lob + 2 * k), idesc0, 1u);
             }
-            slot_release_commit<CL>(&s_empty[s]);
+            chain_commit<CL>(&s_empty[s]);
             if (pw == 1 && nh == 1) {
-              slot_release_commit<CL>(&s_empty[sa0]);
-              slot_release_commit<CL>(&s_empty[sa1]);
-              if (kc == kc0 - 1) umma::mma_commit(acc0_full);
+              chain_commit<CL>(&s_empty[sa0]);
+              chain_commit<CL>(&s_empty[sa1]);
+              if (kc == kc0 - 1) chain_commit<CL>(acc0_full);
             }
           }
           __syncwarp();
@@ -503,8 +572,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (h >= 2) { umma::mbar_wait(&acc1_empty[buf], ((h >> 1) - 1) & 1); umma::fence_after(); }
       const uint32_t d = tmem_base + 256 + buf * 128;
 #pragma unroll 1
-      for (int st8 = 0; st8 < 8; ++st8) {
-        const int kc = st8 >> 1, pw = st8 & 1;
+      for (int st8 = 0; st8 < G1S; ++st8) {
+        const int kc = CL == 2 ? st8 : st8 >> 1, pw = CL == 2 ? 1 : st8 & 1;
         {
           const int s = q % CH_NS;
           umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
@@ -512,20 +581,34 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           umma::fence_after();
           if (umma::elect_one()) {
             const uint32_t low = lo0 + s * TU;
+            if (CL == 2) {
+              // one slot = [weight plane 0: my 64 rows][weight plane 1: my 64 rows] of this K chunk:
+              // plane pairs (act 0, w 0) (act 1, w 0) (act 0, w 1)
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              if (pw == 1 && i == 1) break;          // plane pairs (act 0, w 0) (act 1, w 0) | (act 0, w 1)
+              for (int i = 0; i < 3; ++i) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int ks = kc * 4 + k;             // 16-element k-step: chunk ks >> 1, half ks & 1
-                mma_bf16_tmem_a(d, tmem_base + (ks >> 1) * 32 + i * 16 + (ks & 1) * 8, umma::desc_make(low + 2 * k), idesc,
-                                (kc | pw | i | k) != 0 ? 1u : 0u);
+                for (int k = 0; k < 4; ++k) {
+                  const int ks = kc * 4 + k;
+                  chain_mma_ts<CL>(d, tmem_base + (ks >> 1) * 32 + (i == 1 ? 16 : 0) + (ks & 1) * 8,
+                                   umma::desc_make(low + (i == 2 ? (8192 >> 4) : 0) + 2 * k), idesc, (kc | i | k) != 0 ? 1u : 0u);
+                }
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                if (pw == 1 && i == 1) break;          // plane pairs (act 0, w 0) (act 1, w 0) | (act 0, w 1)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int ks = kc * 4 + k;             // 16-element k-step: chunk ks >> 1, half ks & 1
+                  chain_mma_ts<CL>(d, tmem_base + (ks >> 1) * 32 + i * 16 + (ks & 1) * 8, umma::desc_make(low + 2 * k), idesc,
+                                   (kc | pw | i | k) != 0 ? 1u : 0u);
+                }
               }
             }
-            slot_release_commit<CL>(&s_empty[s]);
+            chain_commit<CL>(&s_empty[s]);
             if (kc == 3 && pw == 1) {
-              umma::mma_commit(&acc1_full[buf]);
-              if (h == NH1 - 1) umma::mma_commit(a_reads_done);
+              chain_commit<CL>(&acc1_full[buf]);
+              if (h == NH1 - 1) chain_commit<CL>(a_reads_done);
             }
           }
           __syncwarp();
@@ -549,10 +632,10 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           bulk_commit();
         }
         static_assert(CH_NWG == 4, "staggered waits below assume 4 stores per round");
-        bulk_wait_read<3>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 0) % CH_NS], peer);
-        bulk_wait_read<2>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 1) % CH_NS], peer);
-        bulk_wait_read<1>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 2) % CH_NS], peer);
-        bulk_wait_read<0>(); slot_release<CL>(&s_empty[(seqEA + r * CH_NWG + 3) % CH_NS], peer);
+        bulk_wait_read<3>(); umma::mbar_arrive(&s_empty[(seqEA + r * CH_NWG + 0) % CH_NS]);
+        bulk_wait_read<2>(); umma::mbar_arrive(&s_empty[(seqEA + r * CH_NWG + 1) % CH_NS]);
+        bulk_wait_read<1>(); umma::mbar_arrive(&s_empty[(seqEA + r * CH_NWG + 2) % CH_NS]);
+        bulk_wait_read<0>(); umma::mbar_arrive(&s_empty[(seqEA + r * CH_NWG + 3) % CH_NS]);
       }
       bulk_wait_all();           // globally visible (the V job re-reads the tile; nothing may be in flight at exit)
       if (p.vjob) umma::mbar_arrive(x_stored);
@@ -681,7 +764,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     CH_TRACE(4, et == 0);
     ChainEpiCtx ectx{tmem_base + lane_addr, slots_u32, row_off, pb_u32, s_full, s_empty, wg, trow, p.ln_mode, mean, rstd, peer};
     chain_emit_planes<CL>(ectx, p.rope, -1, seqTab);
-    umma::mbar_arrive(a_ready);
+    __syncwarp();
+    if (lane == 0) arrive_at_leader<CL>(a_ready, crank);
     CH_TRACE(5, et == 0);
 
     // ---------------- E_B: accumulator half h is drained by the warpgroup PAIR (h & 1): warpgroup `sub` of the pair takes 64 of
@@ -696,7 +780,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         umma::mbar_wait(a_reads_done, 0);    // every GEMM1 MMA has read the rotated planes
         umma::fence_after();
         chain_emit_planes<CL>(ectx, 0, seqVx, 0);
-        umma::mbar_arrive(a2_ready);
+        __syncwarp();
+        if (lane == 0) arrive_at_leader<CL>(a2_ready, crank);
         vprep_done = true;
       }
       const int buf = h & 1;
@@ -712,7 +797,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           float v[16];
           tmem_ld16(tmem_base + lane_addr + 256 + buf * 128 + c16 * 16, v);
           umma::tmem_ld_wait();
-          if (k == 3) { umma::fence_before(); umma::mbar_arrive(&acc1_empty[buf]); }
+          if (k == 3) { umma::fence_before(); __syncwarp(); if (lane == 0) arrive_at_leader<CL>(&acc1_empty[buf], crank); }
           const uint32_t srow = stg_u32 + lane * 64;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -775,10 +860,10 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     CH_TRACE(30, et == 0);
   }
   __syncthreads();
-  if (CL == 2) cluster_sync_all();     // no CTA leaves while its peer may still multicast into it or arrive on its barriers
+  if (CL == 2) cluster_sync_all();     // no CTA leaves while the leader may still issue MMAs on / commit into its peer
   if (warp == 2) {
     umma::fence_after();
-    umma::tmem_dealloc<512>(tmem_base);
+    if (CL == 2) tmem_dealloc_pair<512>(tmem_base); else umma::tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -798,10 +883,15 @@ inline int make_tmap_f32_2d(CUtensorMap* tm, const void* base, long long cols, l
   return 0;
 }
 
-// A2P_CHAIN_CLUSTER=2: pairs of CTAs share the weight stream through TMA multicast (default 1 until measured faster)
+#ifndef A2P_CHAIN_PAIR_DEFAULT
+#define A2P_CHAIN_PAIR_DEFAULT 0
+#endif
+// A2P_CHAIN_PAIR=1: CTA-pair mode (cta_group::2 MMAs, every CTA streams half of each weight tile); 0: one CTA per tile
+inline int& chain_mode_override() { static int v = 0; return v; }   // tests: 1 / 2 forces the mode of the next launches
 inline int chain_cluster_size() {
+  if (chain_mode_override() > 0) return chain_mode_override();
   static int v = -1;
-  if (v < 0) { const char* e = getenv("A2P_CHAIN_CLUSTER"); v = (e && atoi(e) == 2) ? 2 : 1; }
+  if (v < 0) { const char* e = getenv("A2P_CHAIN_PAIR"); v = (e ? atoi(e) != 0 : A2P_CHAIN_PAIR_DEFAULT) ? 2 : 1; }
   return v;
 }
 
@@ -814,19 +904,21 @@ struct ChainOperands {
   const float* rope_ext; long long rope_ext_rows;                       // [T + 128][256] fp32: (cos, sin) pairs of position (row % T)
 };
 
-inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaStream_t st) {
+inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaStream_t st, int force_cl = 0) {
   if (p.K0 % 8 || p.N1 % 8 || p.N1 <= 0 || p.N1 > 1024) A2P_FAIL("chain: bad K0=%d / N1=%d", p.K0, p.N1);
   if (p.T < 128 || p.M % 8) A2P_FAIL("chain: needs T >= 128 and M %% 8 == 0 (T=%d M=%d)", p.T, p.M);
   if (p.vjob && (!o.W2 || !p.Vt)) A2P_FAIL("chain: V job needs W2 and Vt");
   if (p.rope && (!o.rope_ext || o.rope_ext_rows < p.T + 128)) A2P_FAIL("chain: RoPE needs the extended table (T + 128 rows)");
   CUtensorMap tA0, tW0, tW1, tW2, tX, tTab;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  const int cl = chain_cluster_size();
-  const int wbox = 128 / cl;            // weight tiles: every CTA of a cluster fetches 1/cl of the rows and multicasts it
+  const int cl = force_cl > 0 ? force_cl : chain_cluster_size();
+  // pair mode: a CTA loads its 128 of the 256 W0 rows (one plane per box) and, for a 128-column accumulator half of GEMM1 / the
+  // V job, both planes of its 64 rows in ONE box [64 k][64 rows][2 planes] = one 16 KB slot
+  const int w1rows = cl == 2 ? 64 : 128, w1planes = cl == 2 ? 2 : 1;
   A2P_TRY(make_tmap_bf16_3d(&tA0, o.A0, p.K0, o.a0_rows, 2, o.a0_ld, o.a0_plane_stride, 64, 128, sw));
-  A2P_TRY(make_tmap_bf16_3d(&tW0, o.W0, p.K0, 256, 2, p.K0, o.w0_plane_stride, 64, wbox, sw));
-  A2P_TRY(make_tmap_bf16_3d(&tW1, o.W1, 256, p.N1, 2, 256, o.w1_plane_stride, 64, wbox, sw));
-  if (p.vjob) A2P_TRY(make_tmap_bf16_3d(&tW2, o.W2, 256, 256, 2, 256, o.w2_plane_stride, 64, wbox, sw));
+  A2P_TRY(make_tmap_bf16_3d(&tW0, o.W0, p.K0, 256, 2, p.K0, o.w0_plane_stride, 64, 128, sw));
+  A2P_TRY(make_tmap_bf16_3d(&tW1, o.W1, 256, p.N1, 2, 256, o.w1_plane_stride, 64, w1rows, sw, w1planes));
+  if (p.vjob) A2P_TRY(make_tmap_bf16_3d(&tW2, o.W2, 256, 256, 2, 256, o.w2_plane_stride, 64, w1rows, sw, w1planes));
   else tW2 = tW1;
   A2P_TRY(make_tmap_f32_2d(&tX, o.x, 256, p.M, 256, 32, 128));
   if (p.rope) A2P_TRY(make_tmap_f32_2d(&tTab, o.rope_ext, 256, o.rope_ext_rows, 256, 32, 128));

@@ -286,14 +286,14 @@ inline PFN_encodeTiled get_encode_fn() {
 
 // bf16 tensor [planes][rows][ld] (ld >= cols, contiguous cols); box = (box_cols, box_rows, 1)
 inline int make_tmap_bf16_3d(CUtensorMap* tm, const void* base, long long cols, long long rows, long long planes, long long ld,
-                             long long plane_stride, int box_cols, int box_rows, CUtensorMapSwizzle swz) {
+                             long long plane_stride, int box_cols, int box_rows, CUtensorMapSwizzle swz, int box_planes = 1) {
   PFN_encodeTiled fn = get_encode_fn();
   if (!fn) A2P_FAIL("cuTensorMapEncodeTiled entry point not available");
   if ((ld * 2) % 16 || (plane_stride * 2) % 16 || (reinterpret_cast<uintptr_t>(base) % 16))
     A2P_FAIL("TMA operand not 16-byte aligned (ld=%lld plane_stride=%lld)", ld, plane_stride);
   cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)planes};
   cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_stride * 2};
-  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, (cuuint32_t)box_planes};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -294,7 +294,8 @@ def run_reference_arm(a):
         "impl": "reference", "metric": METRIC if fmt == "pose" else FACE_METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * w["B"] * w["T"] / v, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(fmt, w["B"], True)},
+        "config": {"workload": workload_name(fmt, w["B"], True).replace("synthetic wav2vec features [B,1998,1024]", "synthetic RAW 48 kHz audio "
+                                                                       "[B,960000,2] through the stand-in vq-wav2vec stack on every call")},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -302,6 +303,7 @@ def run_reference_arm(a):
 
 
 def main():
+    global SPLIT_TERMS, WORKLOAD, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -320,7 +322,6 @@ def main():
     ap.add_argument("--no-config3", action="store_true", help="skip the extra global-batch-32 (configs[2], strong-scaling) measurement")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU leg")
     a = ap.parse_args()
-    global SPLIT_TERMS, WORKLOAD, METRIC
     face = a.workload == "face"
     SPLIT_TERMS = a.split_terms if a.split_terms is not None else (3 if face else 2)
     if a.impl == "reference":

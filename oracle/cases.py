@@ -85,3 +85,14 @@ def layer_inputs(case, seed=11):
     t = torch.randn(case.B, D, generator=g)
     mem2 = torch.randn(case.B, 20, D, generator=g) if case.fmt == "pose" else None
     return x, mem, t, mem2
+
+
+def variant_inputs(kind: str):
+    """inputs of the sampler-keyword variants case (oracle/make_golden.py golden_loop_variants): pose_small with
+    clip_denoised=True + skip_timesteps=3 + a random init_image (DDIM) / const_noise + clip + skip_timesteps=2 (ancestral)"""
+    case = CASES["pose_small"]
+    resp, skip = ("ddim10", 3) if kind == "ddim" else ("10", 2)
+    n = 10 - skip
+    inp, sd = make_inputs(case, n_noise=n), weights_of(case)
+    init = 0.5 * torch.from_numpy(np.random.RandomState(77).standard_normal(tuple(inp["x"].shape)).astype(np.float32))
+    return case, resp, inp, sd, skip, init

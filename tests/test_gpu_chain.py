@@ -28,13 +28,16 @@ def _lib():
     lib.a2p_test_chain_scratch_bytes.restype = sz
     lib.a2p_test_chain.argtypes = [i32] * 9 + [f32, i32] + [vp] * 15 + [sz, i32, C.POINTER(f32), vp]
     lib.a2p_test_chain.restype = i32
+    lib.a2p_test_chain_set_mode.argtypes = [i32]
+    lib.a2p_test_chain_set_mode.restype = None
     return _lib, lib
 
 
-def run_case(name, iters=0, seed=0):
+def run_case(name, iters=0, seed=0, mode=0):
     """returns dict(stage -> (max abs err, max |ref|)) and the kernel time in ms (iters > 0)"""
     M, T, K0, N1, film_mode, ln_mode, rope, gelu, vjob, scale_ncols = CASES[name]
     L, lib = _lib()
+    lib.a2p_test_chain_set_mode(mode)      # 0 library default, 1 one CTA per tile, 2 CTA pairs (cta_group::2)
     g = torch.Generator(device="cuda").manual_seed(seed)
     dev = "cuda"
     rn = lambda *s, sc=1.0: (torch.randn(*s, generator=g, device=dev) * sc).contiguous()
@@ -100,9 +103,10 @@ def run_case(name, iters=0, seed=0):
     return res, t
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("name", list(CASES))
-def test_chain_vs_fp64(name):
-    res, _ = run_case(name)
+def test_chain_vs_fp64(name, mode):
+    res, _ = run_case(name, mode=mode)
     for stage, (err, scale) in res.items():
         tol = (2e-5 if stage == "x" else 4e-5) * max(1.0, scale)
         assert err <= tol, f"{name}/{stage}: max|d|={err:.3e} (|ref|max={scale:.3f}, tol {tol:.1e})"
@@ -112,6 +116,8 @@ if __name__ == "__main__":
     import os
     import sys
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-    for name in (sys.argv[1:] or list(CASES)):
-        res, t = run_case(name, iters=20)
-        print(name, {k: f"{e:.2e}/{s:.2f}" for k, (e, s) in res.items()}, f"{1e3 * t:.1f} us" if t else "", flush=True)
+    names = [a for a in sys.argv[1:] if not a.startswith("--")] or list(CASES)
+    for mode in (1, 2):
+        for name in names:
+            res, t = run_case(name, iters=20, mode=mode)
+            print(f"mode{mode}", name, {k: f"{e:.2e}/{s:.2f}" for k, (e, s) in res.items()}, f"{1e3 * t:.1f} us" if t else "", flush=True)

@@ -95,8 +95,8 @@ def test_loops_vs_reference_golden(golden_dir, name, resp, kind, eta):
 def test_sampler_variants_vs_reference_golden(golden_dir, kind, terms):
     """clip_denoised=True, skip_timesteps, init_image (DDIM) / const_noise=True + clip + skip with the implicit zeros init
     image (ancestral): gaussian_diffusion.py:305-310,617-632,890-905 through the fused loop, against the reference's output."""
-    from tests.test_oracle_golden import _variant_inputs
-    case, od, inp, sd, skip, init = _variant_inputs(kind)
+    from oracle.cases import variant_inputs
+    case, resp, inp, sd, skip, init = variant_inputs(kind)
     from audio2photoreal_b200.api import CFGDenoiser, create_model_and_diffusion, load_model
     model, sampler = create_model_and_diffusion(_args(case, "ddim10" if kind == "ddim" else "10", terms), "test")
     load_model(model, sd)

@@ -57,20 +57,13 @@ def test_loops_match_reference(golden_dir, name, resp, kind, eta):
     _check(got, ref, atol=3e-4, rtol=1e-4)
 
 
-def _variant_inputs(kind):
-    case = CASES["pose_small"]
-    resp, skip = ("ddim10", 3) if kind == "ddim" else ("10", 2)
-    od = O.OracleDiffusion(resp)
-    inp, sd = make_inputs(case, n_noise=od.num_timesteps - skip), weights_of(case)
-    init = 0.5 * torch.from_numpy(np.random.RandomState(77).standard_normal(tuple(inp["x"].shape)).astype(np.float32))
-    return case, od, inp, sd, skip, init
-
-
 @pytest.mark.parametrize("kind", ["ddim", "ancestral"])
 def test_sampler_variants_match_reference(golden_dir, kind):
     """clip_denoised / skip_timesteps / init_image (DDIM) and const_noise + clip + skip (ancestral) against the
     reference's own loops (oracle/make_golden.py golden_loop_variants)."""
-    case, od, inp, sd, skip, init = _variant_inputs(kind)
+    from oracle.cases import variant_inputs
+    case, resp, inp, sd, skip, init = variant_inputs(kind)
+    od = O.OracleDiffusion(resp)
     fn = lambda x, ts: O.cfg_forward(sd, case.fmt, case.H, x, ts, inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
     ref = np.load(os.path.join(golden_dir, "loop_variants_pose_small.npz"))[kind]
     if kind == "ddim":
