@@ -28,6 +28,12 @@ using namespace a2p;
 
 namespace {
 
+#ifndef A2P_ATTN_DECOUPLE_DEFAULT
+#define A2P_ATTN_DECOUPLE_DEFAULT 0
+#endif
+#ifndef A2P_ATTN_SKEW_DEFAULT_NS
+#define A2P_ATTN_SKEW_DEFAULT_NS 500
+#endif
 constexpr int MAXL = 16;
 constexpr int TCN_PAD = 24;  // receptive_field - 1 (model/diffusion.py:153,215)
 const int TCN_DIL[6] = {1, 2, 3, 1, 2, 3};
@@ -78,7 +84,8 @@ struct a2p_denoiser {
   std::map<const float*, __nv_bfloat16*> wplanes;  // fp32 weight -> split-bf16 planes [P][rows][cols] (plane stride = numel)
   std::map<const float*, long long> wnumel;
   int num_sms = 148;
-  int attn_skew_ns = 0;   // measured: no effect (profiles/r01f_attention_experiments.txt)
+  int attn_skew_ns = 0;   // start delay of head 1's softmax warpgroup; no effect with the lockstep MMA loop (profiles/r01f)
+  int attn_decouple = 0;  // per-head MMA scheduling in umma_attn2_kernel (A2P_ATTN_DECOUPLE)
   CondSet cond[2];
   int64_t launches = 0;
   int64_t graph_nodes = 0;
@@ -523,7 +530,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     TcAttnParams ap{};
     o.Q = qkP; o.q_rows = MT; o.q_ld = 2 * D; o.q_plane_stride = (long long)MT * 2 * D;
     o.vt_rows = D;
-    ap.skew_ns = h->attn_skew_ns;
+    ap.skew_ns = h->attn_skew_ns; ap.decouple = h->attn_decouple;
     if (P == 2) { ap.split_scratch = F(w.splitS); ap.split_counters = reinterpret_cast<int*>(wsb + w.splitC); }
     ap.T = T; ap.R = R; ap.D = D; ap.dh = dh; ap.q_col0 = 0; ap.Op = attP; ap.op_plane_stride = pstrideD; ap.o_ld = D; ap.O = nullptr;
     if (kind == 0) {
@@ -946,7 +953,8 @@ int a2p_denoiser_create(a2p_denoiser_t** out, const a2p_model_cfg* cfg) {
   h->cfg = *cfg;
   h->dh = cfg->D / cfg->H;
   h->nf = cfg->fmt == A2P_FMT_POSE ? 4 : 3;
-  if (getenv("A2P_ATTN_SKEW_NS")) h->attn_skew_ns = atoi(getenv("A2P_ATTN_SKEW_NS"));
+  h->attn_decouple = getenv("A2P_ATTN_DECOUPLE") ? atoi(getenv("A2P_ATTN_DECOUPLE")) : A2P_ATTN_DECOUPLE_DEFAULT;
+  h->attn_skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : (h->attn_decouple ? A2P_ATTN_SKEW_DEFAULT_NS : 0);
   *out = h;
   return 0;
 }

@@ -407,7 +407,8 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint64_t* a2_ready = bars + 29;      // 256 arrivals
   uint64_t* x_stored = bars + 30;      // the x tile written by E_A is globally visible (store warp)
   uint64_t* x_written = bars + 31;     // [8] 128 arrivals each: x chunk at ring position seqEA + j is in its staging slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31 + 8);
+  uint64_t* m_full = bars + 39;        // [11] pair mode, leader only: "the tiles of BOTH CTAs for this MMA use of slot s have landed"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 39 + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * 128;
@@ -434,7 +435,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 1 && lane == 0) {
     // a_ready / a2_ready / acc1_empty are waited on by the MMA warp (leader CTA in pair mode): one arrival per epilogue WARP
     // (4 * CH_NWG warps write the planes, 2 * CH_NWG drain an accumulator half) of each of the CL CTAs
-    for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < CH_NS; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&s_empty[i], 1); umma::mbar_init(&m_full[i], 1); }
     umma::mbar_init(acc0_full, 1); umma::mbar_init(a_ready, 4 * CH_NWG * CL);
     for (int i = 0; i < 2; ++i) { umma::mbar_init(&acc1_full[i], 1); umma::mbar_init(&acc1_empty[i], 2 * CH_NWG * CL); }
     umma::mbar_init(a_reads_done, 1); umma::mbar_init(a2_ready, 4 * CH_NWG * CL); umma::mbar_init(x_stored, 1);
@@ -467,10 +468,13 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           umma::mbar_expect_tx(&s_full[sl_], CH_TILE);
           tma_load_2d(tm, &s_full[sl_], slots_u32 + sl_ * CH_TILE, c0, c1);
         } else if (CL == 2) {
-          // the leader's barrier counts the tiles of both CTAs; the peer only keeps its own (unused) barrier's phase in step
-          if (crank == 0) umma::mbar_expect_tx(&s_full[sl_], 2 * CH_TILE);
-          else umma::mbar_arrive(&s_full[sl_]);
-          tma_load_3d_pair(tm, mapa_rank(umma::smem_u32(&s_full[sl_]), 0), sSlots + sl_ * CH_TILE, c0, c1, c2);
+          // MMA tiles of a pair are counted on the LEADER's m_full[slot] (the bytes of both CTAs), a barrier that only MMA
+          // uses of the slot touch: the two CTAs are not in lockstep on their epilogue-consumed uses of a slot (x / table
+          // chunks), so a peer's tile for the NEXT use must never land on a barrier whose current phase belongs to the
+          // leader's own epilogue tile.  s_full[slot] only keeps its lap parity in step (nobody waits on it for MMA uses).
+          umma::mbar_arrive(&s_full[sl_]);
+          if (crank == 0) umma::mbar_expect_tx(&m_full[sl_], 2 * CH_TILE);
+          tma_load_3d_pair(tm, mapa_rank(umma::smem_u32(&m_full[sl_]), 0), sSlots + sl_ * CH_TILE, c0, c1, c2);
         } else {
           umma::mbar_expect_tx(&s_full[sl_], CH_TILE);
           umma::tma_load_3d(tm, &s_full[sl_], sSlots + sl_ * CH_TILE, c0, c1, c2);
@@ -519,21 +523,26 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     constexpr uint32_t idesc0 = CL == 2 ? umma::idesc_bf16_f32(256, 256) : idesc;     // GEMM0 of a pair: one N = 256 accumulator
     constexpr uint32_t TU = CH_TILE >> 4;
     const uint32_t lo0 = umma::desc_lo(slots_u32);
+    uint32_t mpar = 0;     // pair mode: bit s = parity of the next MMA use of slot s on m_full[s]
+    auto wait_tile = [&](int s_, int q_) {
+      if (CL == 2) { umma::mbar_wait(&m_full[s_], (mpar >> s_) & 1u); mpar ^= 1u << s_; }
+      else umma::mbar_wait(&s_full[s_], (q_ / CH_NS) & 1);
+    };
     // ---- GEMM0 (A0 and W0 both from ring slots).  Single CTA: both 128-column halves of acc0 advance together.
     int q = 0;
     CH_TRACE(16, lane == 0);
 #pragma unroll 1
     for (int kc = 0; kc < kc0; ++kc) {
       const int sa0 = q % CH_NS, sa1 = (q + 1) % CH_NS;
-      umma::mbar_wait(&s_full[sa0], (q / CH_NS) & 1);
-      umma::mbar_wait(&s_full[sa1], ((q + 1) / CH_NS) & 1);
+      wait_tile(sa0, q);
+      wait_tile(sa1, q + 1);
       q += 2;
 #pragma unroll 1
       for (int st4 = 0; st4 < G0S - 2; ++st4) {
         const int pw = CL == 2 ? st4 : st4 >> 1, nh = CL == 2 ? 1 : st4 & 1;   // weight plane; last tile of the plane
         {
           const int s = q % CH_NS;
-          umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
+          wait_tile(s, q);
           ++q;
           umma::fence_after();
           if (umma::elect_one()) {
@@ -576,7 +585,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int kc = CL == 2 ? st8 : st8 >> 1, pw = CL == 2 ? 1 : st8 & 1;
         {
           const int s = q % CH_NS;
-          umma::mbar_wait(&s_full[s], (q / CH_NS) & 1);
+          wait_tile(s, q);
           ++q;
           umma::fence_after();
           if (umma::elect_one()) {

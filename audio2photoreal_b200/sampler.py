@@ -218,6 +218,71 @@ class Sampler(DiffusionTables):
         return x
 
 
+    # ------------------------------------------------------------------ PLMS (gaussian_diffusion.py:938-1158)
+    def _ext(self, arr, i, like):
+        """_extract_into_tensor: fp64 table entry -> fp32 scalar tensor on the device (gaussian_diffusion.py:1260-1273)"""
+        return torch.tensor(float(arr[i]), dtype=torch.float64).float().to(like.device)
+
+    @torch.no_grad()
+    def plms_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None, model_kwargs=None,
+                         device=None, progress=False, skip_timesteps=0, init_image=None, randomize_class=False,
+                         cond_fn_with_grad=False, order=2):
+        """Pseudo linear multistep sampling: the reference's third sampler (unused by its CLI).  The denoiser evaluations run in
+        the CUDA library (one forward per call: this sampler needs x0 at TWO points in its first step and an eps history, so it
+        is driven from the host); the multistep arithmetic is a handful of elementwise fp32 ops in the reference's order.
+        Returns the final sample [B,C,1,T] (:1054)."""
+        self._unsupported(denoised_fn, cond_fn, randomize_class, cond_fn_with_grad)
+        if not int(order) or not 1 <= order <= 4:
+            raise ValueError("order is invalid (should be int from 1-4).")
+        dev = self._device_of(model, device)
+        if dev.type != "cuda":
+            raise _lib.A2PError("a2p_b200 samplers run on CUDA only (no CPU fallback)")
+        model_kwargs = model_kwargs or {}
+        B = shape[0]
+        with torch.cuda.device(dev):
+            img, n = self._init_image(shape, noise, dev, skip_timesteps, init_image)
+
+            def model_out(x, i):
+                ts = torch.full((B,), self.timestep_map[i], device=dev, dtype=torch.int64)      # _WrappedModel (respace.py:140-145)
+                out = model(x, ts, **model_kwargs).float()
+                if clip_denoised:
+                    out = out.clamp(-1, 1)
+                x0 = out.permute(0, 2, 1).unsqueeze(2)
+                eps = (self._ext(self.sqrt_recip_alphas_cumprod, i, x) * x - x0) / self._ext(self.sqrt_recipm1_alphas_cumprod, i, x)
+                return eps, x0
+
+            old_eps = None
+            idx = range(n - 1, -1, -1)
+            if progress:
+                from tqdm.auto import tqdm
+                idx = tqdm(idx)
+            for i in idx:
+                abp = self._ext(self.alphas_cumprod_prev, i, img)
+                eps, x0 = model_out(img, i)
+                if order > 1 and old_eps is None:      # pseudo improved Euler (first step)
+                    old_eps = [eps]
+                    mean_pred = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp) * eps
+                    eps_2, _ = model_out(mean_pred, i - 1)
+                    eps_prime = (eps + eps_2) / 2
+                else:                                   # Adams-Bashforth
+                    old_eps = (old_eps or []) + [eps]
+                    cur = min(order, len(old_eps))
+                    if cur == 1:
+                        eps_prime = old_eps[-1]
+                    elif cur == 2:
+                        eps_prime = (3 * old_eps[-1] - old_eps[-2]) / 2
+                    elif cur == 3:
+                        eps_prime = (23 * old_eps[-1] - 16 * old_eps[-2] + 5 * old_eps[-3]) / 12
+                    else:
+                        eps_prime = (55 * old_eps[-1] - 59 * old_eps[-2] + 37 * old_eps[-3] - 9 * old_eps[-4]) / 24
+                pred_prime = self._ext(self.sqrt_recip_alphas_cumprod, i, img) * img - self._ext(self.sqrt_recipm1_alphas_cumprod, i, img) * eps_prime
+                mean_pred = pred_prime * torch.sqrt(abp) + torch.sqrt(1 - abp) * eps_prime
+                if len(old_eps) >= order:
+                    old_eps.pop(0)
+                img = mean_pred if i != 0 else x0
+            return img
+
+
 def create_gaussian_diffusion(args) -> Sampler:
     """Mirror of utils/model_util.py:79-114 (1000 base steps, cosine default, x0-prediction, fixed-small sigma)."""
     steps = 1000

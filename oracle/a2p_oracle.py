@@ -300,3 +300,34 @@ class OracleDiffusion:
             lv = self._ext(self.posterior_log_variance_clipped, i, x)
             x = mean + (1.0 if i != 0 else 0.0) * torch.exp(0.5 * lv) * noise
         return x
+
+    def plms_sample_loop(self, model_fn, x_T: Tensor, order: int = 2, clip_denoised: bool = False):
+        """plms_sample_loop(_progressive) + plms_sample.  gaussian_diffusion.py:938-1158.  Returns the final sample."""
+        x = x_T
+        old_eps = None
+
+        def out(xx, i):
+            x0 = self._x0(model_fn, xx, i, clip_denoised)
+            eps = (self._ext(self.sqrt_recip_alphas_cumprod, i, xx) * xx - x0) / self._ext(self.sqrt_recipm1_alphas_cumprod, i, xx)
+            return eps, x0
+
+        for i in range(self.num_timesteps - 1, -1, -1):
+            abp = self._ext(self.alphas_cumprod_prev, i, x)
+            eps, x0 = out(x, i)
+            if order > 1 and old_eps is None:
+                old_eps = [eps]
+                mean_pred = x0 * torch.sqrt(abp) + torch.sqrt(1 - abp) * eps
+                eps_2, _ = out(mean_pred, i - 1)
+                eps_prime = (eps + eps_2) / 2
+            else:
+                old_eps = (old_eps or []) + [eps]
+                cur = min(order, len(old_eps))
+                eps_prime = {1: lambda e: e[-1], 2: lambda e: (3 * e[-1] - e[-2]) / 2,
+                             3: lambda e: (23 * e[-1] - 16 * e[-2] + 5 * e[-3]) / 12,
+                             4: lambda e: (55 * e[-1] - 59 * e[-2] + 37 * e[-3] - 9 * e[-4]) / 24}[cur](old_eps)
+            pred_prime = self._ext(self.sqrt_recip_alphas_cumprod, i, x) * x - self._ext(self.sqrt_recipm1_alphas_cumprod, i, x) * eps_prime
+            mean_pred = pred_prime * torch.sqrt(abp) + torch.sqrt(1 - abp) * eps_prime
+            if len(old_eps) >= order:
+                old_eps.pop(0)
+            x = mean_pred if i != 0 else x0
+        return x

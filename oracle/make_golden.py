@@ -178,6 +178,26 @@ def golden_loop_variants():
     print("loop_variants_pose_small.npz written")
 
 
+def golden_plms():
+    """plms_sample_loop (gaussian_diffusion.py:938-1158), orders 2 and 4, pose_small ddim10 -> loop_plms_pose_small.npz"""
+    case = CASES["pose_small"]
+    ref, model, diffusion, sd = _ref_model(case, "ddim10")
+    inp = make_inputs(case)
+    cfg = ref.cfg.ClassifierFreeSampleModel(model)
+    y = {"audio": torch.zeros(case.B, 8, 2), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"], "scale": inp["scale"]}
+    fn = lambda x, ts: O.cfg_forward(sd, case.fmt, case.H, x, ts, inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
+    od = O.OracleDiffusion("ddim10")
+    out = {}
+    for order in (2, 4):
+        with torch.no_grad(), RH.synthetic_features(model, inp["feats"]):
+            res = diffusion.plms_sample_loop(cfg, tuple(inp["x"].shape), noise=inp["x"], clip_denoised=False, model_kwargs={"y": y},
+                                             order=order)
+        _close(od.plms_sample_loop(fn, inp["x"], order=order), res, f"plms/order{order}", atol=3e-4, rtol=1e-4)
+        out[f"order{order}"] = res.numpy()
+    np.savez_compressed(os.path.join(GOLD, "loop_plms_pose_small.npz"), **out)
+    print("loop_plms_pose_small.npz written")
+
+
 def golden_caller():
     """The UNMODIFIED caller: sample/generate.py `_setup_model` + `_run_single_diffusion` on CPU with raw audio (the frozen
     extractor runs inside every denoiser call, model/diffusion.py:355-358) -> tests/golden/caller_pose.npz."""
@@ -212,6 +232,9 @@ def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     os.makedirs(GOLD, exist_ok=True)
+    if "plms" in sys.argv:
+        golden_plms()
+        return
     if "caller" in sys.argv:
         golden_caller()
         return

@@ -116,6 +116,20 @@ def test_sampler_variants_vs_reference_golden(golden_dir, kind, terms):
         assert res.abs().max().item() <= 1.0 + 1e-6 if kind == "ddim" else True      # the returned pred_xstart is clipped
 
 
+@pytest.mark.parametrize("order", [2, 4])
+def test_plms_loop_vs_reference_golden(golden_dir, order):
+    """Sampler.plms_sample_loop (denoiser evaluations in the CUDA library, multistep arithmetic on the host) vs the reference"""
+    case = CASES["pose_small"]
+    model, cfg, sampler = _build(case, "ddim10")
+    inp = make_inputs(case)
+    ref = np.load(os.path.join(golden_dir, "loop_plms_pose_small.npz"))[f"order{order}"]
+    res = sampler.plms_sample_loop(cfg, tuple(inp["x"].shape), noise=inp["x"].cuda(), clip_denoised=False, model_kwargs={"y": _y(inp)},
+                                   order=order)
+    _assert_close(res, ref, True, f"plms/order{order}")
+    with pytest.raises(ValueError):
+        sampler.plms_sample_loop(cfg, tuple(inp["x"].shape), noise=inp["x"].cuda(), model_kwargs={"y": _y(inp)}, order=5)
+
+
 def test_ragged_shapes_vs_oracle():
     """Sizes that are not multiples of any tile (T=77, S=131, B=3) against the oracle on seeded inputs."""
     case = Case("ragged", "pose", 2, 8, 3, 77, 131, seed=21, wseed=22, masked=True)

@@ -73,6 +73,17 @@ def test_sampler_variants_match_reference(golden_dir, kind):
     _check(got, ref, atol=3e-4, rtol=1e-4)
 
 
+@pytest.mark.parametrize("order", [2, 4])
+def test_plms_matches_reference(golden_dir, order):
+    """plms_sample_loop (gaussian_diffusion.py:938-1158) restated by the oracle vs the reference's output"""
+    case = CASES["pose_small"]
+    od = O.OracleDiffusion("ddim10")
+    inp, sd = make_inputs(case), weights_of(case)
+    fn = lambda x, ts: O.cfg_forward(sd, case.fmt, case.H, x, ts, inp["feats"], inp["keyframes"], inp["mask"], inp["scale"])
+    ref = np.load(os.path.join(golden_dir, "loop_plms_pose_small.npz"))[f"order{order}"]
+    _check(od.plms_sample_loop(fn, inp["x"], order=order), ref, atol=3e-4, rtol=1e-4)
+
+
 def test_oracle_fp64_agrees_with_fp32():
     case = CASES["pose_small"]
     inp, sd = make_inputs(case), weights_of(case)
