@@ -28,12 +28,6 @@ using namespace a2p;
 
 namespace {
 
-#ifndef A2P_ATTN_DECOUPLE_DEFAULT
-#define A2P_ATTN_DECOUPLE_DEFAULT 0
-#endif
-#ifndef A2P_ATTN_SKEW_DEFAULT_NS
-#define A2P_ATTN_SKEW_DEFAULT_NS 500
-#endif
 constexpr int MAXL = 16;
 constexpr int TCN_PAD = 24;  // receptive_field - 1 (model/diffusion.py:153,215)
 const int TCN_DIL[6] = {1, 2, 3, 1, 2, 3};
@@ -58,10 +52,11 @@ struct GraphKey {
   const void *kv0, *kv1;
   unsigned long long seed; long long row0; int rng;
   int units;   // how the step was cut into concurrent forwards when the graph was captured
+  int pipes;   // independent per-group pipelines (1: all groups joined every step)
   bool operator==(const GraphKey& o) const {
     return B == o.B && T == o.T && kind == o.kind && n_steps == o.n_steps && clip == o.clip && mask == o.mask &&
            coeffs == o.coeffs && ts == o.ts && scale == o.scale && x == o.x && pred == o.pred && noise == o.noise &&
-           ws == o.ws && kv0 == o.kv0 && kv1 == o.kv1 && seed == o.seed && row0 == o.row0 && rng == o.rng && units == o.units;
+           ws == o.ws && kv0 == o.kv0 && kv1 == o.kv1 && seed == o.seed && row0 == o.row0 && rng == o.rng && units == o.units && pipes == o.pipes;
   }
 };
 
@@ -84,12 +79,15 @@ struct a2p_denoiser {
   std::map<const float*, __nv_bfloat16*> wplanes;  // fp32 weight -> split-bf16 planes [P][rows][cols] (plane stride = numel)
   std::map<const float*, long long> wnumel;
   int num_sms = 148;
-  int attn_skew_ns = 0;   // start delay of head 1's softmax warpgroup; no effect with the lockstep MMA loop (profiles/r01f)
-  int attn_decouple = 0;  // per-head MMA scheduling in umma_attn2_kernel (A2P_ATTN_DECOUPLE)
+  int attn_skew_ns = 0;   // start delay of head 1's softmax warpgroup: no effect (profiles/r01f, r02_attn2_decoupled_mma_ab.txt)
   CondSet cond[2];
   int64_t launches = 0;
   int64_t graph_nodes = 0;
-  cudaGraphExec_t gexec = nullptr;
+  static constexpr int MAXG = 4;      // row groups of a CFG step
+  cudaGraphExec_t gexec[MAXG] = {};   // one graph per independent pipeline (one in total when the groups are joined every step)
+  int n_gexec = 0;
+  cudaStream_t group_stream[MAXG] = {};   // pipelines 1.. run on their own stream (pipeline 0: the caller's)
+  cudaEvent_t ev_gstart = nullptr, ev_gdone[MAXG] = {}, ev_gfork[MAXG] = {};
   cudaStream_t cap_stream = nullptr;  // private stream used only to CAPTURE a step (the legacy default stream cannot capture)
   // A sampling step of the fused arm runs as up to MAXU concurrent forwards ("units" = CFG branch x group of batch rows,
   // see sample_loop_impl).  Per unit: a side stream on which the per-step conditioning chain runs beside the first chain /
@@ -530,7 +528,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     TcAttnParams ap{};
     o.Q = qkP; o.q_rows = MT; o.q_ld = 2 * D; o.q_plane_stride = (long long)MT * 2 * D;
     o.vt_rows = D;
-    ap.skew_ns = h->attn_skew_ns; ap.decouple = h->attn_decouple;
+    ap.skew_ns = h->attn_skew_ns;
     if (P == 2) { ap.split_scratch = F(w.splitS); ap.split_counters = reinterpret_cast<int*>(wsb + w.splitC); }
     ap.T = T; ap.R = R; ap.D = D; ap.dh = dh; ap.q_col0 = 0; ap.Op = attP; ap.op_plane_stride = pstrideD; ap.o_ld = D; ap.O = nullptr;
     if (kind == 0) {
@@ -953,15 +951,20 @@ int a2p_denoiser_create(a2p_denoiser_t** out, const a2p_model_cfg* cfg) {
   h->cfg = *cfg;
   h->dh = cfg->D / cfg->H;
   h->nf = cfg->fmt == A2P_FMT_POSE ? 4 : 3;
-  h->attn_decouple = getenv("A2P_ATTN_DECOUPLE") ? atoi(getenv("A2P_ATTN_DECOUPLE")) : A2P_ATTN_DECOUPLE_DEFAULT;
-  h->attn_skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : (h->attn_decouple ? A2P_ATTN_SKEW_DEFAULT_NS : 0);
+  if (getenv("A2P_ATTN_SKEW_NS")) h->attn_skew_ns = atoi(getenv("A2P_ATTN_SKEW_NS"));
   *out = h;
   return 0;
 }
 
 void a2p_denoiser_destroy(a2p_denoiser_t* h) {
   if (!h) return;
-  if (h->gexec) cudaGraphExecDestroy(h->gexec);
+  for (int i = 0; i < a2p_denoiser::MAXG; ++i) {
+    if (h->gexec[i]) cudaGraphExecDestroy(h->gexec[i]);
+    if (h->group_stream[i]) cudaStreamDestroy(h->group_stream[i]);
+    if (h->ev_gdone[i]) cudaEventDestroy(h->ev_gdone[i]);
+    if (h->ev_gfork[i]) cudaEventDestroy(h->ev_gfork[i]);
+  }
+  if (h->ev_gstart) cudaEventDestroy(h->ev_gstart);
   if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   for (int i = 0; i < a2p_denoiser::MAXU; ++i) {
     if (h->cond_stream[i]) cudaStreamDestroy(h->cond_stream[i]);
@@ -1278,102 +1281,149 @@ static int sample_loop_impl(a2p_denoiser_t* h, int kind, int B, int T, int n_ste
     counter = reinterpret_cast<int*>(wsb + shared_off);
     xin = reinterpret_cast<float*>(wsb + shared_off + 256);
   }
-  auto step_body = [&]() -> int {
-    A2P_TRY(transpose_in(c, x, xin, B, cf.C, T));
+  // Independent pipelines (default when the step is cut into G > 1 row groups; A2P_GROUP_PIPELINES=0 joins the groups every
+  // step): nothing in a step couples the row groups -- the CFG mix and the sampler update are per row -- so every group runs its
+  // own chain [transpose -> cond || uncond forward -> K3 -> its own step counter] on its own stream, one graph per group.  The
+  // groups drift apart instead of draining the machine together at every step boundary (the tail of a forward is eight small TCN
+  // launches), and their heavy phases interleave.
+  static const bool pipes_env = !(getenv("A2P_GROUP_PIPELINES") && atoi(getenv("A2P_GROUP_PIPELINES")) == 0);
+  const int n_pipes = (use_units && G > 1 && pipes_env) ? G : 1;
+  // groups [g_lo, g_hi) of one step on stream c.st (g_lo = 0, g_hi = G: the whole step)
+  auto step_body = [&](int g_lo, int g_hi) -> int {
+    const int rb0 = use_units ? (int)((long long)B * g_lo / G) : 0, rb1 = use_units ? (int)((long long)B * g_hi / G) : B;
+    int* cnt = counter + (n_pipes > 1 ? g_lo : 0);
+    {   // [B,C,1,T] -> [B,T,C] for the rows of these groups
+      dim3 grid(ceil_div(T, 32), ceil_div(cf.C, 32), rb1 - rb0), block(32, 8);
+      bct_to_btc_kernel<<<grid, block, 0, c.st>>>(x + (size_t)rb0 * cf.C * T, xin + (size_t)rb0 * T * cf.C, cf.C, T);
+      h->launches++;
+      A2P_CUDA(cudaGetLastError());
+    }
     const float *x0c[a2p_denoiser::MAXU] = {}, *x0u[a2p_denoiser::MAXU] = {};
     int gb0[a2p_denoiser::MAXU] = {}, gB[a2p_denoiser::MAXU] = {};
     long long sstride = 0;
-    int n_groups = 1;
     if (use_units) {
-      n_groups = G;
-      if (!h->ev_bfork) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_bfork, cudaEventDisableTiming));
+      cudaEvent_t& evf = h->ev_gfork[g_lo];
+      if (!evf) A2P_CUDA(cudaEventCreateWithFlags(&evf, cudaEventDisableTiming));
       const int stag = branch_stagger();
-      for (int u = 0; u < units; ++u) {
-        const int g = u >> 1, br = u & 1;                   // unit 0 = (cond, group 0) runs on the caller's stream
+      const int u_first = 2 * g_lo;
+      for (int u = 2 * g_lo; u < 2 * g_hi; ++u) {
+        const int g = u >> 1, br = u & 1;                   // the first unit of the range runs on the caller's stream
         const int b0 = (int)((long long)B * g / G), b1 = (int)((long long)B * (g + 1) / G);
         gb0[g] = b0; gB[g] = b1 - b0;
         Ctx cu{h, c.st};
         cu.slot = u;
-        if (u == 0) {
-          if (stag == 0) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));
-          else { cu.stagger_ev = h->ev_bfork; cu.stagger_after = stag; }
+        if (u == u_first) {
+          if (stag == 0) A2P_CUDA(cudaEventRecord(evf, c.st));
+          else { cu.stagger_ev = evf; cu.stagger_after = stag; }
         } else {
           if (!h->unit_stream[u]) A2P_CUDA(cudaStreamCreateWithFlags(&h->unit_stream[u], cudaStreamNonBlocking));
           if (!h->ev_ujoin[u]) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_ujoin[u], cudaEventDisableTiming));
-          A2P_CUDA(cudaStreamWaitEvent(h->unit_stream[u], h->ev_bfork, 0));
+          A2P_CUDA(cudaStreamWaitEvent(h->unit_stream[u], evf, 0));
           cu.st = h->unit_stream[u];
         }
         const float* dummy = nullptr;
-        A2P_TRY(forward_core(cu, b1 - b0, T, xin + (size_t)b0 * T * cf.C, (const long long*)timesteps, counter,
+        A2P_TRY(forward_core(cu, b1 - b0, T, xin + (size_t)b0 * T * cf.C, (const long long*)timesteps, cnt,
                              br ? A2P_MASK_UNCOND : A2P_MASK_COND, wsb + (size_t)u * region, br ? &dummy : &x0c[g],
                              br ? &x0u[g] : &dummy, &sstride, b0, B));
-        if (u == 0 && cu.stagger_ev) A2P_CUDA(cudaEventRecord(h->ev_bfork, c.st));   // fewer launches than the stagger asked for
-        if (u > 0) A2P_CUDA(cudaEventRecord(h->ev_ujoin[u], h->unit_stream[u]));
+        if (u == u_first && cu.stagger_ev) A2P_CUDA(cudaEventRecord(evf, c.st));   // fewer launches than the stagger asked for
+        if (u != u_first) A2P_CUDA(cudaEventRecord(h->ev_ujoin[u], h->unit_stream[u]));
       }
-      for (int u = 1; u < units; ++u) A2P_CUDA(cudaStreamWaitEvent(c.st, h->ev_ujoin[u], 0));
+      for (int u = u_first + 1; u < 2 * g_hi; ++u) A2P_CUDA(cudaStreamWaitEvent(c.st, h->ev_ujoin[u], 0));
     } else {
       gB[0] = B;
-      A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, counter, branch_mask, wsb, &x0c[0], &x0u[0], &sstride));
+      A2P_TRY(forward_core(c, B, T, xin, (const long long*)timesteps, cnt, branch_mask, wsb, &x0c[0], &x0u[0], &sstride));
     }
-    for (int g = 0; g < n_groups; ++g) {
+    for (int g = g_lo; g < (use_units ? g_hi : 1); ++g) {
       const size_t off = (size_t)gb0[g] * cf.C * T;
       K3Params p{};
-      p.x_t = x + off; p.x0c = x0c[g]; p.x0u = x0u[g]; p.scale = scale ? scale + gb0[g] : nullptr; p.coeffs = coeffs; p.step_counter = counter;
+      p.x_t = x + off; p.x0c = x0c[g]; p.x0u = x0u[g]; p.scale = scale ? scale + gb0[g] : nullptr; p.coeffs = coeffs; p.step_counter = cnt;
       p.noise = noise_tape ? noise_tape + off : nullptr; p.noise_step_stride = (long long)B * cf.C * T; p.n_steps = n_steps;
       p.x_prev = x + off; p.pred = pred_xstart + off; p.B = gB[g]; p.C = cf.C; p.T = T; p.kind = kind; p.clip = clip_denoised;
       p.x0_sample_stride = sstride;
       p.rng = rng; p.seed = seed; p.rng_row0 = row0 + gb0[g];
       A2P_TRY(launch_k3(c, p));
     }
-    step_dec_kernel<<<1, 1, 0, c.st>>>(counter);
+    step_dec_kernel<<<1, 1, 0, c.st>>>(cnt);
     h->launches++;
     A2P_CUDA(cudaGetLastError());
     return 0;
   };
 
-  step_set_kernel<<<1, 1, 0, c.st>>>(counter, n_steps - 1);
-  h->launches++;
-  if (!use_graph) {
-    for (int i = 0; i < n_steps; ++i) A2P_TRY(step_body());
+  for (int pi = 0; pi < n_pipes; ++pi) {
+    step_set_kernel<<<1, 1, 0, c.st>>>(counter + pi, n_steps - 1);
+    h->launches++;
+  }
+  // pipelines 1.. start after everything the caller queued so far (conditioning, the counters) and hand back at the end
+  cudaStream_t user = c.st;
+  auto pipe_stream = [&](int pi) -> cudaStream_t { return pi == 0 ? user : h->group_stream[pi]; };
+  if (n_pipes > 1) {
+    if (!h->ev_gstart) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_gstart, cudaEventDisableTiming));
+    A2P_CUDA(cudaEventRecord(h->ev_gstart, user));
+    for (int pi = 1; pi < n_pipes; ++pi) {
+      if (!h->group_stream[pi]) A2P_CUDA(cudaStreamCreateWithFlags(&h->group_stream[pi], cudaStreamNonBlocking));
+      if (!h->ev_gdone[pi]) A2P_CUDA(cudaEventCreateWithFlags(&h->ev_gdone[pi], cudaEventDisableTiming));
+      A2P_CUDA(cudaStreamWaitEvent(h->group_stream[pi], h->ev_gstart, 0));
+    }
+  }
+  auto join_pipes = [&]() -> int {
+    for (int pi = 1; pi < n_pipes; ++pi) {
+      A2P_CUDA(cudaEventRecord(h->ev_gdone[pi], h->group_stream[pi]));
+      A2P_CUDA(cudaStreamWaitEvent(user, h->ev_gdone[pi], 0));
+    }
     return 0;
+  };
+  auto pipe_groups = [&](int pi, int* lo, int* hi) { if (n_pipes > 1) { *lo = pi; *hi = pi + 1; } else { *lo = 0; *hi = G; } };
+  if (!use_graph) {
+    for (int i = 0; i < n_steps; ++i)
+      for (int pi = 0; pi < n_pipes; ++pi) {
+        int lo, hi; pipe_groups(pi, &lo, &hi);
+        c.st = pipe_stream(pi);
+        A2P_TRY(step_body(lo, hi));
+      }
+    c.st = user;
+    return join_pipes();
   }
   GraphKey key{B, T, kind, n_steps, clip_denoised, branch_mask, coeffs, timesteps, scale, x, pred_xstart, noise_tape, ws,
-               h->cond[0].base, h->cond[1].base, seed, row0, rng, use_units ? units : 0};
+               h->cond[0].base, h->cond[1].base, seed, row0, rng, use_units ? units : 0, n_pipes};
   if (!h->gvalid || !(h->gkey == key)) {
-    if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+    for (int i = 0; i < a2p_denoiser::MAXG; ++i) if (h->gexec[i]) { cudaGraphExecDestroy(h->gexec[i]); h->gexec[i] = nullptr; }
     h->gvalid = false;
-    cudaGraph_t graph = nullptr;
-    int64_t before = h->launches;
-    if (!h->cap_stream) A2P_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
-    cudaStream_t user = c.st;
-    c.st = h->cap_stream;
-    A2P_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeRelaxed));
-    int rc = step_body();
-    cudaError_t ce = cudaStreamEndCapture(c.st, &graph);
-    c.st = user;
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (ce != cudaSuccess) A2P_FAIL("graph capture failed: %s", cudaGetErrorString(ce));
-    h->launches = before;  // captured launches are counted per replay below
     h->graph_nodes = 0;
-    size_t nn = 0;
-    cudaGraphGetNodes(graph, nullptr, &nn);
-    {   // count the KERNEL nodes only (memset / empty join nodes are not launches of ours)
-      std::vector<cudaGraphNode_t> nodes(nn);
-      if (nn) cudaGraphGetNodes(graph, nodes.data(), &nn);
-      for (size_t i = 0; i < nn; ++i) {
-        cudaGraphNodeType ty;
-        if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) h->graph_nodes++;
+    if (!h->cap_stream) A2P_CUDA(cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking));
+    const int64_t before = h->launches;
+    for (int pi = 0; pi < n_pipes; ++pi) {
+      cudaGraph_t graph = nullptr;
+      int lo, hi; pipe_groups(pi, &lo, &hi);
+      c.st = h->cap_stream;
+      A2P_CUDA(cudaStreamBeginCapture(c.st, cudaStreamCaptureModeRelaxed));
+      int rc = step_body(lo, hi);
+      cudaError_t ce = cudaStreamEndCapture(c.st, &graph);
+      c.st = user;
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (ce != cudaSuccess) A2P_FAIL("graph capture failed: %s", cudaGetErrorString(ce));
+      size_t nn = 0;
+      cudaGraphGetNodes(graph, nullptr, &nn);
+      {   // count the KERNEL nodes only (memset / empty join nodes are not launches of ours)
+        std::vector<cudaGraphNode_t> nodes(nn);
+        if (nn) cudaGraphGetNodes(graph, nodes.data(), &nn);
+        for (size_t i = 0; i < nn; ++i) {
+          cudaGraphNodeType ty;
+          if (cudaGraphNodeGetType(nodes[i], &ty) == cudaSuccess && ty == cudaGraphNodeTypeKernel) h->graph_nodes++;
+        }
       }
+      ce = cudaGraphInstantiate(&h->gexec[pi], graph, 0);
+      cudaGraphDestroy(graph);
+      if (ce != cudaSuccess) A2P_FAIL("graph instantiate failed: %s", cudaGetErrorString(ce));
     }
-    ce = cudaGraphInstantiate(&h->gexec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (ce != cudaSuccess) A2P_FAIL("graph instantiate failed: %s", cudaGetErrorString(ce));
+    h->launches = before;  // captured launches are counted per replay below
+    h->n_gexec = n_pipes;
     h->gkey = key;
     h->gvalid = true;
   }
-  for (int i = 0; i < n_steps; ++i) A2P_CUDA(cudaGraphLaunch(h->gexec, c.st));
+  for (int i = 0; i < n_steps; ++i)
+    for (int pi = 0; pi < n_pipes; ++pi) A2P_CUDA(cudaGraphLaunch(h->gexec[pi], pipe_stream(pi)));
   h->launches += h->graph_nodes * n_steps;
-  return 0;
+  return join_pipes();
 }
 
 int a2p_sample_loop(a2p_denoiser_t* h, int kind, int B, int T, int n_steps, const float* coeffs, const int64_t* timesteps,

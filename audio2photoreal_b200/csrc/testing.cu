@@ -117,7 +117,6 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   p.k_row_stride[0] = S; p.v_col_stride[0] = Sp; p.kx_col0 = 0; p.kx_row_stride = 8; p.vx_row0 = 0; p.vx_col_stride = (int)Xp;
   p.O = O; p.o_ld = D; p.Op = nullptr;
   p.skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : 0;
-  p.decouple = getenv("A2P_ATTN_DECOUPLE") ? atoi(getenv("A2P_ATTN_DECOUPLE")) : 0;
   p.trace = (iters < 0) ? reinterpret_cast<long long*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) : nullptr;   // iters < 0: trace mode
   {  // split-KV scratch behind the trace area (the whole scratch buffer was zeroed above, counters included)
     char* tail = reinterpret_cast<char*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) + 64 * 16 * 8;

@@ -46,7 +46,6 @@ struct TcAttnParams {
   // split_parts key ranges each (one work item per range) whose partial (max, sum, O) are merged by the last finisher
   float* split_scratch; int* split_counters; int split_full, split_parts, n_qt, n_groups;
   int skew_ns;                                                    // start delay of softmax warpgroup 1 (see kernel)
-  int decouple;                                                   // umma_attention2.cuh: per-head MMA scheduling (0: lockstep loop)
   long long* trace;                                               // optional [64 iters][16] clock64 timestamps of CTA (0,0,0) (diagnostics)
 };
 

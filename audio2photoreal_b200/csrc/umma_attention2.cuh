@@ -153,7 +153,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
   if (warp == 1 && lane == 0) {
     umma::mbar_init(q_full, 1);
-    for (int i = 0; i < NST; ++i) { umma::mbar_init(&kv_full[i], 1); umma::mbar_init(&kv_empty[i], p.decouple ? 2 : 1); }
+    for (int i = 0; i < NST; ++i) { umma::mbar_init(&kv_full[i], 1); umma::mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 4; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&p_ready[i], 128); umma::mbar_init(&pv_full[i], 1); }
     for (int i = 0; i < 2; ++i) umma::mbar_init(&p_free[i], 1);
     umma::fence_barrier_init();
@@ -211,74 +211,6 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     umma::mbar_wait(q_full, 0);
     int st = 0; uint32_t ph = 0;        // stage / phase of block i (S side)
     int stj = 0;                        // stage of block i - 1 (PV side)
-    if (p.decouple) {
-      // ---- per-head scheduling.  The lockstep loop below issues S(i) of BOTH heads, then waits for p_ready(i-1) of head 0 and
-      // of head 1 in turn: a head that is ahead is held back to the slower one every block, the two softmax warpgroups run in
-      // phase and stall (barrier wake-up, tcgen05.ld, the max chain) at the same time, leaving the issue slots of all four
-      // schedulers empty together.  Here every head advances on its own data flow: S(w, i) as soon as its key block has landed
-      // and PV(w, i-2) has been issued (that frees S/P buffer i & 1; the tensor pipe executes in order), PV(w, j) as soon as
-      // p_ready(w, j).  With head 1 started half an iteration late (TcAttnParams::skew_ns) one warpgroup's exponentials fill
-      // the other's wait phases.  A K/V stage is released when BOTH heads' PV of its block have completed (kv_empty count 2).
-      int js[2] = {0, 0}, jp[2] = {0, 0};
-      auto ready = [&](uint64_t* bar, uint32_t parity) -> bool {   // warp-uniform non-blocking test
-        uint32_t ok = 0;
-        if (lane == 0) ok = umma::mbar_try_wait(bar, parity) ? 1u : 0u;
-        return __shfl_sync(0xffffffffu, ok, 0) != 0;
-      };
-      long long t0 = clock64();
-      while (jp[0] < n_blocks || jp[1] < n_blocks) {
-        bool progressed = false;
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const int i = js[w];
-          if (i < n_blocks && i <= jp[w] + 1 && ready(&kv_full[i % NST], (i / NST) & 1)) {
-            umma::fence_after();
-            if (umma::elect_one()) {
-              const uint32_t lok = loKV + (i % NST) * (Cfg::KV_STAGE_BYTES >> 4) + w * 4;
-              const uint32_t loq = loQ + w * 4;
-              const uint32_t d = tmem_base + w * 128 + (i & 1) * 64;
-#pragma unroll
-              for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                  umma::mma_bf16(d, umma::desc_make(loq + prod_a(pr) * (16384 >> 4) + 2 * k),
-                                 umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
-              umma::mma_commit(&s_full[w * 2 + (i & 1)]);
-            }
-            __syncwarp();
-            js[w] = i + 1;
-            progressed = true;
-          }
-          const int j = jp[w];
-          if (j < js[w] && ready(&p_ready[w * 2 + (j & 1)], (j >> 1) & 1)) {
-            umma::fence_after();
-            if (umma::elect_one()) {
-              const int b = j & 1;
-              const uint32_t lov = loKV + (j % NST) * (Cfg::KV_STAGE_BYTES >> 4) + 2 * (8192 >> 4) + w * (32 * 128 >> 4);
-              const uint32_t d = tmem_base + 256 + w * 64 + b * 32;
-              const uint32_t tp = tmem_base + w * 128 + b * 64;
-              const uint32_t lop = loP + w * (2 * 16384 >> 4);
-#pragma unroll
-              for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint64_t bd = umma::desc_make(lov + prod_b(pr) * (8192 >> 4) + 2 * k);
-                  if (PT) mma_bf16_ts(d, tp + prod_a(pr) * 32 + 8 * k, bd, idPV, (pr | k) != 0 ? 1u : 0u);
-                  else umma::mma_bf16(d, umma::desc_make(lop + prod_a(pr) * (16384 >> 4) + 2 * k), bd, idPV, (pr | k) != 0 ? 1u : 0u);
-                }
-              umma::mma_commit(&pv_full[w * 2 + b]);
-              if (!PT) umma::mma_commit(&p_free[w]);
-              umma::mma_commit(&kv_empty[j % NST]);
-            }
-            __syncwarp();
-            jp[w] = j + 1;
-            progressed = true;
-          }
-        }
-        if (progressed) t0 = clock64();
-        else if (clock64() - t0 > 4000000000LL) __trap();     // a protocol bug must never hang the box
-      }
-    } else
     for (int i = 0; i <= n_blocks; ++i) {
       A2_TRACE(8, lane == 0);
       if (i < n_blocks) {

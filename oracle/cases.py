@@ -27,6 +27,7 @@ class Case:
     seed: int = 0
     wseed: int = 1
     masked: bool = False   # knock out some keyframes through y["mask"]
+    gstep: float = 1.5     # per-row guidance scale = guidance + gstep * row (exercises the per-sample scale of cfg_sampler.py:33)
 
 
 CASES: Dict[str, Case] = {c.name: c for c in [
@@ -40,7 +41,9 @@ CASES: Dict[str, Case] = {c.name: c for c in [
     Case("pose_smoke", "pose", 2, 8, 2, 160, 398, seed=15, wseed=16, masked=True),
     # the BENCHMARKED configuration (BASELINE configs[1]: pose, T=600, all 1000 steps, CFG) at a batch that takes the
     # loop's row-group cut (4 concurrent forwards, batch-row offsets b0 > 0)
-    Case("pose_full_b4", "pose", 6, 8, 4, 600, 1998, respacing="", seed=13, wseed=14),
+    Case("pose_full_b4", "pose", 6, 8, 4, 600, 1998, respacing="", seed=13, wseed=14),      # guidance 2.0, 3.5, 5.0, 6.5 per row
+    # the same with the benchmark's constant guidance 2.0 on every row (sample/generate.py:128-130 applies ONE guidance_param)
+    Case("pose_full_b4_g2", "pose", 6, 8, 4, 600, 1998, respacing="", seed=13, wseed=14, gstep=0.0),
 ]}
 
 
@@ -57,7 +60,7 @@ def make_inputs(case: Case, n_noise: int = 0) -> Dict[str, torch.Tensor]:
     out = {
         "x": f32(rs.standard_normal((case.B, C, 1, case.T))),
         "feats": f32(rs.standard_normal((case.B, case.S, cd))),
-        "scale": f32(case.guidance + 1.5 * np.arange(case.B)),
+        "scale": f32(case.guidance + case.gstep * np.arange(case.B)),
         "times": torch.from_numpy(rs.randint(0, 1000, size=(case.B,)).astype(np.int64)),
     }
     nk = len(range(0, case.T, 30))

@@ -242,7 +242,8 @@ def main():
         golden_loop_variants()
         return
     if "loop1000" in sys.argv:     # the benchmarked configuration: all 1000 steps, B = 4, CFG (minutes of CPU time)
-        golden_loop("pose_full_b4", "", "ddim", check_oracle="--no-oracle" not in sys.argv)
+        name = "pose_full_b4_g2" if "g2" in sys.argv else "pose_full_b4"
+        golden_loop(name, "", "ddim", check_oracle="--no-oracle" not in sys.argv)
         return
     golden_schedule()
     for n in ["pose_small", "pose_small_h4", "face_small", "pose_full", "face_full"]:
