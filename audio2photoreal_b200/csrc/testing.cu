@@ -147,6 +147,8 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   return 0;
 }
 
+void a2p_test_attn2_set_persist(int on) { attn2_persist_override() = on < 0 ? -1 : (on != 0); }
+
 void a2p_test_chain_set_mode(int cl) { chain_mode_override() = (cl == 1 || cl == 2) ? cl : 0; }
 
 size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T) {

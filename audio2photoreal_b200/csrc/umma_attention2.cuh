@@ -35,7 +35,7 @@ struct Attn2Cfg {
   static constexpr int Q_BYTES = 2 * 16384;            // [2 planes][128 rows][64 cols] bf16
   static constexpr int KV_STAGE_BYTES = 2 * 2 * 8192;  // K planes then V^T planes, 8 KB each
   static constexpr int P_BYTES = PT ? 0 : 2 * 2 * 16384;   // [head][plane][128 rows][64 keys] bf16
-  static constexpr int SMEM_BYTES = Q_BYTES + NST * KV_STAGE_BYTES + P_BYTES + 1024 + 512;
+  static constexpr int SMEM_BYTES = 2 * Q_BYTES + NST * KV_STAGE_BYTES + P_BYTES + 1024 + 512;   // two Q buffers (persistent CTAs)
   static constexpr int THREADS = 384;
 };
 
@@ -116,11 +116,11 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   constexpr int NST = Cfg::NST;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sQ = smem;
-  uint8_t* sKV = sQ + Cfg::Q_BYTES;
+  uint8_t* sQ = smem;                  // [2 buffers][2 planes][128 rows][64 cols]
+  uint8_t* sKV = sQ + 2 * Cfg::Q_BYTES;
   uint8_t* sP = sKV + NST * Cfg::KV_STAGE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sP + Cfg::P_BYTES);
-  uint64_t* q_full = bars;             // [1]
+  uint64_t* q_full = bars;             // [2] at bars[0], bars[26]  (see qf())
   uint64_t* kv_full = bars + 1;        // [3]
   uint64_t* kv_empty = bars + 4;       // [3]
   uint64_t* s_full = bars + 7;         // [head][2]
@@ -128,31 +128,44 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   uint64_t* pv_full = bars + 15;       // [head][2]
   uint64_t* p_free = bars + 19;        // [head]     (PT = 0: the shared-memory P buffer has been read by PV)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  uint64_t* q_empty = bars + 28;       // [2] the S products of the work item that used Q buffer b have completed
+  auto qf = [&](int b) -> uint64_t* { return b ? bars + 26 : q_full; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // work item -> (tile, key range).  Tiles beyond split_full are cut into split_parts key ranges: a launch whose tile count is
-  // not a multiple of the SM count would otherwise leave most SMs idle during its last round (320 tiles on 148 SMs = 3 rounds
-  // for 2.16 rounds of work), and a small batch would not fill the machine at all.
-  int tile = blockIdx.x, part = 0, nparts = 1;
-  if ((int)blockIdx.x >= p.split_full) {
-    const int t_ = blockIdx.x - p.split_full;
-    tile = p.split_full + t_ / p.split_parts; part = t_ % p.split_parts; nparts = p.split_parts;
-  }
-  const int q0 = (tile % p.n_qt) * 128, g = (tile / p.n_qt) % p.n_groups, r = tile / (p.n_qt * p.n_groups);
-  const int br = r >= p.rows_per_branch ? 1 : 0;
-  const int rr = r - br * p.rows_per_branch;
+  // Work items.  Item -> (tile, key range): tiles beyond split_full are cut into split_parts key ranges (a launch whose tile count
+  // is not a multiple of the SM count would otherwise leave most SMs idle during its last round, and a small batch would not
+  // fill the machine at all).  A CTA processes items blockIdx.x, blockIdx.x + gridDim.x, ...: with one CTA per item this is the
+  // plain one-tile kernel; with a grid of (at most) one CTA per SM the CTAs are PERSISTENT -- tensor memory, barriers and the
+  // tensor maps are set up once, the producer warp prefetches the next item's Q tile and first key blocks while the softmax
+  // warps are still normalising / storing the current item, and the per-tile launch / drain gaps disappear.  All pipeline
+  // indices (S / P / PV buffer, barrier parity, K/V ring stage) run on over the items: block i of an item has the global
+  // index base + i, base = number of key blocks of this CTA's earlier items, identical in every role.
+  const int n_items = p.split_full + (p.n_qt * p.n_groups * p.R - p.split_full) * p.split_parts;
   const int nb_main = ceil_div(p.n_keys, 64);
   const int n_blocks_all = nb_main + (p.n_extra > 0 ? 1 : 0);
-  const int kb0 = part * n_blocks_all / nparts, kb1 = (part + 1) * n_blocks_all / nparts;
-  const int n_blocks = kb1 - kb0;        // key blocks [kb0, kb1) of this work item; local index i <-> global block kb0 + i
+  struct Item { int tile, part, nparts, q0, g, r, br, rr, kb0, n_blocks; };
+  auto decode = [&](int item) -> Item {
+    Item it;
+    it.tile = item; it.part = 0; it.nparts = 1;
+    if (item >= p.split_full) {
+      const int t_ = item - p.split_full;
+      it.tile = p.split_full + t_ / p.split_parts; it.part = t_ % p.split_parts; it.nparts = p.split_parts;
+    }
+    it.q0 = (it.tile % p.n_qt) * 128; it.g = (it.tile / p.n_qt) % p.n_groups; it.r = it.tile / (p.n_qt * p.n_groups);
+    it.br = it.r >= p.rows_per_branch ? 1 : 0;
+    it.rr = it.r - it.br * p.rows_per_branch;
+    it.kb0 = it.part * n_blocks_all / it.nparts;
+    it.n_blocks = (it.part + 1) * n_blocks_all / it.nparts - it.kb0;     // key blocks [kb0, kb0 + n_blocks): local i <-> global kb0 + i
+    return it;
+  };
 
   if (warp == 0 && lane == 0) {
     umma::prefetch_tmap(&tmQ);
-    umma::prefetch_tmap(br ? &tmK1 : &tmK0);
-    umma::prefetch_tmap(br ? &tmV1 : &tmV0);
+    umma::prefetch_tmap(&tmK0); umma::prefetch_tmap(&tmV0);
+    if (p.R > p.rows_per_branch) { umma::prefetch_tmap(&tmK1); umma::prefetch_tmap(&tmV1); }
   }
   if (warp == 1 && lane == 0) {
-    umma::mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(qf(i), 1); umma::mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < NST; ++i) { umma::mbar_init(&kv_full[i], 1); umma::mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 4; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&p_ready[i], 128); umma::mbar_init(&pv_full[i], 1); }
     for (int i = 0; i < 2; ++i) umma::mbar_init(&p_free[i], 1);
@@ -168,102 +181,117 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   // TMEM map: head w: S/P buffers at w*128 + b*64, PV buffers at 256 + w*64 + b*32
   if (warp == 0) {
     // ================= TMA producer =================
-    if (umma::elect_one()) {
-      umma::mbar_expect_tx(q_full, Cfg::Q_BYTES);
-#pragma unroll
-      for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmQ, q_full, sQ + i * 16384, p.q_col0 + g * 64, r * p.T + q0, i);
-    }
-    __syncwarp();
-    const CUtensorMap* tK = br ? &tmK1 : &tmK0;
-    const CUtensorMap* tV = br ? &tmV1 : &tmV0;
-    const int k_row_base = (int)(rr * p.k_row_stride[br]);
-    const int v_col_base = (int)(rr * p.v_col_stride[br]);
     int st = 0; uint32_t ph = 0;
-    for (int j = 0; j < n_blocks; ++j) {
-      umma::mbar_wait(&kv_empty[st], ph ^ 1);
+    int itn = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++itn) {
+      const Item it = decode(item);
+      const int qb = itn & 1;
+      umma::mbar_wait(&q_empty[qb], ((itn >> 1) & 1) ^ 1);      // the item that used this Q buffer two items ago is done with it
       if (umma::elect_one()) {
-        umma::mbar_expect_tx(&kv_full[st], Cfg::KV_STAGE_BYTES);
-        uint8_t* sk = sKV + st * Cfg::KV_STAGE_BYTES;
-        uint8_t* sv = sk + 2 * 8192;
-        const int gb = kb0 + j;
-        if (gb < nb_main) {
+        umma::mbar_expect_tx(qf(qb), Cfg::Q_BYTES);
 #pragma unroll
-          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tK, &kv_full[st], sk + i * 8192, p.k_col0 + g * 64, k_row_base + gb * 64, i);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) umma::tma_load_3d(tV, &kv_full[st], sv + i * 8192, v_col_base + gb * 64, g * 64, i);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmKx, &kv_full[st], sk + i * 8192, p.kx_col0 + g * 64, r * p.kx_row_stride, i);
-#pragma unroll
-          for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmVx, &kv_full[st], sv + i * 8192, r * p.vx_col_stride, p.vx_row0 + g * 64, i);
-        }
+        for (int i = 0; i < 2; ++i)
+          umma::tma_load_3d(&tmQ, qf(qb), sQ + qb * Cfg::Q_BYTES + i * 16384, p.q_col0 + it.g * 64, it.r * p.T + it.q0, i);
       }
       __syncwarp();
-      if (++st == NST) { st = 0; ph ^= 1; }
+      const CUtensorMap* tK = it.br ? &tmK1 : &tmK0;
+      const CUtensorMap* tV = it.br ? &tmV1 : &tmV0;
+      const int k_row_base = (int)(it.rr * p.k_row_stride[it.br]);
+      const int v_col_base = (int)(it.rr * p.v_col_stride[it.br]);
+      for (int j = 0; j < it.n_blocks; ++j) {
+        umma::mbar_wait(&kv_empty[st], ph ^ 1);
+        if (umma::elect_one()) {
+          umma::mbar_expect_tx(&kv_full[st], Cfg::KV_STAGE_BYTES);
+          uint8_t* sk = sKV + st * Cfg::KV_STAGE_BYTES;
+          uint8_t* sv = sk + 2 * 8192;
+          const int gb = it.kb0 + j;
+          if (gb < nb_main) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) umma::tma_load_3d(tK, &kv_full[st], sk + i * 8192, p.k_col0 + it.g * 64, k_row_base + gb * 64, i);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) umma::tma_load_3d(tV, &kv_full[st], sv + i * 8192, v_col_base + gb * 64, it.g * 64, i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmKx, &kv_full[st], sk + i * 8192, p.kx_col0 + it.g * 64, it.r * p.kx_row_stride, i);
+#pragma unroll
+            for (int i = 0; i < 2; ++i) umma::tma_load_3d(&tmVx, &kv_full[st], sv + i * 8192, it.r * p.vx_col_stride, p.vx_row0 + it.g * 64, i);
+          }
+        }
+        __syncwarp();
+        if (++st == NST) { st = 0; ph ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);
     constexpr uint32_t idPV = umma::idesc_bf16_f32(128, 32);
-    const uint32_t loQ = umma::desc_lo(umma::smem_u32(sQ));
     const uint32_t loKV = umma::desc_lo(umma::smem_u32(sKV));
     const uint32_t loP = umma::desc_lo(umma::smem_u32(sP));
-    umma::mbar_wait(q_full, 0);
-    int st = 0; uint32_t ph = 0;        // stage / phase of block i (S side)
-    int stj = 0;                        // stage of block i - 1 (PV side)
-    for (int i = 0; i <= n_blocks; ++i) {
-      A2_TRACE(8, lane == 0);
-      if (i < n_blocks) {
-        umma::mbar_wait(&kv_full[st], ph);
-        umma::fence_after();
-        A2_TRACE(9, lane == 0);
-        if (umma::elect_one()) {
-#pragma unroll
-          for (int w = 0; w < 2; ++w) {
-            const uint32_t lok = loKV + st * (Cfg::KV_STAGE_BYTES >> 4) + w * 4;   // head w: columns [32w, 32w+32) = +64 B
-            const uint32_t loq = loQ + w * 4;
-            const uint32_t d = tmem_base + w * 128 + (i & 1) * 64;
-#pragma unroll
-            for (int pr = 0; pr < 3; ++pr)
-#pragma unroll
-              for (int k = 0; k < 2; ++k)
-                umma::mma_bf16(d, umma::desc_make(loq + prod_a(pr) * (16384 >> 4) + 2 * k),
-                               umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
-            umma::mma_commit(&s_full[w * 2 + (i & 1)]);
-          }
-        }
-        __syncwarp();
-      }
-      if (i > 0) {
-        const int j = i - 1, b = j & 1;
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          A2_TRACE(10 + 2 * w, lane == 0);
-          umma::mbar_wait(&p_ready[w * 2 + b], (j >> 1) & 1);
+    int st = 0; uint32_t ph = 0;        // stage / phase of the next S block (runs on over the items)
+    int stj = 0;                        // stage of the next PV block
+    int base = 0, itn = 0;              // global index of this item's block 0; item counter
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++itn) {
+      const int n_blocks = decode(item).n_blocks;
+      const int qb = itn & 1;
+      const uint32_t loQ = umma::desc_lo(umma::smem_u32(sQ + qb * Cfg::Q_BYTES));
+      umma::mbar_wait(qf(qb), (itn >> 1) & 1);
+      for (int i = 0; i <= n_blocks; ++i) {
+        const int gi = base + i;          // buffers / parities follow the global block index
+        A2_TRACE(8, lane == 0);
+        if (i < n_blocks) {
+          umma::mbar_wait(&kv_full[st], ph);
           umma::fence_after();
-          A2_TRACE(11 + 2 * w, lane == 0);
+          A2_TRACE(9, lane == 0);
           if (umma::elect_one()) {
-            const uint32_t lov = loKV + stj * (Cfg::KV_STAGE_BYTES >> 4) + 2 * (8192 >> 4) + w * (32 * 128 >> 4);   // V^T rows [32w, 32w+32)
-            const uint32_t d = tmem_base + 256 + w * 64 + b * 32;
-            const uint32_t tp = tmem_base + w * 128 + b * 64;                    // P planes: +0 (hi), +32 (lo); 8 columns per 16 keys
-            const uint32_t lop = loP + w * (2 * 16384 >> 4);
 #pragma unroll
-            for (int pr = 0; pr < 3; ++pr)
+            for (int w = 0; w < 2; ++w) {
+              const uint32_t lok = loKV + st * (Cfg::KV_STAGE_BYTES >> 4) + w * 4;   // head w: columns [32w, 32w+32) = +64 B
+              const uint32_t loq = loQ + w * 4;
+              const uint32_t d = tmem_base + w * 128 + (gi & 1) * 64;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const uint64_t bd = umma::desc_make(lov + prod_b(pr) * (8192 >> 4) + 2 * k);
-                if (PT) mma_bf16_ts(d, tp + prod_a(pr) * 32 + 8 * k, bd, idPV, (pr | k) != 0 ? 1u : 0u);
-                else umma::mma_bf16(d, umma::desc_make(lop + prod_a(pr) * (16384 >> 4) + 2 * k), bd, idPV, (pr | k) != 0 ? 1u : 0u);
-              }
-            umma::mma_commit(&pv_full[w * 2 + b]);
-            if (!PT) umma::mma_commit(&p_free[w]);
-            if (w == 1) umma::mma_commit(&kv_empty[stj]);
+              for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                  umma::mma_bf16(d, umma::desc_make(loq + prod_a(pr) * (16384 >> 4) + 2 * k),
+                                 umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
+              umma::mma_commit(&s_full[w * 2 + (gi & 1)]);
+            }
+            if (i == n_blocks - 1) umma::mma_commit(&q_empty[qb]);      // last read of this item's Q tile
           }
           __syncwarp();
         }
-        if (++stj == NST) stj = 0;
+        if (i > 0) {
+          const int gj = gi - 1, b = gj & 1;
+#pragma unroll
+          for (int w = 0; w < 2; ++w) {
+            A2_TRACE(10 + 2 * w, lane == 0);
+            umma::mbar_wait(&p_ready[w * 2 + b], (gj >> 1) & 1);
+            umma::fence_after();
+            A2_TRACE(11 + 2 * w, lane == 0);
+            if (umma::elect_one()) {
+              const uint32_t lov = loKV + stj * (Cfg::KV_STAGE_BYTES >> 4) + 2 * (8192 >> 4) + w * (32 * 128 >> 4);   // V^T rows [32w, 32w+32)
+              const uint32_t d = tmem_base + 256 + w * 64 + b * 32;
+              const uint32_t tp = tmem_base + w * 128 + b * 64;                    // P planes: +0 (hi), +32 (lo); 8 columns per 16 keys
+              const uint32_t lop = loP + w * (2 * 16384 >> 4);
+#pragma unroll
+              for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint64_t bd = umma::desc_make(lov + prod_b(pr) * (8192 >> 4) + 2 * k);
+                  if (PT) mma_bf16_ts(d, tp + prod_a(pr) * 32 + 8 * k, bd, idPV, (pr | k) != 0 ? 1u : 0u);
+                  else umma::mma_bf16(d, umma::desc_make(lop + prod_a(pr) * (16384 >> 4) + 2 * k), bd, idPV, (pr | k) != 0 ? 1u : 0u);
+                }
+              umma::mma_commit(&pv_full[w * 2 + b]);
+              if (!PT) umma::mma_commit(&p_free[w]);
+              if (w == 1) umma::mma_commit(&kv_empty[stj]);
+            }
+            __syncwarp();
+          }
+          if (++stj == NST) stj = 0;
+        }
+        if (i < n_blocks) { if (++st == NST) { st = 0; ph ^= 1; } }
       }
-      if (i < n_blocks) { if (++st == NST) { st = 0; ph ^= 1; } }
+      base += n_blocks;
     }
   } else if (warp >= 4) {
     // ================= softmax / output: warpgroup w owns head w =================
@@ -275,9 +303,8 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t tmO = tmem_base + lane_addr + 256 + w * 64;
     const uint32_t sP_u32 = umma::smem_u32(sP) + w * (2 * 16384) + trow * 128;
     float m = -INFINITY, l = 0.f, o[32];
-#pragma unroll
-    for (int c = 0; c < 32; ++c) o[c] = 0.f;
     float alpha_pend = 1.f;
+    int base = 0, kb0 = 0;               // global index of the current item's block 0; its first key block
     // The two warpgroups would run in lockstep (both S tiles arrive together) and hit the MUFU-bound exponential phase at
     // the same time; starting head 1 half an iteration late lets one warpgroup's exponentials overlap the other's
     // load / max / barrier phase on every scheduler.
@@ -296,9 +323,10 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     // that the hot loop carries no per-score select
     auto block = [&](int i, auto masked_tag) {
       constexpr bool MASKED = decltype(masked_tag)::value;
-      const int b = i & 1;
+      const int gi = base + i;           // S / P / PV buffers and barrier parities follow the global block index
+      const int b = gi & 1;
       A2_TRACE(0, threadIdx.x == 128);
-      umma::mbar_wait(&s_full[w * 2 + b], (i >> 1) & 1);
+      umma::mbar_wait(&s_full[w * 2 + b], (gi >> 1) & 1);
       umma::fence_after();
       A2_TRACE(1, threadIdx.x == 128);
       float s[64];
@@ -306,7 +334,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       umma::tmem_ld32(tmS + b * 64 + 32, s + 32);
       // PV(i-1) landed long ago: fold it into O now, so that its tcgen05.ld shares the wait with the S loads and its 32
       // FMAs fill the issue slots between the exponentials below instead of trailing the iteration
-      if (i > 0) consume_pv(i - 1, alpha_pend);
+      if (i > 0) consume_pv(gi - 1, alpha_pend);
       else umma::tmem_ld_wait();
       A2_TRACE(2, threadIdx.x == 128);
       if (MASKED) {
@@ -324,7 +352,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       m = mnew;
       const float nm = -mnew;
       A2_TRACE(3, threadIdx.x == 128);
-      if (!PT && i > 0) umma::mbar_wait(&p_free[w], (i - 1) & 1);   // PV(i-1) has finished reading the shared-memory planes
+      if (!PT && gi > 0) umma::mbar_wait(&p_free[w], (gi - 1) & 1);   // PV(gi-1) has finished reading the shared-memory planes
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
@@ -372,13 +400,20 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       A2_TRACE(6, threadIdx.x == 128);
       alpha_pend = alpha;
     };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const Item it = decode(item);
+    const int n_blocks = it.n_blocks, tile = it.tile, part = it.part, nparts = it.nparts, q0 = it.q0, g = it.g, r = it.r;
+    kb0 = it.kb0;
+    m = -INFINITY; l = 0.f; alpha_pend = 1.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) o[c] = 0.f;
     const int n_full = ::max(0, ::min(p.n_keys / 64 - kb0, n_blocks));    // leading blocks whose 64 keys are all valid
     int i = 0;
 #pragma unroll 1
     for (; i < n_full; ++i) block(i, std::false_type{});
 #pragma unroll 1
     for (; i < n_blocks; ++i) block(i, std::true_type{});
-    consume_pv(n_blocks - 1, alpha_pend);
+    consume_pv(base + n_blocks - 1, alpha_pend);
     bool writer = true;
     if (nparts > 1) {
       // ---- split tile: publish this key range's (max, sum, O); the LAST work item of the tile to finish merges them all
@@ -446,6 +481,8 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
     }
+    base += n_blocks;
+    }   // items
   }
   __syncthreads();
   if (warp == 2) {
@@ -458,6 +495,16 @@ inline int attn2_num_sms() {
   static int v = -1;
   if (v < 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev); if (v <= 0) v = 148; }
   return v;
+}
+#ifndef A2P_ATTN_PERSIST_DEFAULT
+#define A2P_ATTN_PERSIST_DEFAULT 0
+#endif
+inline int& attn2_persist_override() { static int v = -1; return v; }     // tests: 0 / 1 forces the mode of the next launches
+inline bool attn2_persistent() {
+  if (attn2_persist_override() >= 0) return attn2_persist_override() != 0;
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("A2P_ATTN_PERSIST"); v = e ? (atoi(e) != 0) : A2P_ATTN_PERSIST_DEFAULT; }
+  return v == 1;
 }
 inline bool attn2_split_disabled() {
   static int v = -1;
@@ -498,7 +545,9 @@ int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStre
     if (parts > 8) parts = 8;
     if (parts >= 2) { q.split_full = n_tiles - rem; q.split_parts = parts; }
   }
-  dim3 grid(q.split_full + (n_tiles - q.split_full) * q.split_parts);
+  const int n_items = q.split_full + (n_tiles - q.split_full) * q.split_parts;
+  // persistent CTAs (A2P_ATTN_PERSIST=1): one CTA per SM walks items blockIdx.x, + gridDim.x, ...; default: one CTA per item
+  dim3 grid(attn2_persistent() && n_items > sms ? sms : n_items);
   A2P_CUDA(launch_pdl(umma_attn2_kernel<PT, POLY>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
                       tkx, tvx, q));
   return 0;

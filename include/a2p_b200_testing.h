@@ -28,6 +28,8 @@ size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_ext
 int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K,
                           const float* V, const float* Kx, const float* Vx, float* O, void* scratch, size_t scratch_bytes,
                           int iters, float* ms_out, void* stream);
+/* umma_attn2_kernel scheduling: 1 = persistent CTAs (one per SM walks the work items), 0 = one CTA per work item, -1 = library default */
+void a2p_test_attn2_set_persist(int on);
 /* the exact-fp32 FFMA attention on the same inputs */
 int a2p_test_simt_attention(int R, int T, int D, int dh, int S, int n_extra, const float* Q, const float* K, const float* V,
                             const float* Kx, const float* Vx, float* O, int iters, float* ms_out, void* stream);

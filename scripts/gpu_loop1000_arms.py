@@ -7,9 +7,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from oracle.cases import CASES, make_inputs, weights_of
 from audio2photoreal_b200.api import CFGDenoiser, create_model_and_diffusion, load_model
 
-case = CASES["pose_full_b4"]
-ref = torch.from_numpy(np.load("tests/golden/loop_ddim_pose_full_b4_full.npz")["result"]).double()
+NAME = sys.argv[1] if len(sys.argv) > 1 else "pose_full_b4"
+case = CASES[NAME]
+ref = torch.from_numpy(np.load(f"tests/golden/loop_ddim_{NAME}_full.npz")["result"]).double()
 inp = make_inputs(case)
+print(f"case {NAME}: guidance scales {inp['scale'].tolist()}")
 out = {}
 for terms in (0, 3, 2):
     args = Namespace(data_format="pose", add_frame_cond=1, max_seq_length=600, layers=case.L, heads=case.H, not_rotary=False,
@@ -29,6 +31,8 @@ for terms in (0, 3, 2):
     d = (r - ref).abs()
     bad = d > 1e-4 + 1e-3 * ref.abs()
     q = torch.quantile(d.flatten()[:: 7].float(), torch.tensor([0.5, 0.99, 0.9999]))
+    rows = [(d[b].max().item(), int(bad[b].sum())) for b in range(d.shape[0])]
+    print(f"terms={terms}: per-row (max|d|, #outside): " + ", ".join(f"({a:.2e}, {n})" for a, n in rows))
     print(f"terms={terms}: {dt:.1f}s  max|d|={d.max():.3e}  outside={bad.double().mean():.5%} ({int(bad.sum())} of {bad.numel()})  "
           f"median/p99/p99.99 |d| = {q[0]:.2e}/{q[1]:.2e}/{q[2]:.2e}  |ref|max={ref.abs().max():.3f}", flush=True)
     del model, cfg, sampler

@@ -62,6 +62,13 @@ if __name__ == "__main__":
         for terms in (21, 22, 23):     # 22 / 23: 1 / 2 of every 4 exponentials on the FMA pipe
             run(terms, 16, 600, 256, 32, 1998, 2)
             run(terms, 16, 600, 256, 32, 600, 0)
+    if which == "persist":         # persistent-CTA schedule A/B at the loop's launch shapes
+        lib.a2p_test_attn2_set_persist.argtypes = [C.c_int]
+        for on in (0, 1):
+            lib.a2p_test_attn2_set_persist(on)
+            print("persist", on)
+            for R, S, nx in ((4, 1998, 2), (4, 600, 0), (8, 1998, 2), (8, 600, 0), (32, 1998, 2), (32, 600, 0)):
+                run(21, R, 600, 256, 32, S, nx)
     if which == "decouple":        # attention2 timings at the loop's launch shapes (used for the r02 per-head MMA scheduling A/B, profiles/experiments/)
         for R, S, nx in ((4, 1998, 2), (4, 600, 0), (32, 1998, 2), (32, 600, 0), (2, 77, 2), (1, 200, 0)):
             T = 600 if R > 2 else 100

@@ -67,8 +67,9 @@ def test_tc_loops_vs_reference_golden(golden_dir, name, resp, terms):
     assert model.launch_count() > 0
 
 
+@pytest.mark.parametrize("name", ["pose_full_b4_g2", "pose_full_b4"])
 @pytest.mark.parametrize("terms", [0, 3, 2])
-def test_benchmarked_configuration_1000_steps_vs_reference_golden(golden_dir, terms):
+def test_benchmarked_configuration_1000_steps_vs_reference_golden(golden_dir, terms, name):
     """BASELINE configs[1] itself: pose L=6, T=600, S=1998, CFG, ALL 1000 steps (timestep_respacing ''), at B = 4 so that the
     fused arm takes its default cut into concurrent forwards (2 CFG branches x 2 row groups, batch-row offsets b0 > 0), against
     the REFERENCE's own ddim_sample_loop output (oracle/make_golden.py loop1000).
@@ -78,13 +79,15 @@ def test_benchmarked_configuration_1000_steps_vs_reference_golden(golden_dir, te
     tensor-core arms from the exact arm is the same for two and three planes (2.8e-5 vs 3.2e-5 rms, profiles/
     r02_arm_error_probe.txt): it is the accumulation of tcgen05 (fp32 accumulators are truncated, not rounded, per MMA), not the
     operand split, and it is systematic, so it adds up over the 1000 steps.  The exact and three-plane arms must meet the strict
-    criterion; the two-plane arm is held to <= 0.01 % of the elements outside it and max|d| <= 4e-4."""
-    case = CASES["pose_full_b4"]
+    criterion; the two-plane arm is held to <= 0.01 % of the elements outside it and max|d| <= 4e-4 on `pose_full_b4`, whose rows
+    carry guidance scales 2.0 / 3.5 / 5.0 / 6.5 (the CFG mix amplifies the branches' errors by |s| + |1 - s| = 3 ... 12), and to the
+    strict criterion on `pose_full_b4_g2`, the benchmark's own constant guidance 2.0 (sample/generate.py:128-130)."""
+    case = CASES[name]
     model, cfg, sampler = _build(case, "", terms)
     assert sampler.num_timesteps == 1000
     inp = make_inputs(case)
     y = {"audio_embed": inp["feats"].cuda(), "keyframes": inp["keyframes"].clone(), "mask": inp["mask"], "scale": inp["scale"].cuda()}
-    ref = torch.from_numpy(np.load(os.path.join(golden_dir, "loop_ddim_pose_full_b4_full.npz"))["result"]).double()
+    ref = torch.from_numpy(np.load(os.path.join(golden_dir, f"loop_ddim_{name}_full.npz"))["result"]).double()
     res = sampler.ddim_sample_loop(cfg, tuple(inp["x"].shape), noise=inp["x"].cuda(), clip_denoised=False, model_kwargs={"y": y})
     from audio2photoreal_b200 import _lib as L
     if terms == 2:
@@ -92,8 +95,8 @@ def test_benchmarked_configuration_1000_steps_vs_reference_golden(golden_dir, te
     d = (res.double().cpu() - ref).abs()
     bad = d > ATOL + RTOL * ref.abs()
     frac, mx = bad.double().mean().item(), d.max().item()
-    print(f"1000 steps, terms={terms}: max|d|={mx:.3e}, {frac:.4%} outside rtol 1e-3 / atol 1e-4")
-    if terms == 2:
+    print(f"1000 steps, {name}, terms={terms}: max|d|={mx:.3e}, {frac:.4%} outside rtol 1e-3 / atol 1e-4")
+    if terms == 2 and name == "pose_full_b4":
         assert frac <= 1e-4 and mx <= 4e-4, (frac, mx)
     else:
         assert not bad.any(), f"terms={terms}: {frac:.4%} outside tolerance, max|d|={mx:.3e}"
@@ -161,12 +164,22 @@ def test_tcgen05_attention_unit(terms, tol, R, T, D, dh, S, nx):
     assert (O.double() - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("persist", [0, 1])
 @pytest.mark.parametrize("terms", [20, 21])   # umma_attention2.cuh: 20 = P planes in shared memory, 21 = in tensor memory
 @pytest.mark.parametrize("R,T,D,S,nx", [(1, 128, 64, 64, 0), (2, 100, 256, 77, 2), (4, 600, 256, 1998, 2), (3, 600, 256, 20, 0),
-                                        (2, 600, 256, 600, 0)])
-def test_tcgen05_attention2_unit(terms, R, T, D, S, nx):
-    """head-parallel attention kernel (dh = 32, two planes): same cases as above incl. ragged tiles / blocks / extra keys"""
-    test_tcgen05_attention_unit(terms, 4e-5, R, T, D, 32, S, nx)
+                                        (2, 600, 256, 600, 0), (16, 600, 256, 1998, 2), (40, 100, 256, 77, 2), (17, 600, 256, 600, 0)])
+def test_tcgen05_attention2_unit(terms, R, T, D, S, nx, persist):
+    """head-parallel attention kernel (dh = 32, two planes): same cases as above incl. ragged tiles / blocks / extra keys, plus
+    launches with more work items than SMs (320 / 160 / 340 tiles) for the persistent-CTA schedule (persist = 1: one CTA per SM
+    walks the items with the pipeline indices running on across items; odd block counts per item flip the buffer parity)"""
+    _l, lib = _lib()
+    lib.a2p_test_attn2_set_persist.argtypes = [C.c_int]
+    lib.a2p_test_attn2_set_persist.restype = None
+    lib.a2p_test_attn2_set_persist(persist)
+    try:
+        test_tcgen05_attention_unit(terms, 4e-5, R, T, D, 32, S, nx)
+    finally:
+        lib.a2p_test_attn2_set_persist(-1)
 
 
 @pytest.mark.parametrize("R,T,D,S", [(1, 128, 64, 64), (3, 600, 256, 20), (2, 100, 256, 33), (16, 600, 256, 20)])
