@@ -343,10 +343,14 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 64; ++c) s[c] = c < nvalid ? s[c] : -INFINITY;
       }
-      float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]);
+      // four independent 3-input max chains (8 dependent instructions each instead of 15)
+      float mx0 = fmax3(s[0], s[1], s[2]), mx1 = fmax3(s[3], s[4], s[5]), mx2 = fmax3(s[6], s[7], s[8]), mx3 = fmax3(s[9], s[10], s[11]);
 #pragma unroll
-      for (int c = 6; c < 62; c += 4) { mx0 = fmax3(mx0, s[c], s[c + 1]); mx1 = fmax3(mx1, s[c + 2], s[c + 3]); }
-      const float mx = fmax3(fmaxf(mx0, mx1), s[62], s[63]);
+      for (int c = 12; c < 60; c += 8) {
+        mx0 = fmax3(mx0, s[c], s[c + 1]); mx1 = fmax3(mx1, s[c + 2], s[c + 3]);
+        mx2 = fmax3(mx2, s[c + 4], s[c + 5]); mx3 = fmax3(mx3, s[c + 6], s[c + 7]);
+      }
+      const float mx = fmax3(fmax3(mx0, mx1, mx2), fmax3(mx3, s[60], s[61]), fmaxf(s[62], s[63]));
       const float mnew = fmaxf(m, mx);
       const float alpha = umma::ex2_approx(m - mnew);
       m = mnew;
@@ -497,7 +501,7 @@ inline int attn2_num_sms() {
   return v;
 }
 #ifndef A2P_ATTN_PERSIST_DEFAULT
-#define A2P_ATTN_PERSIST_DEFAULT 0
+#define A2P_ATTN_PERSIST_DEFAULT 1
 #endif
 inline int& attn2_persist_override() { static int v = -1; return v; }     // tests: 0 / 1 forces the mode of the next launches
 inline bool attn2_persistent() {

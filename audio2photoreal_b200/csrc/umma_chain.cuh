@@ -895,13 +895,16 @@ inline int make_tmap_f32_2d(CUtensorMap* tm, const void* base, long long cols, l
 #ifndef A2P_CHAIN_PAIR_DEFAULT
 #define A2P_CHAIN_PAIR_DEFAULT 0
 #endif
-// A2P_CHAIN_PAIR=1: CTA-pair mode (cta_group::2 MMAs, every CTA streams half of each weight tile); 0: one CTA per tile
+// A2P_CHAIN_PAIR: 1 = CTA-pair mode for every chain launch (cta_group::2 MMAs, every CTA streams half of each weight tile),
+// 0 = one CTA per tile, 2 = auto: pairs only for the launches whose GEMM0 streams a long weight matrix (K0 >= 1024: the FFN2
+// chains, the only ones the pair mode speeds up -- profiles/r02_chain_pair_mode.txt)
 inline int& chain_mode_override() { static int v = 0; return v; }   // tests: 1 / 2 forces the mode of the next launches
-inline int chain_cluster_size() {
+inline int chain_cluster_size(int K0) {
   if (chain_mode_override() > 0) return chain_mode_override();
   static int v = -1;
-  if (v < 0) { const char* e = getenv("A2P_CHAIN_PAIR"); v = (e ? atoi(e) != 0 : A2P_CHAIN_PAIR_DEFAULT) ? 2 : 1; }
-  return v;
+  if (v < 0) { const char* e = getenv("A2P_CHAIN_PAIR"); v = e ? atoi(e) : A2P_CHAIN_PAIR_DEFAULT; }
+  if (v == 2) return K0 >= 1024 ? 2 : 1;
+  return v == 1 ? 2 : 1;
 }
 
 struct ChainOperands {
@@ -920,7 +923,7 @@ inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaS
   if (p.rope && (!o.rope_ext || o.rope_ext_rows < p.T + 128)) A2P_FAIL("chain: RoPE needs the extended table (T + 128 rows)");
   CUtensorMap tA0, tW0, tW1, tW2, tX, tTab;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
-  const int cl = force_cl > 0 ? force_cl : chain_cluster_size();
+  const int cl = force_cl > 0 ? force_cl : chain_cluster_size(p.K0);
   // pair mode: a CTA loads its 128 of the 256 W0 rows (one plane per box) and, for a 128-column accumulator half of GEMM1 / the
   // V job, both planes of its 64 rows in ONE box [64 k][64 rows][2 planes] = one 16 KB slot
   const int w1rows = cl == 2 ? 64 : 128, w1planes = cl == 2 ? 2 : 1;
