@@ -59,5 +59,20 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_trace() -> str:
+    """liba2p_b200_trace.so: the testing library with the clock64 timeline of umma_attn2_kernel compiled in (diagnostics only:
+    scripts/gpu_attn_trace.py); not part of build() and never loaded by the product or the tests."""
+    out = os.path.join(PKG, "liba2p_b200_trace.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + ["-DA2P_ATTN2_TRACE=1", os.path.join(HERE, "testing.cu"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
+    if "--trace" in sys.argv:
+        print(build_trace())
+        sys.exit(0)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -72,7 +72,7 @@ int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_d
 size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_extra) {
   const size_t Sp = align_up((size_t)S, 8), Xp = 8;
   return (align_up((size_t)3 * R * T * D, 512) + align_up((size_t)3 * R * S * D, 512) + align_up((size_t)3 * D * R * Sp, 512) +
-          align_up((size_t)3 * R * 8 * D, 512) + align_up((size_t)3 * D * R * Xp, 512)) * 2 + 8192 + 64 * 16 * 8 +
+          align_up((size_t)3 * R * 8 * D, 512) + align_up((size_t)3 * D * R * Xp, 512)) * 2 + 8192 + 64 * 32 * 8 +
          attn2_split_scratch_floats() * 4 + attn2_split_counter_ints() * 4 + 1024;
 }
 
@@ -119,7 +119,7 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   p.skew_ns = getenv("A2P_ATTN_SKEW_NS") ? atoi(getenv("A2P_ATTN_SKEW_NS")) : 0;
   p.trace = (iters < 0) ? reinterpret_cast<long long*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) : nullptr;   // iters < 0: trace mode
   {  // split-KV scratch behind the trace area (the whole scratch buffer was zeroed above, counters included)
-    char* tail = reinterpret_cast<char*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) + 64 * 16 * 8;
+    char* tail = reinterpret_cast<char*>(Vxt + align_up((size_t)3 * D * R * Xp, 512)) + 64 * 32 * 8;
     tail += 512 - (reinterpret_cast<uintptr_t>(tail) & 255);
     p.split_scratch = reinterpret_cast<float*>(tail);
     p.split_counters = reinterpret_cast<int*>(tail + attn2_split_scratch_floats() * 4);
@@ -131,7 +131,7 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
   A2P_TRY(launch());
   if (iters < 0) {
     A2P_CUDA(cudaStreamSynchronize(st));
-    A2P_CUDA(cudaMemcpy(O, p.trace, 64 * 16 * sizeof(long long), cudaMemcpyDeviceToDevice));   // trace returned in the O buffer
+    A2P_CUDA(cudaMemcpy(O, p.trace, 64 * 32 * sizeof(long long), cudaMemcpyDeviceToDevice));   // trace returned in the O buffer
     return 0;
   }
   cudaEvent_t e0, e1;

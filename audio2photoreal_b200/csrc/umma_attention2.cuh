@@ -96,17 +96,39 @@ __device__ __forceinline__ void split_prob_pair2(float a, float b, uint32_t& hi,
   lo = __byte_perm(__float_as_uint(ra) + 0x8000u, __float_as_uint(rb) + 0x8000u, 0x7632);
 }
 
+// LO-plane variants of the split (template parameter LO of the kernel):
+//   1: plane 1 = the residual TRUNCATED to bf16 (no rounding adds: 1 instruction per score less).  The truncation loses on average
+//      2^-17 of every probability, one-sided; the row sum uses the unsplit probabilities, so the output is scaled by (1 + 2^-17)
+//      at normalisation to stay unbiased in expectation.
+//   2: plane 1 = cvt.rn.bf16x2.f32 of the residual pair (exact round-to-nearest in ONE instruction per pair, on the XU pipe)
+__device__ __forceinline__ void split_prob_pair_trunc(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  float ra, rb;
+  fadd2(ra, rb, a, b, __uint_as_float((ua & 0xFFFF0000u) | 0x80000000u), __uint_as_float((ub & 0xFFFF0000u) | 0x80000000u));
+  lo = __byte_perm(__float_as_uint(ra), __float_as_uint(rb), 0x7632);
+}
+__device__ __forceinline__ void split_prob_pair_cvt(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const uint32_t ua = __float_as_uint(a), ub = __float_as_uint(b);
+  hi = __byte_perm(ua, ub, 0x7632);
+  float ra, rb;
+  fadd2(ra, rb, a, b, __uint_as_float((ua & 0xFFFF0000u) | 0x80000000u), __uint_as_float((ub & 0xFFFF0000u) | 0x80000000u));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));     // upper half <- rb, lower half <- ra
+}
+
 #ifndef A2P_ATTN2_TRACE
 #define A2P_ATTN2_TRACE 0   // 1: clock64 timeline of CTA (0,0,0) into TcAttnParams::trace (scripts/gpu_attn_trace.py 21)
 #endif
 #if A2P_ATTN2_TRACE
-#define A2_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && (cond) && i < 64) p.trace[i * 16 + (slot)] = clock64(); } while (0)
+#define A2_TRACE(slot, cond) do { if (p.trace && blockIdx.x == 0 && (cond) && i < 64) p.trace[i * 32 + (slot)] = clock64(); } while (0)
+#define A2_TRACE_SM(slot) do { A2_TRACE(slot, threadIdx.x == 128); A2_TRACE(16 + (slot), threadIdx.x == 256); } while (0)
 #else
 #define A2_TRACE(slot, cond) do { } while (0)
+#define A2_TRACE_SM(slot) do { } while (0)
 #endif
 
 // POLY of every 4 exponentials are evaluated with the FMA-pipe polynomial (umma::ex2_poly) instead of MUFU.EX2
-template <int PT, int POLY>
+template <int PT, int POLY, int LO = 0>
 __global__ void __launch_bounds__(384, 1)
 umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                   const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV0,
@@ -325,10 +347,10 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       constexpr bool MASKED = decltype(masked_tag)::value;
       const int gi = base + i;           // S / P / PV buffers and barrier parities follow the global block index
       const int b = gi & 1;
-      A2_TRACE(0, threadIdx.x == 128);
+      A2_TRACE_SM(0);
       umma::mbar_wait(&s_full[w * 2 + b], (gi >> 1) & 1);
       umma::fence_after();
-      A2_TRACE(1, threadIdx.x == 128);
+      A2_TRACE_SM(1);
       float s[64];
       umma::tmem_ld32(tmS + b * 64, s);
       umma::tmem_ld32(tmS + b * 64 + 32, s + 32);
@@ -336,7 +358,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       // FMAs fill the issue slots between the exponentials below instead of trailing the iteration
       if (i > 0) consume_pv(gi - 1, alpha_pend);
       else umma::tmem_ld_wait();
-      A2_TRACE(2, threadIdx.x == 128);
+      A2_TRACE_SM(2);
       if (MASKED) {
         const int gb = kb0 + i;
         const int nvalid = (gb < nb_main) ? ::min(64, p.n_keys - gb * 64) : p.n_extra;   // warp-uniform
@@ -355,7 +377,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const float alpha = umma::ex2_approx(m - mnew);
       m = mnew;
       const float nm = -mnew;
-      A2_TRACE(3, threadIdx.x == 128);
+      A2_TRACE_SM(3);
       if (!PT && gi > 0) umma::mbar_wait(&p_free[w], (gi - 1) & 1);   // PV(gi-1) has finished reading the shared-memory planes
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
@@ -382,7 +404,9 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             pb[f] = ((2 * f + 1) & 3) < POLY ? umma::ex2_poly(x1) : umma::ex2_approx(x1);
           }
           fadd2(rs0, rs1, rs0, rs1, pa[e], pb[e]);
-          split_prob_pair2(pa[e], pb[e], hi[e], lo[e]);
+          if (LO == 1) split_prob_pair_trunc(pa[e], pb[e], hi[e], lo[e]);
+          else if (LO == 2) split_prob_pair_cvt(pa[e], pb[e], hi[e], lo[e]);
+          else split_prob_pair2(pa[e], pb[e], hi[e], lo[e]);
         }
         if (PT) {
           tmem_st16(tmS + b * 64 + hf * 16, hi);
@@ -395,13 +419,13 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
           }
         }
       }
-      A2_TRACE(4, threadIdx.x == 128);
+      A2_TRACE_SM(4);
       if (PT) { tmem_st_wait2(); umma::fence_before(); }
       else umma::fence_proxy_async();
       umma::mbar_arrive(&p_ready[w * 2 + b]);
-      A2_TRACE(5, threadIdx.x == 128);
+      A2_TRACE_SM(5);
       l = l * alpha + (rs0 + rs1);
-      A2_TRACE(6, threadIdx.x == 128);
+      A2_TRACE_SM(6);
       alpha_pend = alpha;
     };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -460,7 +484,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int row = q0 + trow;
     if (writer && row < p.T) {
       const long long grow = (long long)r * p.T + row;
-      const float inv = 1.f / l;
+      const float inv = (LO == 1 ? 1.00000762939453125f : 1.f) / l;      // LO = 1: (1 + 2^-17), see split_prob_pair_trunc
 #pragma unroll
       for (int c = 0; c < 32; ++c) o[c] *= inv;
       const int col = g * 64 + w * 32;
@@ -519,7 +543,7 @@ inline bool attn2_split_disabled() {
 inline size_t attn2_split_scratch_floats() { return (size_t)attn2_num_sms() * 2 * 34 * 128; }
 inline size_t attn2_split_counter_ints() { return (size_t)attn2_num_sms(); }
 
-template <int PT, int POLY>
+template <int PT, int POLY, int LO = 0>
 int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
   using Cfg = Attn2Cfg<PT>;
   CUtensorMap tq, tk[2], tv[2], tkx, tvx;
@@ -552,7 +576,7 @@ int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStre
   const int n_items = q.split_full + (n_tiles - q.split_full) * q.split_parts;
   // persistent CTAs (A2P_ATTN_PERSIST=1): one CTA per SM walks items blockIdx.x, + gridDim.x, ...; default: one CTA per item
   dim3 grid(attn2_persistent() && n_items > sms ? sms : n_items);
-  A2P_CUDA(launch_pdl(umma_attn2_kernel<PT, POLY>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
+  A2P_CUDA(launch_pdl(umma_attn2_kernel<PT, POLY, LO>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
                       tkx, tvx, q));
   return 0;
 }
@@ -566,13 +590,15 @@ inline int launch_umma_attn2(int variant, const TcAttnOperands& o, const TcAttnP
     case 2: return launch_umma_attn2_t<1, 0>(o, p, st);
     case 3: return launch_umma_attn2_t<1, 1>(o, p, st);
     case 4: return launch_umma_attn2_t<1, 2>(o, p, st);
+    case 6: return launch_umma_attn2_t<1, 0, 1>(o, p, st);     // lo plane truncated (+ expectation compensation)
+    case 7: return launch_umma_attn2_t<1, 0, 2>(o, p, st);     // lo plane by cvt.rn.bf16x2.f32
   }
   A2P_FAIL("umma_attn2: unknown variant %d", variant);
 }
 
 inline int init_umma_attn2() {
-#define A2P_SET(PT_, PL_) A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<PT_, PL_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<PT_>::SMEM_BYTES));
-  A2P_SET(0, 0) A2P_SET(1, 0) A2P_SET(1, 1) A2P_SET(1, 2)
+#define A2P_SET(PT_, PL_, LO_) A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<PT_, PL_, LO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<PT_>::SMEM_BYTES));
+  A2P_SET(0, 0, 0) A2P_SET(1, 0, 0) A2P_SET(1, 1, 0) A2P_SET(1, 2, 0) A2P_SET(1, 0, 1) A2P_SET(1, 0, 2)
 #undef A2P_SET
   return 0;
 }

@@ -893,7 +893,7 @@ inline int make_tmap_f32_2d(CUtensorMap* tm, const void* base, long long cols, l
 }
 
 #ifndef A2P_CHAIN_PAIR_DEFAULT
-#define A2P_CHAIN_PAIR_DEFAULT 0
+#define A2P_CHAIN_PAIR_DEFAULT 2
 #endif
 // A2P_CHAIN_PAIR: 1 = CTA-pair mode for every chain launch (cta_group::2 MMAs, every CTA streams half of each weight tile),
 // 0 = one CTA per tile, 2 = auto: pairs only for the launches whose GEMM0 streams a long weight matrix (K0 >= 1024: the FFN2
