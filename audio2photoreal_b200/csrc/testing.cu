@@ -69,6 +69,10 @@ int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_d
   return launch_mma_rate(N, a_from_tmem, n_mma, cycles_out_dev, (cudaStream_t)stream);
 }
 
+int a2p_test_tmem_ldst_rate(int store, int n_ops, int n_warps, long long* cycles_out_dev, void* stream) {
+  return launch_tmem_ldst_rate(store, n_ops, n_warps, cycles_out_dev, (cudaStream_t)stream);
+}
+
 size_t a2p_test_tc_attention_scratch_bytes(int R, int T, int D, int S, int n_extra) {
   const size_t Sp = align_up((size_t)S, 8), Xp = 8;
   return (align_up((size_t)3 * R * T * D, 512) + align_up((size_t)3 * R * S * D, 512) + align_up((size_t)3 * D * R * Sp, 512) +

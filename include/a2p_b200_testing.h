@@ -54,6 +54,10 @@ void a2p_test_philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_
  * from shared memory (0) or tensor memory (1); result written to the DEVICE pointer cycles_out_dev[0]. */
 int a2p_test_mma_rate(int N, int a_from_tmem, int n_mma, long long* cycles_out_dev, void* stream);
 
+/* micro-benchmark: cycles for n_warps warps (1..8; warps 0-3 cover the four TMEM quarters, 4-7 share them) to each issue n_ops
+ * tcgen05.ld (store = 0) or tcgen05.st (store = 1) of 32 lanes x 32 columns (4 KB per instruction); cycles_out_dev[0]. */
+int a2p_test_tmem_ldst_rate(int store, int n_ops, int n_warps, long long* cycles_out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
