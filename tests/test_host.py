@@ -58,7 +58,9 @@ def test_checkpoint_contract_pose_face():
     assert len(denoiser_param_spec(d)) == 241   # = reference state_dict minus frozen audio_model.* (make_golden.py asserts set equality)
     for fmt in ("pose", "face"):
         model, _ = create_model_and_diffusion(_args(fmt), "test")
-        keys = set(model.state_dict().keys())
+        # the frozen side models (present only when fairseq / the reference checkout are importable: the constructor then
+        # loads them like the reference's does) are outside the contract checked here
+        keys = {k for k in model.state_dict().keys() if not k.startswith(("audio_model.", "lip_model.", "transformer.", "tokenizer."))}
         assert keys == {n for n, _, _ in denoiser_param_spec(model.dims)}
         sd = synthetic_state_dict(model.dims, seed=3)
         sd["audio_model.feature_extractor.conv_layers.0.0.weight"] = torch.zeros(512, 1, 10)   # frozen fairseq entry
