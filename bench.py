@@ -163,6 +163,11 @@ class ReferenceLoop:
     the per-call `encode_audio` the reference pays twice per step (model/diffusion.py:355-358)."""
 
     def __init__(self, device: str, batch: int, fmt: str = "pose"):
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):      # the reference prints while it builds; stdout carries ONE JSON line
+            self._init(device, batch, fmt)
+
+    def _init(self, device: str, batch: int, fmt: str):
         from oracle import ref_harness as RH
         from audio2photoreal_b200.weights import model_dims, synthetic_state_dict
         w = WORKLOAD if fmt == "pose" else FACE_WORKLOAD
@@ -203,7 +208,7 @@ class ReferenceLoop:
         if self.dev.type == "cuda":
             torch.cuda.synchronize()
         t0 = time.perf_counter()
-        with torch.no_grad(), shim:
+        with torch.no_grad(), shim, contextlib.redirect_stdout(sys.stderr):
             out = self.diffusion.ddim_sample_loop(self.model, (self.B, self.w["C"], 1, self.w["T"]), noise=self.noise,
                                                   clip_denoised=False, model_kwargs={"y": dict(self.y)},
                                                   skip_timesteps=self.n - k, init_image=None, progress=False)
