@@ -307,6 +307,148 @@ def run_reference_arm(a):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------- BASELINE configs[4]: the full pipeline of one subject per GPU
+PIPE_METRIC = "motion-frames/sec full pipeline (guide keyframes + body 1000 steps + face ddim500, T=600)"
+PIPE_SAMPLES = 16          # samples per subject (configs[4]: 4 subjects x 16 samples)
+
+
+def _synthetic_guide(dev, tokens=1024, dim=512, layers=4, depth=4, latent=64):
+    """GuideSampler + VQDecoder with random weights under the reference's checkpoint key names (model/guide.py, model/vqvae.py) and
+    a random-init frozen extractor of the published vq-wav2vec conv geometry (there are no checkpoints offline)."""
+    import torch.nn as nn
+    from audio2photoreal_b200.guide import GuideSampler, VQDecoder
+    g = torch.Generator().manual_seed(5)
+    rn = lambda *sh, sc=1.0: torch.randn(*sh, generator=g) * sc
+
+    class Extractor(nn.Module):
+        def __init__(self):
+            super().__init__()
+            geo, cin, mods = [(512, 10, 5), (512, 8, 4), (512, 4, 2), (512, 4, 2), (512, 4, 2), (512, 1, 1), (512, 1, 1), (512, 1, 1)], 1, []
+            for d_, k, st in geo:
+                mods.append(nn.Sequential(nn.Conv1d(cin, d_, k, stride=st, bias=False), nn.GroupNorm(1, d_), nn.ReLU()))
+                cin = d_
+            self.conv_layers = nn.ModuleList(mods)
+
+        def feature_extractor(self, x):
+            x = x.unsqueeze(1)
+            for c in self.conv_layers:
+                x = c(x)
+            return torch.log(torch.abs(x) + 1)
+    sd = {"token_embedding.weight": rn(tokens + 1, dim), "rotary.freqs": 1.0 / (10000 ** (torch.arange(0, dim, 2).float() / dim)),
+          "audio_resampler.kernel": rn(1, 1, 41, sc=1 / 41), "null_cond_embed": rn(1, 798, dim), "null_cond_hidden": rn(1, dim),
+          "norm_cond.weight": torch.ones(dim), "norm_cond.bias": torch.zeros(dim),
+          "cond_projection.weight": rn(dim, 1024, sc=1024 ** -0.5), "cond_projection.bias": torch.zeros(dim),
+          "non_attn_cond_projection.0.weight": torch.ones(dim), "non_attn_cond_projection.0.bias": torch.zeros(dim),
+          "non_attn_cond_projection.1.weight": rn(dim, dim, sc=dim ** -0.5), "non_attn_cond_projection.1.bias": torch.zeros(dim),
+          "non_attn_cond_projection.3.weight": rn(dim, dim, sc=dim ** -0.5), "non_attn_cond_projection.3.bias": torch.zeros(dim),
+          "final_layer.weight": rn(tokens, dim, sc=dim ** -0.5), "final_layer.bias": torch.zeros(tokens)}
+    idx = 0
+    for _ in range(2):                      # num_audio_layers = 2 blocks of six dilated convs (model/guide.py:84-119)
+        for _ in range(6):
+            sd[f"pre_audio.{idx}.weight"], sd[f"pre_audio.{idx}.bias"] = rn(1024, 1024, 3, sc=(3 * 1024) ** -0.5), torch.zeros(1024)
+            idx += 3
+    sd[f"pre_audio.{idx}.weight"], sd[f"pre_audio.{idx}.bias"] = rn(1024, 1024, 1, sc=1024 ** -0.5), torch.zeros(1024)
+    for n in range(layers):
+        p_ = f"seqTransDecoder.stack.{n}."
+        for a_ in ("self_attn", "multihead_attn"):
+            sd[p_ + a_ + ".in_proj_weight"], sd[p_ + a_ + ".in_proj_bias"] = rn(3 * dim, dim, sc=dim ** -0.5), torch.zeros(3 * dim)
+            sd[p_ + a_ + ".out_proj.weight"], sd[p_ + a_ + ".out_proj.bias"] = rn(dim, dim, sc=dim ** -0.5), torch.zeros(dim)
+        sd[p_ + "linear1.weight"], sd[p_ + "linear1.bias"] = rn(1024, dim, sc=dim ** -0.5), torch.zeros(1024)
+        sd[p_ + "linear2.weight"], sd[p_ + "linear2.bias"] = rn(dim, 1024, sc=1024 ** -0.5), torch.zeros(dim)
+        for k in ("norm1", "norm2", "norm3"):
+            sd[p_ + k + ".weight"], sd[p_ + k + ".bias"] = torch.ones(dim), torch.zeros(dim)
+        for k in ("film1", "film2", "film3"):
+            sd[p_ + k + ".block.1.weight"], sd[p_ + k + ".block.1.bias"] = rn(2 * dim, dim, sc=dim ** -0.5), torch.zeros(2 * dim)
+        sd[p_ + "rotary.freqs"] = sd["rotary.freqs"].clone()
+    guide = GuideSampler(sd, tokens=tokens, audio_model=Extractor()).to(dev).eval()
+    vq = {f"quantizer.layers.{i}._codebook.embed": rn(tokens, latent) for i in range(depth)}
+    for i in (0, 2, 4, 6):
+        vq[f"decoder.dec.{i}.weight"], vq[f"decoder.dec.{i}.bias"] = rn(latent, latent, 2, sc=(2 * latent) ** -0.5), torch.zeros(latent)
+    vq["decoder.dec.8.weight"], vq["decoder.dec.8.bias"] = rn(104, latent, 1, sc=latent ** -0.5), torch.zeros(104)
+    return guide, VQDecoder(vq, 104, latent, tokens, depth).to(dev).eval()
+
+
+def run_pipeline(a):
+    """One subject per GPU (4 subjects on 4 GPUs; 8 GPUs = the 4 subjects' face and body jobs would be the alternative cut):
+    guide keyframes (KV-cached AR sampler + VQ decode, sample/generate.py:51-71) -> body diffusion (1000 steps, g = 2) with those
+    keyframes -> face diffusion (ddim500, g = 10), 16 samples per subject, T = 600; value = N x 16 x 600 frames / time."""
+    import torch.distributed as dist
+    from audio2photoreal_b200.api import CFGDenoiser, create_model_and_diffusion, load_model
+    from audio2photoreal_b200.dist import all_gather_rows
+    from audio2photoreal_b200.weights import synthetic_state_dict
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = PIPE_SAMPLES, 600
+    guide, vq = _synthetic_guide(dev)
+    models = {}
+    for fmt, resp, g_ in (("pose", "", 2.0), ("face", "ddim500", 10.0)):
+        m = model_args(resp)
+        m.split_terms = 2 if fmt == "pose" else 3
+        if fmt == "face":
+            m.data_format, m.add_frame_cond = "face", None
+            m.layers = FACE_WORKLOAD["layers"]
+        model, sampler = create_model_and_diffusion(m, "test")
+        load_model(model, synthetic_state_dict(model.dims, seed=1))
+        model = model.to(dev).eval()
+        models[fmt] = (model, CFGDenoiser(model), sampler, g_)
+    gen = torch.Generator().manual_seed(20 + rank)
+    audio = (0.1 * torch.randn(B, T * 1600, 2, generator=gen)).pin_memory()
+    feats = {"pose": torch.randn(B, 1998, 1024, generator=gen).pin_memory(), "face": torch.randn(B, 1998, 2038, generator=gen).pin_memory()}
+    noise = {"pose": torch.randn(B, 104, 1, T, generator=gen).pin_memory(), "face": torch.randn(B, 256, 1, T, generator=gen).pin_memory()}
+
+    def once():
+        a_dev = audio.to(dev, non_blocking=True)
+        toks = guide.generate(a_dev, T // 30, layers=vq.residual_depth, n_sequences=B)            # sample/generate.py:60-66
+        keyframes = vq.decode(toks.reshape(B, -1, vq.residual_depth))                              # :67-70 -> [B, 20, 104]
+        out = {}
+        for fmt in ("pose", "face"):
+            model, cfg, sampler, g_ = models[fmt]
+            y = {"audio_embed": feats[fmt].to(dev, non_blocking=True), "keyframes": keyframes.clone(), "mask": torch.ones(B, 1, 1, T, dtype=torch.bool),
+                 "scale": torch.full((B,), g_, device=dev)}
+            model._cond_sig = None
+            out[fmt] = sampler.ddim_sample_loop(cfg, (B, model.nfeats, 1, T), noise=noise[fmt].to(dev, non_blocking=True), clip_denoised=False,
+                                                model_kwargs={"y": y}, advance_rng=False)
+        res = torch.cat([out["pose"], out["face"]], dim=1)                                       # [B, 104 + 256, 1, T]
+        return all_gather_rows(res, B * world).cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(1, min(a.warmup, 2))):
+        once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        res = once()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    barrier()
+    assert torch.isfinite(res).all() and res.shape[0] == B * world
+    if rank == 0:
+        ms = dt.item() * 1e3 / a.steps
+        v = world * B * T / (ms / 1e3)
+        line = {"metric": PIPE_METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2 (pose) / bf16x3 (face) split, fp32 accumulate",
+                "data": "synthetic",
+                "config": {"workload": f"full pipeline per subject and GPU: guide AR sampler (80 tokens, KV cache) + VQ decode -> body diffusion 1000 steps g=2 -> "
+                                       f"face diffusion ddim500 g=10; {B} samples x T=600 per subject, {world} subject(s) (BASELINE configs[4]); random-init weights, "
+                                       f"raw audio for the guide, synthetic wav2vec(+lip) features for the denoisers",
+                           "global_batch": B * world, "parallelism": f"one subject per GPU x{world}, 1 all-gather"},
+                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": int(audio.numel() * 4 + sum(t.numel() * 4 for t in feats.values()) + sum(t.numel() * 4 for t in noise.values())),
+                        "d2h_bytes_per_step": int(res.numel() * 4 // world)},
+                "gpu_launches": int(sum(m[0].launch_count() for m in models.values())), "roofline": None, "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     global SPLIT_TERMS, WORKLOAD, METRIC
     ap = argparse.ArgumentParser()
@@ -322,8 +464,9 @@ def main():
                          "not the benchmark line")
     ap.add_argument("--dump-out", default=None, help="debug only: save the result of the last timed loop as .npy")
     ap.add_argument("--split-terms", type=int, default=None, help="0: exact-fp32 FFMA arm; 2 (pose default, fused chain kernels) | 3 (face default): split-bf16 tcgen05 arms")
-    ap.add_argument("--workload", default="pose", choices=["pose", "face"],
-                    help="pose = BASELINE configs[1] (the contract line); face = configs[3] (ddim500, g=10, 16 rows/GPU), secondary")
+    ap.add_argument("--workload", default="pose", choices=["pose", "face", "pipeline"],
+                    help="pose = BASELINE configs[1] (the contract line); face = configs[3] (ddim500, g=10, 16 rows/GPU); pipeline = configs[4] "
+                         "(guide + body + face per subject and GPU); the last two are secondary")
     ap.add_argument("--no-config3", action="store_true", help="skip the extra global-batch-32 (configs[2], strong-scaling) measurement")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the reference-on-this-GPU leg")
     a = ap.parse_args()
@@ -331,6 +474,8 @@ def main():
     SPLIT_TERMS = a.split_terms if a.split_terms is not None else (3 if face else 2)
     if a.impl == "reference":
         return run_reference_arm(a)
+    if a.workload == "pipeline":
+        return run_pipeline(a)
     if face:
         if a.batch == WORKLOAD["B"]:
             a.batch = FACE_WORKLOAD["B"]
