@@ -62,6 +62,13 @@ if __name__ == "__main__":
         for terms in (21, 22, 23):     # 22 / 23: 1 / 2 of every 4 exponentials on the FMA pipe
             run(terms, 16, 600, 256, 32, 1998, 2)
             run(terms, 16, 600, 256, 32, 600, 0)
+    if which == "sk":              # round-2 experiment (patch in profiles/experiments/): two softmax warpgroups per head (terms 27) vs one
+        lib.a2p_test_attn2_set_persist.argtypes = [C.c_int]
+        lib.a2p_test_attn2_set_persist(1)
+        for terms in (21, 27, 21, 27):
+            for R, S, nx in ((4, 1998, 2), (4, 600, 0), (8, 1998, 2), (32, 1998, 2), (32, 600, 0)):
+                run(terms, R, 600, 256, 32, S, nx)
+        run(27, 16, 600, 256, 32, 1998, 2, qscale=4.0)
     if which == "lo":              # lo-plane variants of the probability split: 21 rounding adds (default), 25 truncation, 26 cvt.rn.bf16x2
         for terms in (21, 25, 26, 21, 25, 26):
             for R, S, nx in ((4, 1998, 2), (4, 600, 0), (32, 1998, 2), (32, 600, 0)):
