@@ -351,8 +351,8 @@ const float* find(const std::map<std::string, std::pair<const float*, int64_t>>&
 
 // A2P_NO_CHAIN=1 keeps the unfused GEMM / LayerNorm kernels (A/B measurements and the P = 3 / face arms use them anyway)
 // A2P_ATTN2: 0 = first-generation attention kernel, 1 = head-parallel kernel with P planes in shared memory,
-// 2 (default) = head-parallel kernel with P planes in tensor memory (umma_attention2.cuh; head dim 32, two planes),
-// 3 / 4 = as 2 with 1 / 2 of every 4 exponentials on the FMA pipe
+// 2 (default) = head-parallel kernel with P and Q planes in tensor memory (umma_attention2.cuh; head dim 32, two planes),
+// 8 = as 2 with the Q planes in shared memory, 3 / 4 = as 8 with 1 / 2 of every 4 exponentials on the FMA pipe
 int attn2_variant() {
   static int v = -1;
   if (v < 0) v = getenv("A2P_ATTN2") ? atoi(getenv("A2P_ATTN2")) : 2;

@@ -128,7 +128,7 @@ __device__ __forceinline__ void split_prob_pair_cvt(float a, float b, uint32_t& 
 #endif
 
 // POLY of every 4 exponentials are evaluated with the FMA-pipe polynomial (umma::ex2_poly) instead of MUFU.EX2
-template <int PT, int POLY, int LO = 0>
+template <int PT, int POLY, int LO = 0, int QT = 0>
 __global__ void __launch_bounds__(384, 1)
 umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK0,
                   const __grid_constant__ CUtensorMap tmK1, const __grid_constant__ CUtensorMap tmV0,
@@ -187,7 +187,9 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     if (p.R > p.rows_per_branch) { umma::prefetch_tmap(&tmK1); umma::prefetch_tmap(&tmV1); }
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < 2; ++i) { umma::mbar_init(qf(i), 1); umma::mbar_init(&q_empty[i], 1); }
+    // QT = 1: the softmax warps copy the Q planes into tensor memory (A operand of S from TMEM); they release the Q buffer
+    for (int i = 0; i < 2; ++i) { umma::mbar_init(qf(i), 1); umma::mbar_init(&q_empty[i], QT ? 256 : 1); }
+    umma::mbar_init(bars + 30, 256);   // q_tm: the item's Q planes are in tensor memory (QT)
     for (int i = 0; i < NST; ++i) { umma::mbar_init(&kv_full[i], 1); umma::mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 4; ++i) { umma::mbar_init(&s_full[i], 1); umma::mbar_init(&p_ready[i], 128); umma::mbar_init(&pv_full[i], 1); }
     for (int i = 0; i < 2; ++i) umma::mbar_init(&p_free[i], 1);
@@ -256,7 +258,8 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       const int n_blocks = decode(item).n_blocks;
       const int qb = itn & 1;
       const uint32_t loQ = umma::desc_lo(umma::smem_u32(sQ + qb * Cfg::Q_BYTES));
-      umma::mbar_wait(qf(qb), (itn >> 1) & 1);
+      if (QT) { umma::mbar_wait(bars + 30, itn & 1); umma::fence_after(); }
+      else umma::mbar_wait(qf(qb), (itn >> 1) & 1);
       for (int i = 0; i <= n_blocks; ++i) {
         const int gi = base + i;          // buffers / parities follow the global block index
         A2_TRACE(8, lane == 0);
@@ -274,11 +277,13 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
               for (int pr = 0; pr < 3; ++pr)
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
-                  umma::mma_bf16(d, umma::desc_make(loq + prod_a(pr) * (16384 >> 4) + 2 * k),
-                                 umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
+                  if (QT) mma_bf16_ts(d, tmem_base + 384 + w * 32 + prod_a(pr) * 16 + 8 * k,
+                                      umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
+                  else umma::mma_bf16(d, umma::desc_make(loq + prod_a(pr) * (16384 >> 4) + 2 * k),
+                                      umma::desc_make(lok + prod_b(pr) * (8192 >> 4) + 2 * k), idS, (pr | k) != 0 ? 1u : 0u);
               umma::mma_commit(&s_full[w * 2 + (gi & 1)]);
             }
-            if (i == n_blocks - 1) umma::mma_commit(&q_empty[qb]);      // last read of this item's Q tile
+            if (!QT && i == n_blocks - 1) umma::mma_commit(&q_empty[qb]);      // last read of this item's Q tile
           }
           __syncwarp();
         }
@@ -428,10 +433,34 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       A2_TRACE_SM(6);
       alpha_pend = alpha;
     };
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+    int itn = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++itn) {
     const Item it = decode(item);
     const int n_blocks = it.n_blocks, tile = it.tile, part = it.part, nparts = it.nparts, q0 = it.q0, g = it.g, r = it.r;
     kb0 = it.kb0;
+    if (QT) {
+      // Q planes of head w, row trow: shared memory (SWIZZLE_128B rows of 128 B: 2 heads x 32 dims) -> tensor memory columns
+      // [384 + 32 w + 16 plane, +16) in the A-operand layout (8 columns per 16 dims), so that S = Q K^T reads A from TMEM like PV
+      // does: no 4 KB shared-memory fetch of Q per MMA (48 KB per block).  The previous item's S products are complete: this
+      // warpgroup has consumed the last S tile of that item.
+      const int qb = itn & 1;
+      umma::mbar_wait(qf(qb), (itn >> 1) & 1);
+      const uint32_t qrow = umma::smem_u32(sQ + qb * Cfg::Q_BYTES) + trow * 128;
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        uint32_t qv[16];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t a_ = qrow + pl * 16384 + (((w * 4 + u) ^ (trow & 7)) << 4);
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(qv[4 * u]), "=r"(qv[4 * u + 1]), "=r"(qv[4 * u + 2]), "=r"(qv[4 * u + 3]) : "r"(a_));
+        }
+        tmem_st16(tmem_base + lane_addr + 384 + w * 32 + pl * 16, qv);
+      }
+      tmem_st_wait2();
+      umma::fence_before();
+      umma::mbar_arrive(bars + 30);            // q_tm
+      umma::mbar_arrive(&q_empty[qb]);         // the shared-memory Q buffer may be refilled
+    }
     m = -INFINITY; l = 0.f; alpha_pend = 1.f;
 #pragma unroll
     for (int c = 0; c < 32; ++c) o[c] = 0.f;
@@ -543,7 +572,7 @@ inline bool attn2_split_disabled() {
 inline size_t attn2_split_scratch_floats() { return (size_t)attn2_num_sms() * 2 * 34 * 128; }
 inline size_t attn2_split_counter_ints() { return (size_t)attn2_num_sms(); }
 
-template <int PT, int POLY, int LO = 0>
+template <int PT, int POLY, int LO = 0, int QT = 0>
 int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
   using Cfg = Attn2Cfg<PT>;
   CUtensorMap tq, tk[2], tv[2], tkx, tvx;
@@ -576,22 +605,23 @@ int launch_umma_attn2_t(const TcAttnOperands& o, const TcAttnParams& p, cudaStre
   const int n_items = q.split_full + (n_tiles - q.split_full) * q.split_parts;
   // persistent CTAs (A2P_ATTN_PERSIST=1): one CTA per SM walks items blockIdx.x, + gridDim.x, ...; default: one CTA per item
   dim3 grid(attn2_persistent() && n_items > sms ? sms : n_items);
-  A2P_CUDA(launch_pdl(umma_attn2_kernel<PT, POLY, LO>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
+  A2P_CUDA(launch_pdl(umma_attn2_kernel<PT, POLY, LO, QT>, grid, dim3(Cfg::THREADS), (size_t)Cfg::SMEM_BYTES, st, tq, tk[0], tk[1], tv[0], tv[1],
                       tkx, tvx, q));
   return 0;
 }
 
-// variant: 1 = P planes in shared memory; 2 = P planes in tensor memory; 3 / 4 = as 2 with 1 / 2 of every 4 exponentials
-// on the FMA pipe
+// variant: 1 = P planes in shared memory; 2 (default) = P planes and Q planes in tensor memory; 8 = as 2 with Q in shared memory;
+// 3 / 4 = as 8 with 1 / 2 of every 4 exponentials on the FMA pipe; 6 / 7 = as 8 with the lo-plane split variants
 inline int launch_umma_attn2(int variant, const TcAttnOperands& o, const TcAttnParams& p, cudaStream_t st) {
   if (p.dh != 32) A2P_FAIL("umma_attn2: head dim must be 32");
   switch (variant) {
     case 1: return launch_umma_attn2_t<0, 0>(o, p, st);
-    case 2: return launch_umma_attn2_t<1, 0>(o, p, st);
+    case 2: return launch_umma_attn2_t<1, 0, 0, 1>(o, p, st);  // default: P planes AND Q planes in tensor memory
     case 3: return launch_umma_attn2_t<1, 1>(o, p, st);
     case 4: return launch_umma_attn2_t<1, 2>(o, p, st);
     case 6: return launch_umma_attn2_t<1, 0, 1>(o, p, st);     // lo plane truncated (+ expectation compensation)
     case 7: return launch_umma_attn2_t<1, 0, 2>(o, p, st);     // lo plane by cvt.rn.bf16x2.f32
+    case 8: return launch_umma_attn2_t<1, 0, 0, 0>(o, p, st);  // as 2 with the Q planes read from shared memory by every S product (A/B)
   }
   A2P_FAIL("umma_attn2: unknown variant %d", variant);
 }
@@ -600,6 +630,7 @@ inline int init_umma_attn2() {
 #define A2P_SET(PT_, PL_, LO_) A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<PT_, PL_, LO_>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<PT_>::SMEM_BYTES));
   A2P_SET(0, 0, 0) A2P_SET(1, 0, 0) A2P_SET(1, 1, 0) A2P_SET(1, 2, 0) A2P_SET(1, 0, 1) A2P_SET(1, 0, 2)
 #undef A2P_SET
+  A2P_CUDA(cudaFuncSetAttribute(umma_attn2_kernel<1, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Attn2Cfg<1>::SMEM_BYTES));
   return 0;
 }
 

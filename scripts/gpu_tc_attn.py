@@ -62,7 +62,7 @@ if __name__ == "__main__":
         for terms in (21, 22, 23):     # 22 / 23: 1 / 2 of every 4 exponentials on the FMA pipe
             run(terms, 16, 600, 256, 32, 1998, 2)
             run(terms, 16, 600, 256, 32, 600, 0)
-    if which == "sk":              # round-2 experiment (patch in profiles/experiments/): two softmax warpgroups per head (terms 27) vs one
+    if which == "sk":              # A/B of attention2 variant 8 (terms 27) against the default (terms 21)
         lib.a2p_test_attn2_set_persist.argtypes = [C.c_int]
         lib.a2p_test_attn2_set_persist(1)
         for terms in (21, 27, 21, 27):

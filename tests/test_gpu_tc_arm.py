@@ -165,7 +165,7 @@ def test_tcgen05_attention_unit(terms, tol, R, T, D, dh, S, nx):
 
 
 @pytest.mark.parametrize("persist", [0, 1])
-@pytest.mark.parametrize("terms", [20, 21])   # umma_attention2.cuh: 20 = P planes in shared memory, 21 = in tensor memory
+@pytest.mark.parametrize("terms", [20, 21, 27])   # umma_attention2.cuh: 20 = P planes in shared memory, 21 = P and Q planes in tensor memory (default), 27 = Q planes in shared memory
 @pytest.mark.parametrize("R,T,D,S,nx", [(1, 128, 64, 64, 0), (2, 100, 256, 77, 2), (4, 600, 256, 1998, 2), (3, 600, 256, 20, 0),
                                         (2, 600, 256, 600, 0), (16, 600, 256, 1998, 2), (40, 100, 256, 77, 2), (17, 600, 256, 600, 0)])
 def test_tcgen05_attention2_unit(terms, R, T, D, S, nx, persist):
