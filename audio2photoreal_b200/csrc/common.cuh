@@ -52,16 +52,22 @@ struct BranchPtr {
 };
 
 // ---- programmatic dependent launch (PDL): a kernel launched through launch_pdl() may start while its stream
-// predecessor is still draining; it must call pdl_wait() before touching anything the predecessor wrote and
-// should call pdl_trigger() early so that ITS successor can be scheduled.  Only kernels containing pdl_wait()
-// may be launched with the attribute.  Opt-in with A2P_PDL=1: measured neutral on the B=8 loop (1109 vs 1114 frames/s,
-// profiles/r01g), so the default stays plain stream serialisation.
+// predecessor is still draining; it must call pdl_wait() before touching anything the predecessor wrote.  Only kernels
+// containing pdl_wait() may be launched with the attribute.  pdl_trigger() allows the stream successor to be scheduled once
+// every CTA of the grid has issued it (or exited).  Round 1 triggered at kernel entry: the successor's CTAs then sat on SMs
+// (227 KB of shared memory each) spinning in pdl_wait() for the whole duration of this kernel -- neutral on a single
+// forward, 10 % slower with concurrent forwards (profiles/r01t).  The trigger now sits where a CTA's producer warp has
+// requested its last inbound tile, i.e. a few microseconds before the CTA ends: only the successor's prologue (barrier
+// init, tensor-memory allocation, descriptor prefetch) and the launch latency overlap this kernel's tail.  A2P_PDL=1 / 0.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+#ifndef A2P_PDL_DEFAULT
+#define A2P_PDL_DEFAULT 0
+#endif
 inline bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) v = getenv("A2P_PDL") ? 1 : 0;
+  if (v < 0) { const char* e = getenv("A2P_PDL"); v = e ? (atoi(e) != 0) : A2P_PDL_DEFAULT; }
   return v == 1;
 }
 

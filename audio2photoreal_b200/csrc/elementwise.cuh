@@ -77,7 +77,6 @@ __global__ void __launch_bounds__(256) ln_rope_planes_kernel(const float* __rest
   constexpr int PER = D / 32;
   constexpr int NV = PER / 4;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  pdl_trigger();
   pdl_wait();
   if (warp >= rows) return;
   const float* xr = x + (long long)warp * ldx;

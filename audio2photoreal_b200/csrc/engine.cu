@@ -271,6 +271,7 @@ struct Ctx {
   int cat = CAT_MISC;
   bool skinny = false;   // route the next FFMA GEMMs to the warp-per-column kernel (per-step conditioning linears)
   int slot = 0;          // which set of side streams / events of the handle this forward uses
+  int concurrent = 1;    // how many forwards of this size share the GPU (the units of a sampling step): sizes the chain N split
   cudaEvent_t stagger_ev = nullptr;   // recorded after the stagger_after-th chain / attention launch of the fused arm
   int stagger_after = 0, n_main = 0;
   std::string tag;
@@ -382,6 +383,26 @@ int chain_priority() {   // A2P_CHAIN_PRIO=p: launch priority of the chain kerne
   static int v = 1 << 30;
   if (v == (1 << 30)) { const char* e = getenv("A2P_CHAIN_PRIO"); v = e ? atoi(e) : 0; }
   return v;
+}
+
+// N split of the chain launches (umma_chain.cuh): a launch of `tiles` 128-row tiles whose GEMM1 / V job has n_acc 128-column
+// accumulator halves is cut into s parts per tile when the step's `concurrent` forwards together leave SMs idle:
+// s = the largest divisor of n_acc with tiles * s * concurrent <= budget and n_acc / s >= min halves per part.
+// A2P_CHAIN_NSPLIT=0 off, 1 auto (default), n >= 2 force (capped by n_acc); A2P_CHAIN_SPLIT_BUDGET (default 160 CTAs),
+// A2P_CHAIN_SPLIT_MINH (default 2).
+int chain_nsplit_for(int tiles, int n_acc, int concurrent) {
+  static int mode = -1, budget = 160, minh = 2;
+  if (mode < 0) {
+    const char* e = getenv("A2P_CHAIN_NSPLIT"); mode = e ? atoi(e) : 1; if (mode < 0) mode = 0;
+    if ((e = getenv("A2P_CHAIN_SPLIT_BUDGET"))) budget = atoi(e);
+    if ((e = getenv("A2P_CHAIN_SPLIT_MINH"))) minh = atoi(e) > 0 ? atoi(e) : 1;
+  }
+  if (mode == 0 || n_acc < 2) return 1;
+  if (mode >= 2) return mode < n_acc ? mode : n_acc;
+  int best = 1;
+  for (int s_ = 2; s_ <= 4 && s_ <= n_acc; ++s_)
+    if (n_acc % s_ == 0 && n_acc / s_ >= minh && (long long)tiles * s_ * (concurrent > 0 ? concurrent : 1) <= budget) best = s_;
+  return best;
 }
 
 bool chain_disabled() {
@@ -592,6 +613,9 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
     struct Next { const float* lnw; const float* lnb; int rope; const float* w1; long long w1_row0; int N1; const float* b1;
                   float oscale; int scale_ncols; int gelu; __nv_bfloat16* Cp; long long cp_ps, ldcp; int remap_rps, remap_pad;
                   const float* w2; long long w2_row0; const float* b2; };
+    // residual stream: in place in `x`, except for N-split launches with a FiLM / residual update, which read the current
+    // buffer and write the other one (the LayerNorm scratch of the unfused arm is free here)
+    float *xcur = x, *xalt = hh;
     auto run_chain = [&](int cat, const char* tag, const __nv_bfloat16* A0, long long a0_rows, int K0, const float* w0, const float* b0,
                          int film_off, const Next& nx) -> int {
       ChainOperands o{};
@@ -602,7 +626,9 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       if (nx.w2) A2P_TRY(planes(nx.w2, nx.w2_row0, D, &o.W2, &o.w2_plane_stride));
       cp.M = MT; cp.T = T; cp.K0 = K0; cp.bias0 = b0;
       cp.film_mode = film_off >= 0 ? 1 : 0; cp.film = film; cp.film_ld = film_ld; cp.film_scale_off = film_off; cp.film_shift_off = film_off + D;
-      o.x = x; o.rope_ext = ropeX; o.rope_ext_rows = T + 128;
+      o.x = xcur; o.rope_ext = ropeX; o.rope_ext_rows = T + 128;
+      cp.nsplit = chain_nsplit_for(ceil_div(MT, 128), ceil_div(nx.N1, 128) + (nx.w2 ? 2 : 0), c.concurrent);
+      if (cp.nsplit > 1 && cp.film_mode) { o.x_out = xalt; std::swap(xcur, xalt); }
       cp.ln_mode = nx.lnw ? 1 : 0; cp.ln_w = nx.lnw; cp.ln_b = nx.lnb; cp.rope = nx.rope;
       cp.N1 = nx.N1; cp.bias1 = nx.b1; cp.out_scale = nx.oscale; cp.scale_ncols = nx.scale_ncols; cp.gelu = nx.gelu;
       cp.Cp = nx.Cp; cp.cp_plane_stride = nx.cp_ps; cp.ldcp = nx.ldcp; cp.remap_rps = nx.remap_rps; cp.remap_pad = nx.remap_pad;
@@ -1312,6 +1338,7 @@ static int sample_loop_impl(a2p_denoiser_t* h, int kind, int B, int T, int n_ste
         gb0[g] = b0; gB[g] = b1 - b0;
         Ctx cu{h, c.st};
         cu.slot = u;
+        cu.concurrent = units;
         if (u == u_first) {
           if (stag == 0) A2P_CUDA(cudaEventRecord(evf, c.st));
           else { cu.stagger_ev = evf; cu.stagger_after = stag; }
@@ -1466,6 +1493,10 @@ int a2p_profile_forward_rows(a2p_denoiser_t* h, int B_total, int b0, int Bs, int
   Prof prof;
   Ctx c{h, (cudaStream_t)stream};
   c.prof = &prof;
+  if (branch_mask != A2P_MASK_BOTH) {   // one unit of a sampling step: launch shapes (chain N split) as in the loop
+    const int G = a2p_loop_row_groups(h, B_total, T);
+    c.concurrent = G > 0 ? 2 * G : 1;
+  }
   const float *x0c, *x0u; long long ss;
   A2P_TRY(forward_core(c, Bs, T, x_btc, (const long long*)timesteps, nullptr, branch_mask, (char*)ws, &x0c, &x0u, &ss, b0, B_total));
   A2P_CUDA(cudaStreamSynchronize(c.st));

@@ -154,6 +154,7 @@ int a2p_test_tc_attention(int terms, int R, int T, int D, int dh, int S, int n_e
 void a2p_test_attn2_set_persist(int on) { attn2_persist_override() = on < 0 ? -1 : (on != 0); }
 
 void a2p_test_chain_set_mode(int cl) { chain_mode_override() = (cl == 1 || cl == 2) ? cl : 0; }
+void a2p_test_chain_set_nsplit(int n) { chain_nsplit_override() = n > 0 ? n : 0; }
 
 size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T) {
   return ((size_t)2 * align_up((size_t)M, 128) * K0 + (size_t)2 * 256 * K0 + (size_t)2 * N1 * 256 + (size_t)2 * 256 * 256) * 2 +
@@ -199,7 +200,19 @@ int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int
     cp.trace = reinterpret_cast<long long*>(ext + (size_t)(T + 128) * 128);
     A2P_CUDA(cudaMemsetAsync(cp.trace, 0, 64 * sizeof(long long), st));
   }
+  // N split (a2p_test_chain_set_nsplit): the parts of a tile read x and write the updated stream to a second buffer, which
+  // is copied back so that the caller sees the same in-place contract
+  float* xtmp = nullptr;
+  {
+    const int n_acc = ceil_div(N1, 128) + (vjob ? 2 : 0);
+    cp.nsplit = chain_nsplit_override() > n_acc ? n_acc : chain_nsplit_override();
+    if (cp.nsplit > 1) {
+      A2P_CUDA(cudaMalloc(&xtmp, (size_t)M * 256 * sizeof(float)));
+      o.x_out = xtmp;
+    }
+  }
   A2P_TRY(launch_umma_chain(o, cp, st));
+  if (xtmp) A2P_CUDA(cudaMemcpyAsync(x, xtmp, (size_t)M * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (cp.trace) {
     long long tr[64];
     A2P_CUDA(cudaStreamSynchronize(st));
@@ -209,7 +222,7 @@ int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int
     fprintf(stderr, "\n");
     cp.trace = nullptr;
   }
-  if (iters <= 0) { A2P_CUDA(cudaStreamSynchronize(st)); return 0; }
+  if (iters <= 0) { A2P_CUDA(cudaStreamSynchronize(st)); if (xtmp) cudaFree(xtmp); return 0; }
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, st);
@@ -220,6 +233,7 @@ int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int
   cudaEventElapsedTime(&ms, e0, e1);
   if (ms_out) *ms_out = ms / iters;
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (xtmp) cudaFree(xtmp);
   return 0;
 }
 

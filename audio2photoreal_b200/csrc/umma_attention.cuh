@@ -121,7 +121,6 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
-  pdl_trigger();
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
@@ -164,6 +163,7 @@ umma_attn_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       }
       __syncwarp();
     }
+    pdl_trigger();    // all key blocks requested: the successor's prologue may overlap this CTA's tail (no-op without A2P_PDL)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);

@@ -196,7 +196,6 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
-  pdl_trigger();
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
@@ -245,6 +244,7 @@ umma_attn2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if (++st == NST) { st = 0; ph ^= 1; }
       }
     }
+    pdl_trigger();    // every key block of this CTA's last item is requested: the successor's prologue may overlap the tail (no-op without A2P_PDL)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);

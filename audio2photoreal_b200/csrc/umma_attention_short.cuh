@@ -61,7 +61,6 @@ umma_attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<512>(tmem_slot);
-  pdl_trigger();
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
@@ -91,6 +90,7 @@ umma_attn_short_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       __syncwarp();
       if (++st == NST) { st = 0; ph ^= 1; }
     }
+    pdl_trigger();    // all inbound tiles requested: the stream successor's prologue may overlap this CTA's tail (no-op without A2P_PDL)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idS = umma::idesc_bf16_f32(128, 64);

@@ -49,6 +49,7 @@ struct ChainParams {
   int gelu;
   __nv_bfloat16* Cp; long long cp_plane_stride, ldcp; int remap_rps, remap_pad;
   int vjob; const float* bias2; __nv_bfloat16* Vt; long long vt_plane_stride, ldvt;
+  int nsplit;                // > 1: every 128-row tile is worked on by nsplit CTAs (CTA pairs in pair mode), see "N split" below
   long long* trace;          // optional [64] clock64 timeline of CTA 0 (A2P_CHAIN_TRACE=1 in the test hook)
 };
 
@@ -389,7 +390,8 @@ template <int CL>
 __global__ void __launch_bounds__(CH_THREADS, 1)
 umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmTab, ChainParams p) {
+                  const __grid_constant__ CUtensorMap tmXin, const __grid_constant__ CUtensorMap tmXout,
+                  const __grid_constant__ CUtensorMap tmTab, ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sSlots = smem;
@@ -411,11 +413,24 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 39 + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * 128;
   const uint32_t crank = CL == 2 ? cluster_ctarank() : 0u, peer = crank ^ 1u;
   const int kc0 = ceil_div(p.K0, 64);
   const int NH1 = ceil_div(p.N1, 128);
   const int n_acc = NH1 + (p.vjob ? 2 : 0);
+  // ---- N split (small batches: a launch of 10-40 tiles leaves most of the 148 SMs idle, and its duration is the serial
+  // GEMM0 -> E_A -> GEMM1 / E_B time of ONE tile).  Every tile is given to nsplit "parts" = consecutive CTAs (consecutive CTA pairs
+  // in pair mode); each part runs GEMM0 + E_A redundantly (idle SMs are free; bit-identical work) and then only ITS range
+  // [h_lo, h_hi) of the n_acc 128-column accumulator halves of GEMM1 / the V job.  The parts never talk to each other: the
+  // residual stream is read from x_in and written to a DIFFERENT buffer x_out (by the parts that own V halves, which re-read
+  // their own store; by part 0 when there is no V job), so no part can observe another part's update of the tile.
+  const int nsp = p.nsplit > 1 ? p.nsplit : 1;
+  const int unit_ = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_ = unit_ / nsp, part = unit_ - tile_ * nsp;
+  const int m0 = (CL == 2 ? tile_ * 2 + (int)crank : tile_) * 128;
+  const int h_lo = part * n_acc / nsp, h_hi = (part + 1) * n_acc / nsp, n_loc = h_hi - h_lo;
+  const int g_lo = ::min(h_lo, NH1), g_hi = ::min(h_hi, NH1), n_g1 = g_hi - g_lo;       // GEMM1 halves of this part
+  const int v_lo = ::max(h_lo, NH1) - NH1, v_hi = ::max(h_hi, NH1) - NH1, n_v = v_hi - v_lo;   // V-job halves of this part
+  const bool x_writer = p.vjob ? n_v > 0 : part == 0;
   // ring positions of the slot sequence (identical arithmetic in every role)
   // single CTA: per 64-wide K chunk of GEMM0 two A0 tiles + four W0 tiles (plane x 128-row half), per 128-column half of
   // GEMM1 / the V job eight W tiles (K chunk x plane).  CTA pair: every CTA fetches HALF of the weight rows -- two A0 tiles +
@@ -423,12 +438,13 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   constexpr int G0S = CL == 2 ? 4 : 6, G1S = CL == 2 ? 4 : 8;
   const int seqEA = G0S * kc0;                    // 8 x chunks (loaded, or only reserved as store buffers if !film_mode)
   const int seqTab = seqEA + 8;                   // 8 RoPE-table chunks (if rope)
-  const int seqG1 = seqTab + (p.rope ? 8 : 0);    // NH1 * G1S W1 tiles
-  const int seqVx = seqG1 + G1S * NH1;            // 8 x chunks again (V job)
-  const int seqV = seqVx + 8;                     // 2 * G1S W2 tiles
+  const int seqG1 = seqTab + (p.rope ? 8 : 0);    // n_g1 * G1S W1 tiles
+  const int seqVx = seqG1 + G1S * n_g1;           // 8 x chunks again (V job)
+  const int seqV = seqVx + 8;                     // n_v * G1S W2 tiles
 
   if (warp == 0 && lane == 0) {
-    umma::prefetch_tmap(&tmA0); umma::prefetch_tmap(&tmW0); umma::prefetch_tmap(&tmW1); umma::prefetch_tmap(&tmX);
+    umma::prefetch_tmap(&tmA0); umma::prefetch_tmap(&tmW0); umma::prefetch_tmap(&tmW1); umma::prefetch_tmap(&tmXin);
+    umma::prefetch_tmap(&tmXout);
     if (p.rope) umma::prefetch_tmap(&tmTab);
     if (p.vjob) umma::prefetch_tmap(&tmW2);
   }
@@ -443,7 +459,6 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     umma::fence_barrier_init();
   }
   if (warp == 2) { if (CL == 2) tmem_alloc_pair<512>(tmem_slot); else umma::tmem_alloc<512>(tmem_slot); }
-  pdl_trigger();
   umma::fence_before();
   __syncthreads();
   if (CL == 2) cluster_sync_all();     // the peer's barriers and tensor memory exist before anything is committed / arrived remotely
@@ -494,7 +509,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     CH_TRACE(24, lane == 0);
 #pragma unroll 1
-    for (int j = 0; j < 8; ++j) issue(&tmX, p.film_mode ? 1 : 2, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0, 0);
+    for (int j = 0; j < 8; ++j) issue(&tmXin, p.film_mode ? 1 : 2, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0, 0);
     if (p.rope) {
       const int tab_row = m0 % p.T;
 #pragma unroll 1
@@ -502,21 +517,31 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     }
     CH_TRACE(25, lane == 0);
 #pragma unroll 1
-    for (int j = 0; j < G1S * NH1; ++j) {
-      if (CL == 2) issue(&tmW1, 0, (j & 3) * 64, (j >> 2) * 128 + (int)crank * 64, 0);  // box = both planes of my 64 rows
-      else issue(&tmW1, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
-    }
-    CH_TRACE(26, lane == 0);
-    if (p.vjob) {
-      umma::mbar_wait(x_stored, 0);   // the x tile written by E_A is globally visible
+    for (int h = g_lo; h < g_hi; ++h) {
 #pragma unroll 1
-      for (int j = 0; j < 8; ++j) issue(&tmX, 1, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0, 0);
-#pragma unroll 1
-      for (int j = 0; j < 2 * G1S; ++j) {
-        if (CL == 2) issue(&tmW2, 0, (j & 3) * 64, (j >> 2) * 128 + (int)crank * 64, 0);
-        else issue(&tmW2, 0, ((j >> 1) & 3) * 64, (j >> 3) * 128, j & 1);
+      for (int j = 0; j < G1S; ++j) {
+        if (CL == 2) issue(&tmW1, 0, (j & 3) * 64, h * 128 + (int)crank * 64, 0);       // box = both planes of my 64 rows
+        else issue(&tmW1, 0, ((j >> 1) & 3) * 64, h * 128, j & 1);
       }
     }
+    CH_TRACE(26, lane == 0);
+    if (n_v > 0) {
+      umma::mbar_wait(x_stored, 0);   // the x tile written by E_A is globally visible
+#pragma unroll 1
+      for (int j = 0; j < 8; ++j) issue(&tmXout, 1, ((j % CH_NWG) * (8 / CH_NWG) + j / CH_NWG) * 32, m0, 0);
+#pragma unroll 1
+      for (int hv = v_lo; hv < v_hi; ++hv) {
+#pragma unroll 1
+        for (int j = 0; j < G1S; ++j) {
+          if (CL == 2) issue(&tmW2, 0, (j & 3) * 64, hv * 128 + (int)crank * 64, 0);
+          else issue(&tmW2, 0, ((j >> 1) & 3) * 64, hv * 128, j & 1);
+        }
+      }
+    }
+    // every inbound tile of this CTA has been requested: what is left is the tail of GEMM1 / the last epilogue halves, so the
+    // stream successor (launched with the programmatic-serialisation attribute when A2P_PDL is on) may be scheduled now: its
+    // prologue overlaps this tail instead of idling through it; no-op without the attribute
+    pdl_trigger();
   } else if (warp == 1 && (CL == 1 || crank == 0)) {
     // ================= MMA issuer (pair mode: the leader CTA issues for both) =================
     constexpr uint32_t idesc = CL == 2 ? umma::idesc_bf16_f32(256, 128) : umma::idesc_bf16_f32(128, 128);
@@ -574,11 +599,12 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     // ---- GEMM1 and the V job: A = planes in tensor memory, B = weight tile from the ring
     CH_TRACE(17, lane == 0);
 #pragma unroll 1
-    for (int h = 0; h < n_acc; ++h) {
-      if (h == 0) { umma::mbar_wait(a_ready, 0); umma::fence_after(); q = seqG1; CH_TRACE(18, lane == 0); }
-      if (h == NH1) { umma::mbar_wait(a2_ready, 0); umma::fence_after(); q = seqV; }
-      const int buf = h & 1;
-      if (h >= 2) { umma::mbar_wait(&acc1_empty[buf], ((h >> 1) - 1) & 1); umma::fence_after(); }
+    for (int jh = 0; jh < n_loc; ++jh) {
+      const int h = h_lo + jh;           // global accumulator half (columns / V half); buffers and parities follow the local index
+      if (jh == 0 && n_g1 > 0) { umma::mbar_wait(a_ready, 0); umma::fence_after(); q = seqG1; CH_TRACE(18, lane == 0); }
+      if (jh == n_g1 && n_v > 0) { umma::mbar_wait(a2_ready, 0); umma::fence_after(); q = seqV; }
+      const int buf = jh & 1;
+      if (jh >= 2) { umma::mbar_wait(&acc1_empty[buf], ((jh >> 1) - 1) & 1); umma::fence_after(); }
       const uint32_t d = tmem_base + 256 + buf * 128;
 #pragma unroll 1
       for (int st8 = 0; st8 < G1S; ++st8) {
@@ -617,7 +643,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             chain_commit<CL>(&s_empty[s]);
             if (kc == 3 && pw == 1) {
               chain_commit<CL>(&acc1_full[buf]);
-              if (h == NH1 - 1) chain_commit<CL>(a_reads_done);
+              if (h == g_hi - 1) chain_commit<CL>(a_reads_done);     // last GEMM1 half of this part (never true for a V half)
             }
           }
           __syncwarp();
@@ -637,8 +663,10 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int g = 0; g < CH_NWG; ++g) {
           const int j = r * CH_NWG + g;
           umma::mbar_wait(&x_written[j], 0);
-          tma_store_2d(&tmX, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, (g * (8 / CH_NWG) + r) * 32, m0);
-          bulk_commit();
+          if (x_writer) {
+            tma_store_2d(&tmXout, slots_u32 + ((seqEA + j) % CH_NS) * CH_TILE, (g * (8 / CH_NWG) + r) * 32, m0);
+            bulk_commit();
+          }
         }
         static_assert(CH_NWG == 4, "staggered waits below assume 4 stores per round");
         bulk_wait_read<3>(); umma::mbar_arrive(&s_empty[(seqEA + r * CH_NWG + 0) % CH_NS]);
@@ -647,7 +675,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         bulk_wait_read<0>(); umma::mbar_arrive(&s_empty[(seqEA + r * CH_NWG + 3) % CH_NS]);
       }
       bulk_wait_all();           // globally visible (the V job re-reads the tile; nothing may be in flight at exit)
-      if (p.vjob) umma::mbar_arrive(x_stored);
+      if (n_v > 0) umma::mbar_arrive(x_stored);
     }
     __syncwarp();
   } else if (warp >= 4) {
@@ -782,19 +810,21 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
     const int pair = wg >> 1, sub = wg & 1;
     const int r8 = lane >> 2, u4 = lane & 3;               // transposed phase: lane -> (row sub-index, 16-byte unit)
     bool vprep_done = false;
+    // one extra (empty) iteration for a warpgroup pair that drains no V half of this part: its plane chunks are still needed
 #pragma unroll 1
-    for (int h = pair; h < n_acc; h += 2) {
+    for (int jh = pair; jh < n_loc || (n_v > 0 && !vprep_done); jh += 2) {
+      const int h = h_lo + jh;
       const bool vj = h >= NH1;
       if (vj && !vprep_done) {
-        umma::mbar_wait(a_reads_done, 0);    // every GEMM1 MMA has read the rotated planes
-        umma::fence_after();
+        if (n_g1 > 0) { umma::mbar_wait(a_reads_done, 0); umma::fence_after(); }   // every GEMM1 MMA of this part has read the rotated planes
         chain_emit_planes<CL>(ectx, 0, seqVx, 0);
         __syncwarp();
         if (lane == 0) arrive_at_leader<CL>(a2_ready, crank);
         vprep_done = true;
       }
-      const int buf = h & 1;
-      umma::mbar_wait(&acc1_full[buf], (h >> 1) & 1);
+      if (jh >= n_loc) break;
+      const int buf = jh & 1;
+      umma::mbar_wait(&acc1_full[buf], (jh >> 1) & 1);
       umma::fence_after();
       CH_TRACE(6 + h, et == 0 && h < 10);
       const int remap_first = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_pad : 0;   // pad rows in front of the tile's first sample
@@ -899,6 +929,7 @@ inline int make_tmap_f32_2d(CUtensorMap* tm, const void* base, long long cols, l
 // 0 = one CTA per tile, 2 = auto: pairs only for the launches whose GEMM0 streams a long weight matrix (K0 >= 1024: the FFN2
 // chains, the only ones the pair mode speeds up -- profiles/r02_chain_pair_mode.txt)
 inline int& chain_mode_override() { static int v = 0; return v; }   // tests: 1 / 2 forces the mode of the next launches
+inline int& chain_nsplit_override() { static int v = 0; return v; }  // tests: > 0 forces the N split of the next launches
 inline int chain_cluster_size(int K0) {
   if (chain_mode_override() > 0) return chain_mode_override();
   static int v = -1;
@@ -913,6 +944,7 @@ struct ChainOperands {
   const __nv_bfloat16* W1; long long w1_plane_stride;                   // [2][N1][256]
   const __nv_bfloat16* W2; long long w2_plane_stride;                   // [2][256][256] (null without a V job)
   float* x;                                                             // [M][256] fp32 residual stream (read if film_mode, always written)
+  float* x_out;                                                         // null: update x in place; else the new stream is written here (required by nsplit > 1 with film_mode)
   const float* rope_ext; long long rope_ext_rows;                       // [T + 128][256] fp32: (cos, sin) pairs of position (row % T)
 };
 
@@ -921,9 +953,13 @@ inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaS
   if (p.T < 128 || p.M % 8) A2P_FAIL("chain: needs T >= 128 and M %% 8 == 0 (T=%d M=%d)", p.T, p.M);
   if (p.vjob && (!o.W2 || !p.Vt)) A2P_FAIL("chain: V job needs W2 and Vt");
   if (p.rope && (!o.rope_ext || o.rope_ext_rows < p.T + 128)) A2P_FAIL("chain: RoPE needs the extended table (T + 128 rows)");
-  CUtensorMap tA0, tW0, tW1, tW2, tX, tTab;
+  CUtensorMap tA0, tW0, tW1, tW2, tXin, tXout, tTab;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   const int cl = force_cl > 0 ? force_cl : chain_cluster_size(p.K0);
+  const int n_acc = ceil_div(p.N1, 128) + (p.vjob ? 2 : 0);
+  const int nsp = p.nsplit > 1 ? p.nsplit : 1;
+  if (nsp > n_acc) A2P_FAIL("chain: nsplit=%d exceeds the %d accumulator halves of the launch", nsp, n_acc);
+  if (nsp > 1 && p.film_mode && (!o.x_out || o.x_out == o.x)) A2P_FAIL("chain: nsplit > 1 needs a separate x_out buffer");
   // pair mode: a CTA loads its 128 of the 256 W0 rows (one plane per box) and, for a 128-column accumulator half of GEMM1 / the
   // V job, both planes of its 64 rows in ONE box [64 k][64 rows][2 planes] = one 16 KB slot
   const int w1rows = cl == 2 ? 64 : 128, w1planes = cl == 2 ? 2 : 1;
@@ -932,20 +968,29 @@ inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaS
   A2P_TRY(make_tmap_bf16_3d(&tW1, o.W1, 256, p.N1, 2, 256, o.w1_plane_stride, 64, w1rows, sw, w1planes));
   if (p.vjob) A2P_TRY(make_tmap_bf16_3d(&tW2, o.W2, 256, 256, 2, 256, o.w2_plane_stride, 64, w1rows, sw, w1planes));
   else tW2 = tW1;
-  A2P_TRY(make_tmap_f32_2d(&tX, o.x, 256, p.M, 256, 32, 128));
+  A2P_TRY(make_tmap_f32_2d(&tXin, o.x, 256, p.M, 256, 32, 128));
+  if (o.x_out && o.x_out != o.x) A2P_TRY(make_tmap_f32_2d(&tXout, o.x_out, 256, p.M, 256, 32, 128));
+  else tXout = tXin;
   if (p.rope) A2P_TRY(make_tmap_f32_2d(&tTab, o.rope_ext, 256, o.rope_ext_rows, 256, 32, 128));
-  else tTab = tX;
+  else tTab = tXin;
   const int tiles = ceil_div(p.M, 128);
   if (cl == 2) {
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((tiles + 1) / 2 * 2); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = CH_SMEM_BYTES; cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cfg.gridDim = dim3((tiles + 1) / 2 * 2 * nsp); cfg.blockDim = dim3(CH_THREADS); cfg.dynamicSmemBytes = CH_SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    A2P_CUDA(cudaLaunchKernelEx(&cfg, umma_chain_kernel<2>, tA0, tW0, tW1, tW2, tX, tTab, p));
+    int na = 1;
+    if (pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    A2P_CUDA(cudaLaunchKernelEx(&cfg, umma_chain_kernel<2>, tA0, tW0, tW1, tW2, tXin, tXout, tTab, p));
   } else {
-    A2P_CUDA(launch_pdl(umma_chain_kernel<1>, dim3(tiles), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, st, tA0, tW0, tW1, tW2, tX, tTab, p));
+    A2P_CUDA(launch_pdl(umma_chain_kernel<1>, dim3(tiles * nsp), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, st, tA0, tW0, tW1, tW2, tXin, tXout,
+                        tTab, p));
   }
   return 0;
 }

@@ -86,7 +86,6 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
     umma::fence_barrier_init();
   }
   if (warp == 2) umma::tmem_alloc<2 * TC_BN>(tmem_slot);
-  pdl_trigger();   // the successor may be scheduled as soon as this CTA's resources free up
   umma::fence_before();
   __syncthreads();
   umma::fence_after();
@@ -118,6 +117,7 @@ __global__ void __launch_bounds__(256, 1) umma_gemm_kernel(const __grid_constant
         if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
       }
     }
+    pdl_trigger();   // all operand tiles requested: the successor's prologue may overlap this CTA's last tiles (no-op without A2P_PDL)
   } else if (warp == 1) {
     // ================= MMA issuer =================
     constexpr uint32_t idesc = umma::idesc_bf16_f32(TC_BM, TC_BN);
