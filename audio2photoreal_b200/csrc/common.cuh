@@ -58,12 +58,13 @@ struct BranchPtr {
 // (227 KB of shared memory each) spinning in pdl_wait() for the whole duration of this kernel -- neutral on a single
 // forward, 10 % slower with concurrent forwards (profiles/r01t).  The trigger now sits where a CTA's producer warp has
 // requested its last inbound tile, i.e. a few microseconds before the CTA ends: only the successor's prologue (barrier
-// init, tensor-memory allocation, descriptor prefetch) and the launch latency overlap this kernel's tail.  A2P_PDL=1 / 0.
+// init, tensor-memory allocation, descriptor prefetch) and the launch latency overlap this kernel's tail: B = 8 loop +4.6 %, B = 4 +3 %, B = 32 unchanged (SM-time bound) -- default on
+// (profiles/r02_chain_nsplit_pdl.txt).  A2P_PDL=0 switches the attribute off.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 #ifndef A2P_PDL_DEFAULT
-#define A2P_PDL_DEFAULT 0
+#define A2P_PDL_DEFAULT 1
 #endif
 inline bool pdl_enabled() {
   static int v = -1;

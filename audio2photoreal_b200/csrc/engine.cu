@@ -386,11 +386,15 @@ int chain_priority() {   // A2P_CHAIN_PRIO=p: launch priority of the chain kerne
 }
 
 // N split of the chain launches (umma_chain.cuh): a launch of `tiles` 128-row tiles whose GEMM1 / V job has n_acc 128-column
-// accumulator halves is cut into s parts per tile when the step's `concurrent` forwards together leave SMs idle:
-// s = the largest divisor of n_acc with tiles * s * concurrent <= budget and n_acc / s >= min halves per part.
-// A2P_CHAIN_NSPLIT=0 off, 1 auto (default), n >= 2 force (capped by n_acc); A2P_CHAIN_SPLIT_BUDGET (default 160 CTAs),
-// A2P_CHAIN_SPLIT_MINH (default 2).
-int chain_nsplit_for(int tiles, int n_acc, int concurrent) {
+// accumulator halves is cut into s parts per tile when the step's `concurrent` forwards together leave SMs idle.  The parts
+// repeat GEMM0 + E_A, so the split pays where that prefix is short against the GEMM1 / E_B tail: s = the largest divisor of
+// n_acc with n_acc / s >= 2 halves per part and tiles * s * concurrent <= budget CTAs, budget = 160 (the machine) for launches
+// with K0 <= 256 (the FFN1 + GELU launch: 45 -> 33 -> 27 us at s = 1 / 2 / 4) and 80 for the K0 = 1024 launches (FFN2 -> LN ->
+// Q|K|V: 57 -> 49 -> 42 us at s = 1 / 2 / 3, but their redundant prefix is 60 % of the launch).  Measured on the loop
+// (profiles/r02_chain_nsplit_pdl.txt): B = 4 + 7 %, B = 8 + 1..3 %, B >= 16 never splits.
+// A2P_CHAIN_NSPLIT=0 off, 1 auto (default), n >= 2 force (capped by n_acc); A2P_CHAIN_SPLIT_BUDGET (CTAs, default 160),
+// A2P_CHAIN_SPLIT_MINH (halves per part, default 2).
+int chain_nsplit_for(int tiles, int n_acc, int concurrent, int K0) {
   static int mode = -1, budget = 160, minh = 2;
   if (mode < 0) {
     const char* e = getenv("A2P_CHAIN_NSPLIT"); mode = e ? atoi(e) : 1; if (mode < 0) mode = 0;
@@ -399,9 +403,10 @@ int chain_nsplit_for(int tiles, int n_acc, int concurrent) {
   }
   if (mode == 0 || n_acc < 2) return 1;
   if (mode >= 2) return mode < n_acc ? mode : n_acc;
+  const long long cap = K0 <= 256 ? budget : budget / 2;
   int best = 1;
   for (int s_ = 2; s_ <= 4 && s_ <= n_acc; ++s_)
-    if (n_acc % s_ == 0 && n_acc / s_ >= minh && (long long)tiles * s_ * (concurrent > 0 ? concurrent : 1) <= budget) best = s_;
+    if (n_acc % s_ == 0 && n_acc / s_ >= minh && (long long)tiles * s_ * (concurrent > 0 ? concurrent : 1) <= cap) best = s_;
   return best;
 }
 
@@ -627,7 +632,7 @@ int forward_core(Ctx& c, int B, int T, const float* xin, const long long* ts, co
       cp.M = MT; cp.T = T; cp.K0 = K0; cp.bias0 = b0;
       cp.film_mode = film_off >= 0 ? 1 : 0; cp.film = film; cp.film_ld = film_ld; cp.film_scale_off = film_off; cp.film_shift_off = film_off + D;
       o.x = xcur; o.rope_ext = ropeX; o.rope_ext_rows = T + 128;
-      cp.nsplit = chain_nsplit_for(ceil_div(MT, 128), ceil_div(nx.N1, 128) + (nx.w2 ? 2 : 0), c.concurrent);
+      cp.nsplit = chain_nsplit_for(ceil_div(MT, 128), ceil_div(nx.N1, 128) + (nx.w2 ? 2 : 0), c.concurrent, K0);
       if (cp.nsplit > 1 && cp.film_mode) { o.x_out = xalt; std::swap(xcur, xalt); }
       cp.ln_mode = nx.lnw ? 1 : 0; cp.ln_w = nx.lnw; cp.ln_b = nx.lnb; cp.rope = nx.rope;
       cp.N1 = nx.N1; cp.bias1 = nx.b1; cp.out_scale = nx.oscale; cp.scale_ncols = nx.scale_ncols; cp.gelu = nx.gelu;
