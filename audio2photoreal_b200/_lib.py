@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "liba2p_b200.so")
 SYMBOLS = [
     "a2p_abi_version", "a2p_last_error", "a2p_has_tcgen05", "a2p_denoiser_create", "a2p_denoiser_destroy",
     "a2p_packed_weight_bytes", "a2p_denoiser_bind_weights", "a2p_kv_cache_bytes", "a2p_denoiser_set_conditioning",
-    "a2p_conditioning_workspace_bytes", "a2p_workspace_bytes", "a2p_denoiser_forward", "a2p_sampler_step",
+    "a2p_conditioning_workspace_bytes", "a2p_encode_workspace_bytes", "a2p_denoiser_encode_conditioning", "a2p_workspace_bytes", "a2p_denoiser_forward", "a2p_sampler_step",
     "a2p_sample_loop", "a2p_sample_loop_rng", "a2p_sampler_step_rng", "a2p_profile_forward", "a2p_profile_forward_rows", "a2p_loop_row_groups", "a2p_launch_count",
 ]
 
@@ -63,6 +63,9 @@ def load() -> C.CDLL:
     lib.a2p_kv_cache_bytes.restype = sz
     lib.a2p_conditioning_workspace_bytes.argtypes = [P(ModelCfg), i32, i32]
     lib.a2p_conditioning_workspace_bytes.restype = sz
+    lib.a2p_encode_workspace_bytes.argtypes = [P(ModelCfg), i32, i32, i32]
+    lib.a2p_encode_workspace_bytes.restype = sz
+    lib.a2p_denoiser_encode_conditioning.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.a2p_workspace_bytes.argtypes = [P(ModelCfg), i32, i32]
     lib.a2p_workspace_bytes.restype = sz
     lib.a2p_denoiser_set_conditioning.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp, sz, vp]
@@ -80,7 +83,8 @@ def load() -> C.CDLL:
     lib.a2p_launch_count.argtypes = [vp]
     lib.a2p_launch_count.restype = i64
     for name in ("a2p_denoiser_create", "a2p_denoiser_bind_weights", "a2p_denoiser_set_conditioning",
-                 "a2p_denoiser_forward", "a2p_sampler_step", "a2p_sample_loop", "a2p_sample_loop_rng", "a2p_sampler_step_rng"):
+                 "a2p_denoiser_encode_conditioning", "a2p_denoiser_forward", "a2p_sampler_step", "a2p_sample_loop", "a2p_sample_loop_rng",
+                 "a2p_sampler_step_rng"):
         getattr(lib, name).restype = i32
     if lib.a2p_abi_version() != 1:
         raise A2PError("liba2p_b200.so ABI version mismatch")

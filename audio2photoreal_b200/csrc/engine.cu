@@ -69,6 +69,16 @@ struct a2p_denoiser {
   LayerW lw[MAXL]{};
   const float *time_w1, *time_b1, *time_w2, *time_b2, *time_w3, *time_b3;
   const float *normc_w, *normc_b, *inp_w, *inp_b, *fin_w, *fin_b, *fconv_w, *fconv_b;
+  // step-invariant conditioning encoders (a2p_denoiser_encode_conditioning; optional in the weight table)
+  struct EncLayerW { const float *n1w, *n1b, *n2w, *n2b, *in_w, *in_b, *out_w, *out_b, *l1w, *l1b, *l2w, *l2b; };
+  struct EncW {
+    const float *cp_w = nullptr, *cp_b = nullptr;                                   // cond_projection [D, feat_dim]
+    const float *p0w = nullptr, *p0b = nullptr, *p1w = nullptr, *p1b = nullptr, *p3w = nullptr, *p3b = nullptr;   // non_attn_cond_projection
+    const float *fp_w = nullptr, *fp_b = nullptr, *fn_w = nullptr, *fn_b = nullptr; // frame_cond_projection, frame_norm_cond (pose)
+    EncLayerW enc[2]{};                                                             // cond_encoder (face)
+    int feat_dim = 0;
+    bool ok = false;
+  } encw;
   const float* conv_b[6];
   const float* time_freqs;
   // derived arena
@@ -1033,6 +1043,41 @@ int a2p_denoiser_bind_weights(a2p_denoiser_t* h, const a2p_weight_t* table, int 
   h->fin_w = W("final_layer.weight", C * D); h->fin_b = W("final_layer.bias", C);
   h->time_freqs = W("a2p.time_freqs", D / 2);
   const float* freqs = W("rotary.freqs", D / 2);
+  {   // conditioning encoders: optional (a table without them can still be driven through set_conditioning with caller-made tokens)
+    auto WO = [&](const std::string& k, int64_t numel) -> const float* {
+      auto it = m.find(k);
+      return (it != m.end() && (numel < 0 || it->second.second == numel)) ? it->second.first : nullptr;
+    };
+    a2p_denoiser::EncW& ew = h->encw;
+    ew = a2p_denoiser::EncW{};
+    auto itc = m.find("cond_projection.weight");
+    if (itc != m.end() && itc->second.second % D == 0) {
+      ew.feat_dim = (int)(itc->second.second / D);
+      ew.cp_w = itc->second.first; ew.cp_b = WO("cond_projection.bias", D);
+      ew.p0w = WO("non_attn_cond_projection.0.weight", D); ew.p0b = WO("non_attn_cond_projection.0.bias", D);
+      ew.p1w = WO("non_attn_cond_projection.1.weight", D * D); ew.p1b = WO("non_attn_cond_projection.1.bias", D);
+      ew.p3w = WO("non_attn_cond_projection.3.weight", D * D); ew.p3b = WO("non_attn_cond_projection.3.bias", D);
+      bool ok = ew.cp_b && ew.p0w && ew.p0b && ew.p1w && ew.p1b && ew.p3w && ew.p3b;
+      if (cf.fmt == A2P_FMT_POSE) {
+        ew.fp_w = WO("frame_cond_projection.weight", D * C); ew.fp_b = WO("frame_cond_projection.bias", D);
+        ew.fn_w = WO("frame_norm_cond.weight", D); ew.fn_b = WO("frame_norm_cond.bias", D);
+        ok = ok && ew.fp_w && ew.fp_b && ew.fn_w && ew.fn_b;
+      } else {
+        for (int i = 0; i < 2; ++i) {
+          const std::string p = "cond_encoder." + std::to_string(i) + ".";
+          a2p_denoiser::EncLayerW& e = ew.enc[i];
+          e.n1w = WO(p + "norm1.weight", D); e.n1b = WO(p + "norm1.bias", D);
+          e.n2w = WO(p + "norm2.weight", D); e.n2b = WO(p + "norm2.bias", D);
+          e.in_w = WO(p + "self_attn.in_proj_weight", 3 * D * D); e.in_b = WO(p + "self_attn.in_proj_bias", 3 * D);
+          e.out_w = WO(p + "self_attn.out_proj.weight", D * D); e.out_b = WO(p + "self_attn.out_proj.bias", D);
+          e.l1w = WO(p + "linear1.weight", FF * D); e.l1b = WO(p + "linear1.bias", FF);
+          e.l2w = WO(p + "linear2.weight", D * FF); e.l2b = WO(p + "linear2.bias", D);
+          ok = ok && e.n1w && e.n1b && e.n2w && e.n2b && e.in_w && e.in_b && e.out_w && e.out_b && e.l1w && e.l1b && e.l2w && e.l2b;
+        }
+      }
+      ew.ok = ok;
+    }
+  }
   char* pb = (char*)packed;
   auto P = [&](size_t off) { return reinterpret_cast<float*>(pb + off); };
   h->film_w = P(pl.film_w); h->film_b = P(pl.film_b); h->ttk_w = P(pl.ttk_w); h->ttk_b = P(pl.ttk_b);
@@ -1155,6 +1200,126 @@ size_t a2p_workspace_bytes(const a2p_model_cfg* cfg, int B, int T) {
     if (n > need) need = n;
   }
   return need;
+}
+
+// ---- step-invariant conditioning encoders (model/diffusion.py:355-381), exact fp32 (FFMA GEMMs, fp32 attention): they run once
+// per distinct y and their result feeds every one of the 2000 denoiser evaluations of a loop
+__global__ void pad_cols_kernel(const float* __restrict__ src, long long ld_src, int cols, float* __restrict__ dst, long long ld_dst,
+                                long long rows) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * ld_dst) return;
+  const long long r = idx / ld_dst;
+  const int c = (int)(idx - r * ld_dst);
+  dst[idx] = c < cols ? src[r * ld_src + c] : 0.f;
+}
+// out[b][d] = mean over s of tok[b][s][d]  (tokens.mean(dim=-2), model/diffusion.py:380); fp64 accumulation, one thread per column
+__global__ void mean_rows_kernel(const float* __restrict__ tok, int S, int D, float* __restrict__ out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (d >= D) return;
+  const float* p = tok + (long long)b * S * D + d;
+  double acc = 0.0;
+  for (int s_ = 0; s_ < S; ++s_) acc += (double)p[(long long)s_ * D];
+  out[(long long)b * D + d] = (float)(acc / (double)S);
+}
+
+static size_t encode_ws_floats(const a2p_model_cfg& cf, int Bc, int S, int feat_dim) {
+  const size_t D = cf.D, rows = (size_t)Bc * S;
+  const size_t Kp = align_up((size_t)feat_dim, 8);
+  size_t n = 0;
+  if ((size_t)feat_dim != Kp) n += align_up(rows * Kp, 64) + align_up(D * Kp, 64);
+  n += 3 * align_up((size_t)Bc * D, 64);                                   // pooled mean, LayerNorm, hidden layer
+  if (cf.fmt == A2P_FMT_POSE) n += align_up((size_t)Bc * (cf.S2 > 0 ? cf.S2 : 1) * D, 64);
+  else n += 2 * align_up(rows * D, 64) + align_up(rows * 3 * D, 64) + align_up(rows * D, 64) + align_up(rows * cf.FF, 64);
+  return n;
+}
+
+size_t a2p_encode_workspace_bytes(const a2p_model_cfg* cfg, int Bc, int S, int feat_dim) {
+  if (check_cfg(cfg) || Bc <= 0 || S <= 0 || feat_dim <= 0) return 0;
+  return encode_ws_floats(*cfg, Bc, S, feat_dim) * sizeof(float) + 512;
+}
+
+int a2p_denoiser_encode_conditioning(a2p_denoiser_t* h, int Bc, int S, int S2, int feat_dim, const float* feats,
+                                     const float* keyframes, float* cond_tokens, float* cond_hidden, float* pose_tokens,
+                                     void* ws, size_t ws_bytes, void* stream) {
+  if (!h || !h->bound) A2P_FAIL("encode_conditioning: weights not bound");
+  const a2p_model_cfg& cf = h->cfg;
+  const a2p_denoiser::EncW& ew = h->encw;
+  if (!ew.ok) A2P_FAIL("encode_conditioning: the bound weight table has no (complete) cond_projection / non_attn_cond_projection / %s",
+                       cf.fmt == A2P_FMT_POSE ? "frame_cond_projection" : "cond_encoder");
+  if (Bc <= 0 || S <= 0 || !feats || !cond_tokens || !cond_hidden || !ws) A2P_FAIL("encode_conditioning: bad argument");
+  if (feat_dim != ew.feat_dim) A2P_FAIL("encode_conditioning: feature width %d, cond_projection expects %d", feat_dim, ew.feat_dim);
+  if (cf.fmt == A2P_FMT_POSE && (!keyframes || !pose_tokens || S2 <= 0 || S2 > cf.S2))
+    A2P_FAIL("encode_conditioning: pose model needs keyframes / pose_tokens with 0 < S2 <= %d", cf.S2);
+  if (S > cf.max_pos) A2P_FAIL("encode_conditioning: S=%d exceeds cfg.max_pos=%d", S, cf.max_pos);
+  if (ws_bytes < a2p_encode_workspace_bytes(&cf, Bc, S, feat_dim)) A2P_FAIL("encode_conditioning: workspace too small");
+  const int D = cf.D, rows = Bc * S;
+  Ctx c{h, (cudaStream_t)stream};
+  cudaStream_t st = c.st;
+  c.cat = CAT_COND;
+  float* wp = reinterpret_cast<float*>(ws);
+  auto take = [&](size_t n) { float* r = wp; wp += align_up(n, 64); return r; };
+  // ---- tokens = cond_projection(feats)   (model/diffusion.py:372; K padded to a multiple of 8 for the GEMM's 16-byte loads)
+  const int Kp = (int)align_up((size_t)feat_dim, 8);
+  const float *A = feats, *Wc = ew.cp_w;
+  if (Kp != feat_dim) {
+    float* Ap = take((size_t)rows * Kp);
+    float* Wp = take((size_t)D * Kp);
+    pad_cols_kernel<<<(unsigned)(((long long)rows * Kp + 255) / 256), 256, 0, st>>>(feats, feat_dim, feat_dim, Ap, Kp, rows);
+    pad_cols_kernel<<<(unsigned)(((long long)D * Kp + 255) / 256), 256, 0, st>>>(ew.cp_w, feat_dim, feat_dim, Wp, Kp, D);
+    A2P_CUDA(cudaGetLastError());
+    h->launches += 2;
+    A = Ap; Wc = Wp;
+  }
+  A2P_TRY(gemm(c, A, Kp, rows, Wc, Kp, ew.cp_b, D, Kp, cond_tokens, D));
+  float* pooled = take((size_t)Bc * D);
+  float* pooled_n = take((size_t)Bc * D);
+  float* hid1 = take((size_t)Bc * D);
+  if (cf.fmt == A2P_FMT_FACE) {
+    // ---- cond_encoder: two pre-LN encoder layers with rotary self-attention (transformer_modules.py:69-102, model/diffusion.py:158-171)
+    float* hn = take((size_t)rows * D);
+    float* hr = take((size_t)rows * D);
+    float* qkv = take((size_t)rows * 3 * D);
+    float* att = take((size_t)rows * D);
+    float* u = take((size_t)rows * cf.FF);
+    const long long sS = (long long)S * D;
+    const float scale_log2e = (1.0f / sqrtf((float)h->dh)) * 1.4426950408889634f;
+    for (int i = 0; i < 2; ++i) {
+      const a2p_denoiser::EncLayerW& e = ew.enc[i];
+      A2P_TRY(launch_ln_rope(D, cond_tokens, D, e.n1w, e.n1b, hn, hr, D, h->rope_tab, S, 0, rows, st));
+      h->launches++;
+      A2P_TRY(gemm(c, hr, D, rows, e.in_w, D, e.in_b, 2 * D, D, qkv, 3 * D));                                        // q | k from the rotated rows
+      A2P_TRY(gemm(c, hn, D, rows, e.in_w + (size_t)2 * D * D, D, e.in_b + 2 * D, D, D, qkv + 2 * D, 3 * D));       // v from the plain rows
+      AttnParams a{};
+      a.Q = qkv; a.q_ld = 3 * D; a.q_sample_stride = 3 * sS;
+      a.K.base[0] = qkv + D; a.K.stride[0] = 3 * sS; a.K.base[1] = nullptr; a.K.stride[1] = 0; a.K.rows_per_branch = Bc;
+      a.V = a.K; a.V.base[0] = qkv + 2 * D;
+      a.kv_ld = 3 * D; a.S_main = S; a.S_extra = 0;
+      a.O = att; a.o_ld = D; a.o_sample_stride = sS; a.T = S; a.H = cf.H; a.R = Bc; a.scale_log2e = scale_log2e;
+      A2P_TRY(launch_attn_simt(a, h->dh, st));
+      h->launches++;
+      A2P_TRY(gemm(c, att, D, rows, e.out_w, D, e.out_b, D, D, cond_tokens, D, EPI_RESID));
+      A2P_TRY(launch_ln_rope(D, cond_tokens, D, e.n2w, e.n2b, hn, nullptr, D, h->rope_tab, S, 0, rows, st));
+      h->launches++;
+      A2P_TRY(gemm(c, hn, D, rows, e.l1w, D, e.l1b, cf.FF, D, u, cf.FF, EPI_GELU));
+      A2P_TRY(gemm(c, u, cf.FF, rows, e.l2w, cf.FF, e.l2b, D, cf.FF, cond_tokens, D, EPI_RESID));
+    }
+  }
+  // ---- hidden = non_attn_cond_projection(mean_S tokens)   (model/diffusion.py:380-381)
+  mean_rows_kernel<<<dim3(ceil_div(D, 128), Bc), 128, 0, st>>>(cond_tokens, S, D, pooled);
+  A2P_CUDA(cudaGetLastError());
+  A2P_TRY(launch_ln_rope(D, pooled, D, ew.p0w, ew.p0b, pooled_n, nullptr, D, h->rope_tab, 1, 0, Bc, st));
+  h->launches += 2;
+  A2P_TRY(gemm(c, pooled_n, D, Bc, ew.p1w, D, ew.p1b, D, D, hid1, D, EPI_SILU));
+  A2P_TRY(gemm(c, hid1, D, Bc, ew.p3w, D, ew.p3b, D, D, cond_hidden, D));
+  if (cf.fmt == A2P_FMT_POSE) {
+    // ---- pose tokens = frame_norm_cond(frame_cond_projection(keyframes))   (model/diffusion.py:316-336; unknown keyframes
+    //      are zeroed by the caller; the null-embedding select of the uncond branch is the caller's too)
+    float* ph = take((size_t)Bc * S2 * D);
+    A2P_TRY(gemm(c, keyframes, cf.C, Bc * S2, ew.fp_w, cf.C, ew.fp_b, D, cf.C, ph, D));
+    A2P_TRY(launch_ln_rope(D, ph, D, ew.fn_w, ew.fn_b, pose_tokens, nullptr, D, h->rope_tab, 1, 0, Bc * S2, st));
+    h->launches++;
+  }
+  return 0;
 }
 
 int a2p_denoiser_set_conditioning(a2p_denoiser_t* h, int branch, int Bc, int S, int S2, const float* cond_tokens,

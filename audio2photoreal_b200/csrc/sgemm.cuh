@@ -16,7 +16,9 @@ enum Epi : int {
   EPI_ADDROW_MISH = 3,   // mish(acc + bias + rowvec[row])  (t = to_time_cond(.) + cond_hidden; FiLM input Mish(t))
   EPI_FILM_RESID = 4,    // C += (film_scale + 1) * (acc + bias) + film_shift   (transformer_modules.py:122-124)
   EPI_LRELU = 5,         // leaky_relu(acc + bias, slope)
-  EPI_LRELU_SKIPAVG = 6  // (skip + leaky_relu(acc + bias)) / 2           (model/diffusion.py:220-221)
+  EPI_LRELU_SKIPAVG = 6, // (skip + leaky_relu(acc + bias)) / 2           (model/diffusion.py:220-221)
+  EPI_SILU = 7,          // nn.SiLU (non_attn_cond_projection, model/diffusion.py:175-180)
+  EPI_RESID = 8          // C += acc + bias   (pre-LN encoder layer residuals, transformer_modules.py:73-76)
 };
 
 struct GemmParams {
@@ -133,6 +135,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(GemmParams p) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
             break;
+          case EPI_SILU:
+#pragma unroll
+            for (int j = 0; j < 4; ++j) v[j] = v[j] / (1.0f + expf(-v[j]));
+            break;
+          case EPI_RESID: {
+            const float4 x = *reinterpret_cast<const float4*>(cptr);
+            v[0] += x.x; v[1] += x.y; v[2] += x.z; v[3] += x.w;
+          } break;
           case EPI_LRELU_SKIPAVG: {
             float4 s = *reinterpret_cast<const float4*>(p.skip + (long long)row * p.ldskip + col);
             const float ss[4] = {s.x, s.y, s.z, s.w};

@@ -829,18 +829,22 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       CH_TRACE(6 + h, et == 0 && h < 10);
       const int remap_first = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_pad : 0;   // pad rows in front of the tile's first sample
       const int remap_edge = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_rps : 0x7fffffff;   // first row of the next sample (T >= 128)
+      // the accumulator chunks are read one ahead: the tcgen05.ld of chunk k + 1 is in flight while chunk k goes through the
+      // staging tile and out to global memory (its registers are free once the chunk has been staged)
+      float v[16];
+      const uint32_t acc_addr = tmem_base + lane_addr + 256 + buf * 128 + sub * 64;
+      tmem_ld16(acc_addr, v);
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {
         const int c16 = sub * 4 + k;                       // 16-column chunk of the half
         {
-          float v[16];
-          tmem_ld16(tmem_base + lane_addr + 256 + buf * 128 + c16 * 16, v);
           umma::tmem_ld_wait();
           if (k == 3) { umma::fence_before(); __syncwarp(); if (lane == 0) arrive_at_leader<CL>(&acc1_empty[buf], crank); }
           const uint32_t srow = stg_u32 + lane * 64;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
             sts128(srow + ((q ^ ((lane >> 1) & 3)) << 4), make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          if (k < 3) tmem_ld16(acc_addr + (k + 1) * 16, v);
         }
         __syncwarp();
         if (!vj) {

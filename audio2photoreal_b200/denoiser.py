@@ -15,6 +15,7 @@ signature; the computation is split the B200 way:
 from __future__ import annotations
 
 import ctypes as C
+import os
 import math
 from typing import Callable, Dict, Optional
 
@@ -300,6 +301,37 @@ class Denoiser(nn.Module):
         return x + F.linear(F.gelu(F.linear(h, sd[p + ".linear1.weight"], sd[p + ".linear1.bias"])),
                             sd[p + ".linear2.weight"], sd[p + ".linear2.bias"])
 
+    def _encode_conditioning_torch(self, feats, pred, sd):
+        """The conditioning encoders in PyTorch (A2P_COND_TORCH=1 and the parity test of the native encoders): cond_projection
+        (-> face cond_encoder), mean-pool MLP, keyframe projection -- model/diffusion.py:355-381, 316-336.  One sample at a
+        time: library GEMMs pick shape-dependent algorithms, and a row's result must not depend on how the batch is sharded."""
+        d = self.dims
+        D = d.D
+
+        def per_sample(fn, t):
+            return torch.cat([fn(t[i:i + 1]) for i in range(t.shape[0])], dim=0)
+
+        def tokens_of(f1):
+            tk = F.linear(f1, sd["cond_projection.weight"], sd["cond_projection.bias"])
+            if d.fmt == "face":
+                for i in range(2):
+                    tk = self._encoder_layer(tk, sd, f"cond_encoder.{i}")
+            return tk
+
+        def hidden_of(tokens):
+            hdn = F.layer_norm(tokens.mean(dim=-2), (D,), sd["non_attn_cond_projection.0.weight"],
+                               sd["non_attn_cond_projection.0.bias"], 1e-5)
+            hdn = F.silu(F.linear(hdn, sd["non_attn_cond_projection.1.weight"], sd["non_attn_cond_projection.1.bias"]))
+            return F.linear(hdn, sd["non_attn_cond_projection.3.weight"], sd["non_attn_cond_projection.3.bias"])
+
+        tok = per_sample(tokens_of, feats)
+        hid = per_sample(hidden_of, tok)
+        pose_c = None
+        if pred is not None:
+            ph = per_sample(lambda k1: F.linear(k1, sd["frame_cond_projection.weight"], sd["frame_cond_projection.bias"]), pred)
+            pose_c = F.layer_norm(ph, (D,), sd["frame_norm_cond.weight"], sd["frame_norm_cond.bias"], 1e-5).contiguous()
+        return tok, hid, pose_c
+
     @torch.no_grad()
     def prepare(self, y, batch_size: int, T: int, dev: torch.device) -> None:
         """Compute + upload the conditioning of BOTH branches unless `y` is unchanged since the last call."""
@@ -329,40 +361,31 @@ class Denoiser(nn.Module):
             feats = torch.zeros(batch_size, T, self.cond_feature_dim, device=dev)
         else:
             feats = self._audio_features(y, dev)
-        # One sample at a time: library GEMMs pick shape-dependent algorithms, and the result of a row must not
-        # depend on how the batch is sharded across GPUs (bit-identical 1-GPU vs W-GPU results, dist.py).
-        def per_sample(fn, t):
-            return torch.cat([fn(t[i:i + 1]) for i in range(t.shape[0])], dim=0)
-
-        def tokens_of(f1):
-            tk = F.linear(f1, sd["cond_projection.weight"], sd["cond_projection.bias"])
-            if d.fmt == "face":
-                for i in range(2):
-                    tk = self._encoder_layer(tk, sd, f"cond_encoder.{i}")
-            return tk
-
-        tok = per_sample(tokens_of, feats)
-        S = tok.shape[1]
+        S = feats.shape[1]
         if S > EMB_LEN:
             raise ValueError(f"{S} audio tokens exceed null_cond_embed's {EMB_LEN} rows (model/diffusion.py:136,378)")
-
-        def hidden_of(tokens):
-            hdn = F.layer_norm(tokens.mean(dim=-2), (D,), sd["non_attn_cond_projection.0.weight"],
-                               sd["non_attn_cond_projection.0.bias"], 1e-5)
-            hdn = F.silu(F.linear(hdn, sd["non_attn_cond_projection.1.weight"], sd["non_attn_cond_projection.1.bias"]))
-            return F.linear(hdn, sd["non_attn_cond_projection.3.weight"], sd["non_attn_cond_projection.3.bias"])
-
-        pose_c = pose_u = None
+        pred = None
         nk = 0
         if d.fmt == "pose":
-            pred = y["keyframes"]      # unknown keyframes already zeroed above (model/diffusion.py:318-320)
-            ph = per_sample(lambda k1: F.linear(k1, sd["frame_cond_projection.weight"], sd["frame_cond_projection.bias"]),
-                            pred.detach().clone().to(dev, torch.float32))
-            pose_c = F.layer_norm(ph, (D,), sd["frame_norm_cond.weight"], sd["frame_norm_cond.bias"], 1e-5).contiguous()
-            nk = pose_c.shape[1]
-            pose_u = sd["null_pose_embed"][:, :nk].contiguous()
+            pred = y["keyframes"].detach().clone().to(dev, torch.float32).contiguous()   # unknown keyframes zeroed above
+            nk = pred.shape[1]
+        if os.environ.get("A2P_COND_TORCH"):
+            tok, hid, pose_c = self._encode_conditioning_torch(feats, pred, sd)
+        else:
+            # native encoders (a2p_denoiser_encode_conditioning: exact-fp32 FFMA GEMMs / fp32 attention, batch-invariant per row)
+            feats = feats.to(dev, torch.float32).contiguous()
+            Fd = feats.shape[2]
+            tok = torch.empty(batch_size, S, D, device=dev)
+            hid = torch.empty(batch_size, D, device=dev)
+            pose_c = torch.empty(batch_size, nk, D, device=dev) if pred is not None else None
+            ews = self._workspace(lib.a2p_encode_workspace_bytes(C.byref(self._cfg), batch_size, S, Fd), dev)
+            _lib.check(lib.a2p_denoiser_encode_conditioning(
+                self._handle, batch_size, S, nk, Fd, feats.data_ptr(), pred.data_ptr() if pred is not None else None,
+                tok.data_ptr(), hid.data_ptr(), pose_c.data_ptr() if pose_c is not None else None, ews.data_ptr(), ews.numel(),
+                torch.cuda.current_stream(dev).cuda_stream))
+        pose_u = sd["null_pose_embed"][:, :nk].contiguous() if d.fmt == "pose" else None
         sets = [
-            (0, batch_size, tok.contiguous(), per_sample(hidden_of, tok).contiguous(), pose_c),
+            (0, batch_size, tok.contiguous(), hid.contiguous(), pose_c),
             (1, 1, sd["null_cond_embed"][:, :S].contiguous(), sd["null_cond_hidden"].contiguous(), pose_u),
         ]
         st = torch.cuda.current_stream(dev).cuda_stream

@@ -117,6 +117,22 @@ int a2p_denoiser_set_conditioning(a2p_denoiser_t* h, int branch, int Bc, int S, 
                                   const float* cond_hidden, const float* pose_tokens, void* kv_cache,
                                   size_t kv_bytes, void* ws, size_t ws_bytes, void* stream);
 
+/* The step-invariant conditioning ENCODERS of one batch, native (exact fp32 FFMA GEMMs / fp32 attention): what
+ * FiLMTransformer.forward computes from the frozen encoders' features before the null-embedding select
+ * (model/diffusion.py:355-381, 316-336; transformer_modules.py:69-102):
+ *   feats     [Bc, S, feat_dim]  encode_audio output (+ lip features for face): 1024 (pose) / 2038 (face) columns
+ *   keyframes [Bc, S2, C]        pose only: y["keyframes"] with the unknown keyframes already zeroed; NULL / S2 = 0 for face
+ *   cond_tokens [Bc, S, D]   <-  cond_projection (-> face: the two rotary pre-LN layers of cond_encoder)
+ *   cond_hidden [Bc, D]      <-  non_attn_cond_projection(mean over S of cond_tokens)
+ *   pose_tokens [Bc, S2, D]  <-  frame_norm_cond(frame_cond_projection(keyframes))      (pose only)
+ * The outputs are exactly the inputs of a2p_denoiser_set_conditioning(branch 0).  Needs cond_projection.*,
+ * non_attn_cond_projection.{0,1,3}.*, and frame_cond_projection.* / frame_norm_cond.* (pose) or cond_encoder.{0,1}.*
+ * (face) in the bound weight table; fails if they are missing.  A row's result does not depend on Bc. */
+size_t a2p_encode_workspace_bytes(const a2p_model_cfg* cfg, int Bc, int S, int feat_dim);
+int a2p_denoiser_encode_conditioning(a2p_denoiser_t* h, int Bc, int S, int S2, int feat_dim, const float* feats,
+                                     const float* keyframes, float* cond_tokens, float* cond_hidden,
+                                     float* pose_tokens, void* ws, size_t ws_bytes, void* stream);
+
 /* scratch needed by set_conditioning (normalised + rotated copies of the memories). */
 size_t a2p_conditioning_workspace_bytes(const a2p_model_cfg* cfg, int Bc, int S);
 

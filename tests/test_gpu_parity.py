@@ -262,3 +262,52 @@ def test_conditioning_cache_fresh_tensors_per_request():
     assert torch.equal(outs[0], outs[4])
     for i in range(4):
         assert not torch.allclose(outs[i], outs[i + 1]), i
+
+
+@pytest.mark.parametrize("name", ["pose_small", "face_small", "pose_full", "face_full"])
+def test_native_conditioning_encoders_match_torch(name):
+    """a2p_denoiser_encode_conditioning (cond_projection -> face cond_encoder, mean-pool MLP, keyframe projection;
+    model/diffusion.py:355-381, 316-336; transformer_modules.py:69-102) against the same encoders in PyTorch fp32, and
+    batch-row invariance of the native path (a row's tokens do not depend on how many rows are encoded with it)."""
+    import ctypes as C
+    from audio2photoreal_b200 import _lib
+    case = CASES[name]
+    inp = make_inputs(case)
+    model, _, _ = _build(case)
+    dev = torch.device("cuda")
+    T = inp["x"].shape[-1]
+    model._ensure_bound(dev, max(T, 1998 + 2))
+    lib, sd = _lib.load(), model._sd()
+    feats = inp["feats"].cuda().float().contiguous()
+    B, S, Fd = feats.shape
+    pred = None
+    if case.fmt == "pose":
+        pred = inp["keyframes"].clone().cuda().float().contiguous()
+    with torch.no_grad():
+        tok_t, hid_t, pose_t = model._encode_conditioning_torch(feats, pred, sd)
+
+    def native(f, p):
+        b = f.shape[0]
+        D = model.dims.D
+        nk = p.shape[1] if p is not None else 0
+        tok, hid = torch.empty(b, S, D, device=dev), torch.empty(b, D, device=dev)
+        pose = torch.empty(b, nk, D, device=dev) if p is not None else None
+        nb = lib.a2p_encode_workspace_bytes(C.byref(model._cfg), b, S, Fd)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        _lib.check(lib.a2p_denoiser_encode_conditioning(
+            model._handle, b, S, nk, Fd, f.data_ptr(), p.data_ptr() if p is not None else None, tok.data_ptr(), hid.data_ptr(),
+            pose.data_ptr() if pose is not None else None, ws.data_ptr(), nb, torch.cuda.current_stream().cuda_stream))
+        torch.cuda.synchronize()
+        return tok, hid, pose
+
+    tok, hid, pose = native(feats, pred)
+    for what, a, b in (("tokens", tok, tok_t), ("hidden", hid, hid_t), ("pose", pose, pose_t)):
+        if a is None:
+            continue
+        scale = max(1.0, b.abs().max().item())
+        err = (a.double() - b.double()).abs().max().item()
+        assert err <= 5e-5 * scale, f"{name}/{what}: max|d|={err:.3e} at scale {scale:.2f}"
+    tok1, hid1, pose1 = native(feats[:1].contiguous(), pred[:1].contiguous() if pred is not None else None)
+    assert torch.equal(tok1[0], tok[0]) and torch.equal(hid1[0], hid[0])
+    if pose is not None:
+        assert torch.equal(pose1[0], pose[0])
