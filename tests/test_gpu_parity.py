@@ -274,11 +274,11 @@ def test_native_conditioning_encoders_match_torch(name):
     case = CASES[name]
     inp = make_inputs(case)
     model, _, _ = _build(case)
-    dev = torch.device("cuda")
+    feats = inp["feats"].cuda().float().contiguous()
+    dev = feats.device
     T = inp["x"].shape[-1]
     model._ensure_bound(dev, max(T, 1998 + 2))
     lib, sd = _lib.load(), model._sd()
-    feats = inp["feats"].cuda().float().contiguous()
     B, S, Fd = feats.shape
     pred = None
     if case.fmt == "pose":
