@@ -50,6 +50,7 @@ struct ChainParams {
   __nv_bfloat16* Cp; long long cp_plane_stride, ldcp; int remap_rps, remap_pad;
   int vjob; const float* bias2; __nv_bfloat16* Vt; long long vt_plane_stride, ldvt;
   int nsplit;                // > 1: every 128-row tile is worked on by nsplit CTAs (CTA pairs in pair mode), see "N split" below
+  int eb_tma;                // E_B writes the output planes with TMA stores from a bf16 staging tile (set by the launcher)
   long long* trace;          // optional [64] clock64 timeline of CTA 0 (A2P_CHAIN_TRACE=1 in the test hook)
 };
 
@@ -118,6 +119,14 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -391,7 +400,8 @@ __global__ void __launch_bounds__(CH_THREADS, 1)
 umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmW0,
                   const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                   const __grid_constant__ CUtensorMap tmXin, const __grid_constant__ CUtensorMap tmXout,
-                  const __grid_constant__ CUtensorMap tmTab, ChainParams p) {
+                  const __grid_constant__ CUtensorMap tmTab, const __grid_constant__ CUtensorMap tmC,
+                  const __grid_constant__ CUtensorMap tmVt, ChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sSlots = smem;
@@ -445,6 +455,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
   if (warp == 0 && lane == 0) {
     umma::prefetch_tmap(&tmA0); umma::prefetch_tmap(&tmW0); umma::prefetch_tmap(&tmW1); umma::prefetch_tmap(&tmXin);
     umma::prefetch_tmap(&tmXout);
+    if (p.eb_tma) { umma::prefetch_tmap(&tmC); if (p.vjob) umma::prefetch_tmap(&tmVt); }
     if (p.rope) umma::prefetch_tmap(&tmTab);
     if (p.vjob) umma::prefetch_tmap(&tmW2);
   }
@@ -605,6 +616,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       if (jh == n_g1 && n_v > 0) { umma::mbar_wait(a2_ready, 0); umma::fence_after(); q = seqV; }
       const int buf = jh & 1;
       if (jh >= 2) { umma::mbar_wait(&acc1_empty[buf], ((jh >> 1) - 1) & 1); umma::fence_after(); }
+      CH_TRACE(44 + jh, lane == 0 && jh < 10);      // accumulator buffer free: the MMAs of local half jh start
       const uint32_t d = tmem_base + 256 + buf * 128;
 #pragma unroll 1
       for (int st8 = 0; st8 < G1S; ++st8) {
@@ -826,20 +838,60 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
       const int buf = jh & 1;
       umma::mbar_wait(&acc1_full[buf], (jh >> 1) & 1);
       umma::fence_after();
-      CH_TRACE(6 + h, et == 0 && h < 10);
+      CH_TRACE(6 + h, trow == 0 && sub == 0 && h < 10);      // acc1_full(h) seen by the draining warpgroup pair
       const int remap_first = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_pad : 0;   // pad rows in front of the tile's first sample
       const int remap_edge = p.remap_rps > 0 ? (m0 / p.remap_rps + 1) * p.remap_rps : 0x7fffffff;   // first row of the next sample (T >= 128)
-      // the accumulator chunks are read one ahead: the tcgen05.ld of chunk k + 1 is in flight while chunk k goes through the
-      // staging tile and out to global memory (its registers are free once the chunk has been staged)
+      // the accumulator chunks are read one ahead: the tcgen05.ld of chunk k + 1 is in flight while chunk k is processed
       float v[16];
       const uint32_t acc_addr = tmem_base + lane_addr + 256 + buf * 128 + sub * 64;
+      const bool tma_out = p.eb_tma && !vj;
       tmem_ld16(acc_addr, v);
 #pragma unroll 1
       for (int k = 0; k < 4; ++k) {
         const int c16 = sub * 4 + k;                       // 16-column chunk of the half
+        umma::tmem_ld_wait();
+        if (k == 3) { umma::fence_before(); __syncwarp(); if (lane == 0) arrive_at_leader<CL>(&acc1_empty[buf], crank); }
+        if (p.eb_tma) {      // the TMA stores that read this warp's staging tile last have finished reading it
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
+        }
+        if (tma_out) {
+          // ---- thread = row: bias / scale / GELU and the plane split in registers, the two bf16 planes of the [32 rows x 16
+          // columns] chunk staged row-major ([32][32 B] each) and written by ONE TMA store per plane.  The transposed path
+          // below spends 8 + 8 shared-memory wavefronts and 8 global-store instructions of 8 partial lines each per chunk and
+          // warp -- the E_B phase was bound by that LSU traffic, not by its arithmetic (profiles/r02_chain_eb_timeline.txt).
+          const int col = h * 128 + c16 * 16;
+          const float osc = (p.scale_ncols != 0 && col >= p.scale_ncols) ? 1.f : p.out_scale;
+          const uint32_t pbb = pb_u32 + (CH_PB_BIAS1 + col) * 4;
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 bb = lds128(pbb + q * 16);      // same address in every lane: broadcast
+            f2 o01 = add2(f2{v[4 * q], v[4 * q + 1]}, f2{bb.x, bb.y}), o23 = add2(f2{v[4 * q + 2], v[4 * q + 3]}, f2{bb.z, bb.w});
+            if (p.gelu) {
+              o01 = gelu_as2(o01); o23 = gelu_as2(o23);
+            } else {
+              o01 = mul2(o01, bc2(osc)); o23 = mul2(o23, bc2(osc));
+            }
+            split_act_pair(o01.x, o01.y, hi[2 * q], lo[2 * q]);
+            split_act_pair(o23.x, o23.y, hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          if (k < 3) tmem_ld16(acc_addr + (k + 1) * 16, v);
+          const uint32_t srow = stg_u32 + lane * 32;
+          sts128u(srow, hi[0], hi[1], hi[2], hi[3]);
+          sts128u(srow + 16, hi[4], hi[5], hi[6], hi[7]);
+          sts128u(srow + 1024, lo[0], lo[1], lo[2], lo[3]);
+          sts128u(srow + 1040, lo[4], lo[5], lo[6], lo[7]);
+          umma::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && col < p.N1 && m0 + wq * 32 < p.M) {
+            tma_store_3d(&tmC, stg_u32, col, m0 + wq * 32, 0);
+            tma_store_3d(&tmC, stg_u32 + 1024, col, m0 + wq * 32, 1);
+            bulk_commit();
+          }
+          continue;
+        }
         {
-          umma::tmem_ld_wait();
-          if (k == 3) { umma::fence_before(); __syncwarp(); if (lane == 0) arrive_at_leader<CL>(&acc1_empty[buf], crank); }
           const uint32_t srow = stg_u32 + lane * 64;
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -888,18 +940,37 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
           uint32_t hi[8], lo[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) split_act_pair(t[2 * e], t[2 * e + 1], hi[e], lo[e]);
-          __nv_bfloat16* dst = p.Vt + (long long)ch * p.ldvt + tok0;
+          if (p.eb_tma) {
+            // the V^T planes of the chunk ([16 channels][32 tokens] bf16 each) go back into the staging tile and leave by TMA
+            __syncwarp();                                  // every lane has read its column of the fp32 tile
+            const uint32_t srow = stg_u32 + chl * 64 + th * 32;
+            sts128u(srow, hi[0], hi[1], hi[2], hi[3]);
+            sts128u(srow + 16, hi[4], hi[5], hi[6], hi[7]);
+            sts128u(srow + 1024, lo[0], lo[1], lo[2], lo[3]);
+            sts128u(srow + 1040, lo[4], lo[5], lo[6], lo[7]);
+            umma::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && m0 + wq * 32 < p.M) {
+              tma_store_3d(&tmVt, stg_u32, m0 + wq * 32, (h - NH1) * 128 + c16 * 16, 0);
+              tma_store_3d(&tmVt, stg_u32 + 1024, m0 + wq * 32, (h - NH1) * 128 + c16 * 16, 1);
+              bulk_commit();
+            }
+          } else {
+            __nv_bfloat16* dst = p.Vt + (long long)ch * p.ldvt + tok0;
 #pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            if (tok0 + 8 * u < p.M) {   // M % 8 == 0 (checked by the launcher)
-              *reinterpret_cast<uint4*>(dst + 8 * u) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
-              *reinterpret_cast<uint4*>(dst + p.vt_plane_stride + 8 * u) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+            for (int u = 0; u < 2; ++u) {
+              if (tok0 + 8 * u < p.M) {   // M % 8 == 0 (checked by the launcher)
+                *reinterpret_cast<uint4*>(dst + 8 * u) = make_uint4(hi[4 * u], hi[4 * u + 1], hi[4 * u + 2], hi[4 * u + 3]);
+                *reinterpret_cast<uint4*>(dst + p.vt_plane_stride + 8 * u) = make_uint4(lo[4 * u], lo[4 * u + 1], lo[4 * u + 2], lo[4 * u + 3]);
+              }
             }
           }
         }
         __syncwarp();
       }
+      CH_TRACE(54 + h, trow == 0 && sub == 0 && h < 10);     // half h drained
     }
+    if (p.eb_tma && lane == 0) bulk_wait_all();     // nothing may still read this CTA's shared memory at exit
     CH_TRACE(30, et == 0);
   }
   __syncthreads();
@@ -957,7 +1028,7 @@ inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaS
   if (p.T < 128 || p.M % 8) A2P_FAIL("chain: needs T >= 128 and M %% 8 == 0 (T=%d M=%d)", p.T, p.M);
   if (p.vjob && (!o.W2 || !p.Vt)) A2P_FAIL("chain: V job needs W2 and Vt");
   if (p.rope && (!o.rope_ext || o.rope_ext_rows < p.T + 128)) A2P_FAIL("chain: RoPE needs the extended table (T + 128 rows)");
-  CUtensorMap tA0, tW0, tW1, tW2, tXin, tXout, tTab;
+  CUtensorMap tA0, tW0, tW1, tW2, tXin, tXout, tTab, tC, tVt;
   const CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_128B;
   const int cl = force_cl > 0 ? force_cl : chain_cluster_size(p.K0);
   const int n_acc = ceil_div(p.N1, 128) + (p.vjob ? 2 : 0);
@@ -977,6 +1048,17 @@ inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaS
   else tXout = tXin;
   if (p.rope) A2P_TRY(make_tmap_f32_2d(&tTab, o.rope_ext, 256, o.rope_ext_rows, 256, 32, 128));
   else tTab = tXin;
+  // E_B output planes by TMA store ([16 columns x 32 rows] boxes per plane) unless the rows are remapped (final_layer -> padded
+  // TCN layout: a 32-row box may straddle a sample boundary) or the columns do not come in whole 16-column chunks
+  static const bool eb_tma_env = !(getenv("A2P_CHAIN_EB_TMA") && atoi(getenv("A2P_CHAIN_EB_TMA")) == 0);
+  ChainParams pp = p;
+  pp.eb_tma = (eb_tma_env && p.remap_rps == 0 && p.N1 % 16 == 0 && p.ldcp % 8 == 0 && p.cp_plane_stride % 8 == 0 &&
+               reinterpret_cast<uintptr_t>(p.Cp) % 16 == 0) ? 1 : 0;
+  if (pp.eb_tma && p.vjob && (p.ldvt % 8 || p.vt_plane_stride % 8 || reinterpret_cast<uintptr_t>(p.Vt) % 16)) pp.eb_tma = 0;
+  if (pp.eb_tma) A2P_TRY(make_tmap_bf16_3d(&tC, p.Cp, p.N1, p.M, 2, p.ldcp, p.cp_plane_stride, 16, 32, CU_TENSOR_MAP_SWIZZLE_NONE));
+  else tC = tXin;
+  if (pp.eb_tma && p.vjob) A2P_TRY(make_tmap_bf16_3d(&tVt, p.Vt, p.M, 256, 2, p.ldvt, p.vt_plane_stride, 32, 16, CU_TENSOR_MAP_SWIZZLE_NONE));
+  else tVt = tXin;
   const int tiles = ceil_div(p.M, 128);
   if (cl == 2) {
     cudaLaunchConfig_t cfg{};
@@ -991,10 +1073,10 @@ inline int launch_umma_chain(const ChainOperands& o, const ChainParams& p, cudaS
       ++na;
     }
     cfg.attrs = attr; cfg.numAttrs = na;
-    A2P_CUDA(cudaLaunchKernelEx(&cfg, umma_chain_kernel<2>, tA0, tW0, tW1, tW2, tXin, tXout, tTab, p));
+    A2P_CUDA(cudaLaunchKernelEx(&cfg, umma_chain_kernel<2>, tA0, tW0, tW1, tW2, tXin, tXout, tTab, tC, tVt, pp));
   } else {
     A2P_CUDA(launch_pdl(umma_chain_kernel<1>, dim3(tiles * nsp), dim3(CH_THREADS), (size_t)CH_SMEM_BYTES, st, tA0, tW0, tW1, tW2, tXin, tXout,
-                        tTab, p));
+                        tTab, tC, tVt, pp));
   }
   return 0;
 }
