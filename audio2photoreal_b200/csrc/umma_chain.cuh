@@ -851,7 +851,7 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         const int c16 = sub * 4 + k;                       // 16-column chunk of the half
         umma::tmem_ld_wait();
         if (k == 3) { umma::fence_before(); __syncwarp(); if (lane == 0) arrive_at_leader<CL>(&acc1_empty[buf], crank); }
-        if (p.eb_tma) {      // the TMA stores that read this warp's staging tile last have finished reading it
+        if (p.eb_tma && !tma_out) {      // the TMA stores that read this warp's staging tile last have finished reading it
           if (lane == 0) bulk_wait_read<0>();
           __syncwarp();
         }
@@ -877,6 +877,9 @@ umma_chain_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
             split_act_pair(o23.x, o23.y, hi[2 * q + 1], lo[2 * q + 1]);
           }
           if (k < 3) tmem_ld16(acc_addr + (k + 1) * 16, v);
+          // the previous chunk's TMA stores have finished READING the staging tile (they had the arithmetic above to do so)
+          if (lane == 0) bulk_wait_read<0>();
+          __syncwarp();
           const uint32_t srow = stg_u32 + lane * 32;
           sts128u(srow, hi[0], hi[1], hi[2], hi[3]);
           sts128u(srow + 16, hi[4], hi[5], hi[6], hi[7]);
