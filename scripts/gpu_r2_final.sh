@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/*.ncu-rep
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/r02_pytest_gpu.log 2>&1; tail -3 gpurun_out/r02_pytest_gpu.log
 timeout 300 python __graft_entry__.py --smoke > gpurun_out/r02_smoke.log 2>&1; tail -1 gpurun_out/r02_smoke.log
-timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/r02_bench_default_line.json 2> gpurun_out/r02_bench_default_line.err; tail -c 300 gpurun_out/r02_bench_default_line.json
+timeout 900 python bench.py > gpurun_out/r02_bench_default_line.json 2> gpurun_out/r02_bench_default_line.err; tail -c 300 gpurun_out/r02_bench_default_line.json
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 1600 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-gpu-baseline --no-config3 --diffusion-steps 20 > gpurun_out/r02_ncu_launches.log 2>&1
 python scripts/summarize_launches.py gpurun_out/r02_launches_bench.csv > gpurun_out/r02_launches_bench_summary.txt; head -12 gpurun_out/r02_launches_bench_summary.txt
 cap() {  # name regex skip count extra-bench-args
