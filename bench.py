@@ -586,7 +586,7 @@ def main():
     if not a.no_config3 and not a.no_cfg:
         from audio2photoreal_b200.dist import shard_range
         lo, hi = shard_range(CONFIG3_GLOBAL_BATCH, world, rank)
-        l3, l3e, h2d3, _ = make_loops(hi - lo, CONFIG3_GLOBAL_BATCH, 100 + rank)
+        l3, l3e, h2d3, y_dev3 = make_loops(hi - lo, CONFIG3_GLOBAL_BATCH, 100 + rank)
         l3()
         k3 = max(2, min(a.steps, 5))
         ms3, out3 = timed(l3, k3)
@@ -619,6 +619,7 @@ def main():
         ncat = 9
         ms_cat = (C.c_float * ncat)()
         n_cat = (C.c_int64 * ncat)()
+        n_cat_c = n_cat                      # the ctypes array (n_cat is rebound to a list of ints below)
         x_btc = torch.randn(B, T, w["C"], device=dev)
         ts = torch.full((B,), 500, device=dev, dtype=torch.int64)
         ws = model._workspace(lib.a2p_workspace_bytes(C.byref(model._cfg), B, T), dev)
@@ -690,6 +691,41 @@ def main():
                                      "timed alone; in the loop the forwards overlap" if two_branch else "both CFG branches (2B rows) per launch"),
                     "note": ("algorithmic FLOPs (one product per MAC) over measured time; the split-bf16 arm spends %d tensor-core "
                              "products per MAC for fp32-level parity" % {0: 0, 1: 1, 2: 3, 3: 6}[SPLIT_TERMS])}
+        if config3 is not None and SPLIT_TERMS == 2:
+            # the same per-launch view at the launch shapes of configs[2] (the rows of this rank's share of the global batch 32)
+            try:
+                B3 = hi - lo
+                model._cond_sig = None
+                model.prepare(dict(y_dev3), B3, T, dev)
+                x3 = torch.randn(B3, T, w["C"], device=dev)
+                ts3 = torch.full((B3,), 500, device=dev, dtype=torch.int64)
+                ws3 = model._workspace(lib.a2p_workspace_bytes(C.byref(model._cfg), B3, T), dev)
+                g3 = int(lib.a2p_loop_row_groups(model._handle, B3, T))
+                units3 = [(3, 0, B3)] if g3 == 0 else [(mk, B3 * g // g3, B3 * (g + 1) // g3 - B3 * g // g3) for g in range(g3) for mk in (1, 2)]
+                acc3, cnt3 = np.zeros(ncat), np.zeros(ncat, dtype=np.int64)
+                for i in range(4):
+                    for mk, b0, bs in units3:
+                        _lib.check(lib.a2p_profile_forward_rows(model._handle, B3, b0, bs, T, x3[b0:].data_ptr(), ts3[b0:].data_ptr(), mk,
+                                                                ws3.data_ptr(), ws3.numel(), torch.cuda.current_stream().cuda_stream,
+                                                                ms_cat, n_cat_c, ncat))
+                        if i:
+                            acc3 += np.array(list(ms_cat))
+                        if i == 1:
+                            cnt3 += np.array(list(n_cat_c), dtype=np.int64)
+                acc3 /= 3
+                R3 = 2 * B3
+                alg3 = {4: 4 * T * (S + 2) * D * R3 * L / max(1, cnt3[4]), 3: 4 * T * T * D * R3 * L / max(1, cnt3[3]),
+                        2: 8 * T * D * D * R3 * L / max(1, cnt3[2]), 6: (2 * T * D * D + 4 * T * D * 1024 + 6 * T * D * D) * R3 * L / max(1, cnt3[6])}
+                per = {}
+                for k_ in (4, 3, 6, 2):
+                    msl = acc3[k_] / max(1, cnt3[k_])
+                    tf = alg3[k_] / (msl * 1e-3) / 1e12 if msl > 0 else 0.0
+                    per[names[k_]] = {"ms_per_launch": round(float(msl), 5), "achieved_tflops": round(float(tf), 2), "frac": round(float(tf / peak_tf), 4),
+                                      "launches_per_forward": int(cnt3[k_])}
+                config3["roofline_per_launch"] = {"rows_per_launch": units3[0][2], "concurrent_forwards": len(units3), "peak": peak_tf, "unit": "TFLOP/s",
+                                                  "kernels": per, "note": "algorithmic FLOPs per launch / CUDA-event time of the launch timed alone, as in `roofline`"}
+            except Exception as e:   # diagnostics only: never lose the contract line over it
+                config3["roofline_per_launch"] = {"error": str(e)[:200]}
         gpu_base = None
         if not a.no_gpu_baseline and world == 1 and not face and not a.no_cfg:
             gpu_base = {"configs[1]": gpu_baseline(B)}
