@@ -734,7 +734,7 @@ def main():
                 gb = gpu_base["configs[2]"]
                 if gb and gb.get("value"):
                     config3["vs_gpu_baseline"] = config3["value"] / gb["value"]
-        if not a.no_cpu_baseline:
+        if not a.no_cpu_baseline and world == 1:      # reported on rank 0 at N = 1 only (the contract); the reference arm covers N > 1
             cpu_base = cpu_baseline(w["fmt"])
         f_fwd = flops_per_sample_forward(T=T, S=S + 2, S2=20, D=model.dims.D, L=L, FF=1024, C=w["C"], fmt=w["fmt"])
         if config3 is not None:
