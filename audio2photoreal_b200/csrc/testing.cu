@@ -155,6 +155,7 @@ void a2p_test_attn2_set_persist(int on) { attn2_persist_override() = on < 0 ? -1
 
 void a2p_test_chain_set_mode(int cl) { chain_mode_override() = (cl == 1 || cl == 2) ? cl : 0; }
 void a2p_test_chain_set_nsplit(int n) { chain_nsplit_override() = n > 0 ? n : 0; }
+int a2p_test_chain_nsplit_policy(int tiles, int n_acc, int concurrent, int K0) { return chain_nsplit_for(tiles, n_acc, concurrent, K0); }
 
 size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T) {
   return ((size_t)2 * align_up((size_t)M, 128) * K0 + (size_t)2 * 256 * K0 + (size_t)2 * N1 * 256 + (size_t)2 * 256 * 256) * 2 +

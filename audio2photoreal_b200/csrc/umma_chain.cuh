@@ -1016,6 +1016,31 @@ inline int chain_cluster_size(int K0) {
   return v == 1 ? 2 : 1;
 }
 
+// N split policy of the chain launches (used by engine.cu forward_core): a launch of `tiles` 128-row tiles whose GEMM1 / V job has n_acc 128-column
+// accumulator halves is cut into s parts per tile when the step's `concurrent` forwards together leave SMs idle.  The parts
+// repeat GEMM0 + E_A, so the split pays where that prefix is short against the GEMM1 / E_B tail: s = the largest divisor of
+// n_acc with n_acc / s >= 2 halves per part and tiles * s * concurrent <= budget CTAs, budget = 160 (the machine) for launches
+// with K0 <= 256 (the FFN1 + GELU launch: 45 -> 33 -> 27 us at s = 1 / 2 / 4) and 80 for the K0 = 1024 launches (FFN2 -> LN ->
+// Q|K|V: 57 -> 49 -> 42 us at s = 1 / 2 / 3, but their redundant prefix is 60 % of the launch).  Measured on the loop
+// (profiles/r02_chain_nsplit_pdl.txt): B = 4 + 7 %, B = 8 + 1..3 %, B >= 16 never splits.
+// A2P_CHAIN_NSPLIT=0 off, 1 auto (default), n >= 2 force (capped by n_acc); A2P_CHAIN_SPLIT_BUDGET (CTAs, default 160),
+// A2P_CHAIN_SPLIT_MINH (halves per part, default 2).
+inline int chain_nsplit_for(int tiles, int n_acc, int concurrent, int K0) {
+  static int mode = -1, budget = 160, minh = 2;
+  if (mode < 0) {
+    const char* e = getenv("A2P_CHAIN_NSPLIT"); mode = e ? atoi(e) : 1; if (mode < 0) mode = 0;
+    if ((e = getenv("A2P_CHAIN_SPLIT_BUDGET"))) budget = atoi(e);
+    if ((e = getenv("A2P_CHAIN_SPLIT_MINH"))) minh = atoi(e) > 0 ? atoi(e) : 1;
+  }
+  if (mode == 0 || n_acc < 2) return 1;
+  if (mode >= 2) return mode < n_acc ? mode : n_acc;
+  const long long cap = K0 <= 256 ? budget : budget / 2;
+  int best = 1;
+  for (int s_ = 2; s_ <= 4 && s_ <= n_acc; ++s_)
+    if (n_acc % s_ == 0 && n_acc / s_ >= minh && (long long)tiles * s_ * (concurrent > 0 ? concurrent : 1) <= cap) best = s_;
+  return best;
+}
+
 struct ChainOperands {
   const __nv_bfloat16* A0; long long a0_rows, a0_ld, a0_plane_stride;   // [2][a0_rows][a0_ld], K0 valid columns
   const __nv_bfloat16* W0; long long w0_plane_stride;                   // [2][256][K0]

@@ -41,7 +41,8 @@ int a2p_test_simt_attention(int R, int T, int D, int dh, int S, int n_extra, con
 size_t a2p_test_chain_scratch_bytes(int M, int K0, int N1, int T);
 /* 1: one CTA per 128-row tile; 2: CTA pairs (cta_group::2 MMAs, half of every weight tile per CTA); 0: the library default */
 void a2p_test_chain_set_mode(int cl);
-void a2p_test_chain_set_nsplit(int n);   /* > 0: every tile is worked on by n CTAs (N split of GEMM1 / the V job); 0 = off */
+void a2p_test_chain_set_nsplit(int n);
+int a2p_test_chain_nsplit_policy(int tiles, int n_acc, int concurrent, int K0);   /* host logic only: parts per tile the engine would choose */   /* > 0: every tile is worked on by n CTAs (N split of GEMM1 / the V job); 0 = off */
 int a2p_test_chain(int M, int T, int K0, int N1, int film_mode, int ln_mode, int rope, int gelu, int vjob, float out_scale,
                    int scale_ncols, const float* A0, const float* W0, const float* bias0, const float* film, float* x,
                    const float* ln_w, const float* ln_b, const float* rope_freqs, const float* W1, const float* bias1,

@@ -116,3 +116,25 @@ def test_workspace_query_covers_every_cut_of_a_step():
         assert f >= 2 * one_region_floor
     assert lib.a2p_workspace_bytes(C.byref(mk(2)), 0, T) == 0 and lib.a2p_workspace_bytes(C.byref(mk(2, D=300)), 8, T) == 0
     assert lib.a2p_loop_row_groups(None, 8, T) == 1       # null handle: defined answer, no crash
+
+
+def test_chain_n_split_policy():
+    """Host logic of the chain launches' N split (umma_chain.cuh chain_nsplit_for; measured in profiles/r02_chain_nsplit_pdl.txt):
+    parts per tile = the largest divisor of the accumulator halves with >= 2 halves per part whose CTAs (tiles x parts x
+    concurrent forwards) fit the budget -- 160 CTAs for the short-prefix launches (K0 <= 256), 80 for the K0 = 1024 ones."""
+    import ctypes as C
+    tl = _lib.load_testing()
+    f = tl.a2p_test_chain_nsplit_policy
+    f.argtypes = [C.c_int] * 4
+    f.restype = C.c_int
+    tiles = lambda rows: (rows * 600 + 127) // 128
+    # B = 8: four concurrent forwards of 4 rows (19 tiles): FFN1 (8 halves, K0 = 256) in 2 parts, FFN2 -> Q|K|V (6 halves, K0 = 1024) whole
+    assert f(tiles(4), 8, 4, 256) == 2 and f(tiles(4), 6, 4, 1024) == 1
+    # a Q-only launch (2 halves) never splits: one half per part would repeat the whole prefix for half of a short tail
+    assert f(tiles(4), 2, 4, 256) == 1
+    # B = 4 (the per-GPU share of the strong-scaling job at 8 GPUs): four forwards of 2 rows (10 tiles)
+    assert f(tiles(2), 8, 4, 256) == 4 and f(tiles(2), 6, 4, 1024) == 2
+    # B = 32: two forwards of 32 rows fill the machine on their own
+    assert f(tiles(32), 8, 2, 256) == 1 and f(tiles(32), 6, 2, 1024) == 1
+    # a single small forward (a2p_denoiser_forward on one sample): split as far as the halves allow
+    assert f(tiles(1), 8, 1, 256) == 4 and f(tiles(1), 6, 1, 1024) == 3 and f(tiles(1), 1, 1, 1024) == 1
